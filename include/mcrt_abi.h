@@ -1,0 +1,231 @@
+/*
+ * mcrt_abi.h — C ABI of the B200-native path-tracing integrator.
+ *
+ * Drop-in boundary for the ray/BVH/BSDF hot path of linusmossberg/monte-carlo-ray-tracer.
+ * The reference has no FFI; the interface this replaces is the C++ virtual
+ *     glm::dvec3 Integrator::sampleRay(Ray)            (source/integrator/integrator.hpp:20)
+ * and its only caller, the per-pixel loop in
+ *     Camera::samplePixel / Camera::sampleImage        (source/camera/camera.cpp:66-145).
+ * Because one scalar ray per virtual call cannot feed a GPU, the batch boundary sits at
+ * the body of Camera::sampleImage ("render these rows of this camera"), plus batched
+ * sampleRay / Scene::intersect entry points with the reference's per-call semantics.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer is a HOST pointer unless the name ends
+ *     in _dev; the caller owns host buffers, the context owns device memory.
+ *   - return 0 on success, a negative mcrt_status on failure; mcrt_last_error() gives text.
+ *   - one context per GPU, driven from one host thread at a time.
+ *   - all scene arrays are the *built* state of the reference's Scene/BVH/Material objects
+ *     in float64 (the reference computes in double), flattened by the exporter
+ *     (monte-carlo-ray-tracer_b200/host/exporter.cpp). Layouts for the device (FP64 parity
+ *     arrays, FP32 wide-node arrays) are derived inside mcrt_scene_upload.
+ */
+#ifndef MCRT_ABI_H
+#define MCRT_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCRT_ABI_VERSION 1
+
+typedef enum mcrt_status {
+    MCRT_OK = 0,
+    MCRT_ERR_INVALID = -1,   /* bad argument / inconsistent scene description        */
+    MCRT_ERR_CUDA = -2,      /* CUDA runtime error (text in mcrt_last_error)          */
+    MCRT_ERR_NO_SCENE = -3,  /* render/trace called before mcrt_scene_upload          */
+    MCRT_ERR_UNSUPPORTED = -4, /* feature outside the hot path (e.g. non-box film)     */
+    MCRT_ERR_NO_PHOTONS = -5 /* photon-mapped render without mcrt_photon_upload       */
+} mcrt_status;
+
+/* Primitive type tags: Surface::{Triangle,Sphere,Quadric} (source/surface/surface.hpp:54-116). */
+enum { MCRT_PRIM_TRIANGLE = 0, MCRT_PRIM_SPHERE = 1, MCRT_PRIM_QUADRIC = 2 };
+
+/* Integrator kinds: PathTracer / PhotonMapper (source/camera/camera.cpp:22-29). */
+enum { MCRT_INTEGRATOR_PATH = 0, MCRT_INTEGRATOR_PHOTON = 1 };
+
+/* Arithmetic of the device path.
+ *   MCRT_PRECISION_F64: parity mode — double, operation order of the reference, no FMA
+ *                       contraction, reference's best-first traversal order.
+ *   MCRT_PRECISION_F32: fast mode — float, wide-node stack traversal, scale-aware offsets. */
+enum { MCRT_PRECISION_F64 = 0, MCRT_PRECISION_F32 = 1 };
+
+/* Material record: the built state of class Material (source/material/material.hpp:37-54)
+ * including the derived flags/constants of Material::computeProperties (material.cpp:97-111). */
+typedef struct mcrt_material {
+    double reflectance[3];
+    double specular_reflectance[3];
+    double transmittance[3];
+    double emittance[3];          /* radiosity after Scene::generateEmissives (scene.cpp:202) */
+    double roughness, specular_roughness, ior, transparency;
+    double complex_ior_real[3], complex_ior_imag[3];
+    double A, B;                  /* Oren–Nayar constants (material.cpp:106-108)              */
+    double a[2];                  /* GGX alpha (material.cpp:110)                             */
+    uint32_t has_complex_ior, perfect_mirror;
+    uint32_t rough, rough_specular, opaque, emissive, dirac_delta;
+    uint32_t _pad;
+} mcrt_material;
+
+/* Flattened Scene + BVH (source/scene/scene.hpp, source/bvh/bvh.hpp:68-108). */
+typedef struct mcrt_scene_desc {
+    uint32_t abi_version;             /* MCRT_ABI_VERSION */
+    /* BVH::linear_tree in depth-first order; n_nodes == 0 means "no bvh object" and the
+     * linear-scan branch of Scene::intersect (scene.cpp:159-173) is taken. */
+    uint32_t n_nodes;
+    const double* node_bounds;        /* [n_nodes][6]  min.xyz, max.xyz                       */
+    const uint32_t* node_first_prim;  /* [n_nodes]     LinearNode::start_surface              */
+    const uint32_t* node_prim_count;  /* [n_nodes]     LinearNode::num_surfaces (0 = inner)   */
+    const uint32_t* node_next_sibling;/* [n_nodes]     0 = none                               */
+    /* BVH::ordered_surfaces (or Scene::surfaces without a BVH). */
+    uint32_t n_prims;
+    const uint8_t* prim_type;         /* [n_prims] MCRT_PRIM_*                                */
+    const uint32_t* prim_index;       /* [n_prims] index into the per-type arrays             */
+    const uint32_t* prim_material;    /* [n_prims] index into materials                       */
+    const double* prim_area;          /* [n_prims] Surface::Base::area_                       */
+    /* triangles (source/surface/surface.hpp:92-96) */
+    uint32_t n_tris;
+    const double* tri_v0;             /* [n_tris][3] */
+    const double* tri_v1;
+    const double* tri_v2;
+    const double* tri_e1;             /* stored, not recomputed: keeps the reference's rounding */
+    const double* tri_e2;
+    const double* tri_normal;         /* face normal_ */
+    const int32_t* tri_vn_index;      /* [n_tris] index into vertex_normals or -1             */
+    uint32_t n_vertex_normals;
+    const double* vertex_normals;     /* [n_vertex_normals][9]  n0,n1,n2                      */
+    /* spheres (surface.hpp:68-69) */
+    uint32_t n_spheres;
+    const double* sphere_origin_radius; /* [n_spheres][4] */
+    /* quadrics (surface.hpp:114-115, clip box = Base::BB_) */
+    uint32_t n_quadrics;
+    const double* quadric_Q;          /* [n_quadrics][16] column-major dmat4                  */
+    const double* quadric_G;          /* [n_quadrics][12] column-major dmat4x3                */
+    const double* quadric_bounds;     /* [n_quadrics][6]                                      */
+    /* materials: one entry per distinct Material object */
+    uint32_t n_materials;
+    const mcrt_material* materials;
+    /* Scene::emissives / cumulative_emissives_importance (scene.cpp:178-209) */
+    uint32_t n_lights;
+    const uint32_t* light_prim;       /* [n_lights] ordered-primitive index of each emissive  */
+    const double* light_cdf;          /* [n_lights]                                           */
+    double scene_ior;                 /* Scene::ior */
+} mcrt_scene_desc;
+
+/* Camera state after Camera::Camera (source/camera/camera.cpp:20-64). */
+typedef struct mcrt_camera {
+    double eye[3], forward[3], left[3], up[3];
+    double focal_length, sensor_width, aperture_radius, focus_distance;
+    uint32_t width, height;
+    uint32_t thin_lens;
+    uint32_t _pad;
+} mcrt_camera;
+
+/* Ray as the reference's Ray(start, direction, medium_ior) (source/ray/ray.cpp:13-14). */
+typedef struct mcrt_ray {
+    double origin[3];
+    double direction[3];
+} mcrt_ray;
+
+/* Result of Scene::intersect (source/ray/intersection.hpp:9-23). prim == 0xFFFFFFFF: miss. */
+typedef struct mcrt_hit {
+    double t, u, v;
+    uint32_t prim;
+    uint32_t interpolate;
+} mcrt_hit;
+
+/* LinearOctree<Photon> (source/octree/linear-octree.hpp:19-29, photon.hpp:35-37). */
+typedef struct mcrt_photon_map_desc {
+    uint32_t n_octants;
+    const double* octant_bounds;        /* [n_octants][6]                                     */
+    const uint64_t* octant_start;       /* start_data                                         */
+    const uint64_t* octant_count;       /* contained_data                                     */
+    const uint32_t* octant_next_sibling;/* 0xFFFFFFFF = none                                  */
+    const uint8_t* octant_leaf;
+    uint64_t n_photons;
+    const float* photons;               /* [n_photons][8] flux.xyz, pos.xyz, phi, theta       */
+} mcrt_photon_map_desc;
+
+typedef struct mcrt_stats {
+    uint64_t paths;            /* camera paths started                                        */
+    uint64_t extension_rays;   /* closest-hit queries for path extension (incl. primary)      */
+    uint64_t shadow_rays;      /* closest-hit queries for next-event estimation               */
+    uint64_t box_tests;        /* AABB slab tests executed by the traversal kernels           */
+    uint64_t prim_tests;       /* primitive intersection tests executed                       */
+    uint64_t knn_queries;      /* photon-map k-NN queries                                     */
+    uint64_t wavefront_iterations;
+    uint64_t kernel_launches;
+    uint64_t ior_stack_overflows;
+    uint32_t max_depth;
+    uint32_t _pad;
+    double gpu_ms_total;       /* CUDA-event time of the render, first launch → last          */
+    double gpu_ms_generate, gpu_ms_extend, gpu_ms_shade, gpu_ms_shadow, gpu_ms_knn;
+} mcrt_stats;
+
+typedef struct mcrt_ctx mcrt_ctx;
+
+int mcrt_abi_version(void);
+
+/* Create a context on CUDA device `device`. */
+int mcrt_init(int device, mcrt_ctx** out_ctx);
+void mcrt_destroy(mcrt_ctx* ctx);
+const char* mcrt_last_error(const mcrt_ctx* ctx);
+
+/* Replaces the Scene held by Integrator (integrator.hpp:25): copies the description to the
+ * device and derives both device layouts. Returns bytes copied host→device in *h2d_bytes. */
+int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d_bytes);
+
+/* Replaces PhotonMapper's caustic_map/global_map members (photon-mapper.hpp:27-28). */
+int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map,
+                       const mcrt_photon_map_desc* global_map, uint32_t k_nearest,
+                       uint32_t direct_visualization, uint64_t* h2d_bytes);
+
+/* Replaces Camera::sampleImage (camera.cpp:101-145) for rows [y0, y1) with the default box
+ * film (film.cpp:13-17): out_rgb[(y-y0)*W+x][3] = mean over sqrtspp² samples of
+ * Integrator::sampleRay, clamped at 0 (film.cpp:112). Sample s of pixel p uses
+ * Sampler::initiate(p) / setIndex(s) with `global_seed` (sampler.hpp:30-44,58).
+ * out_rgb is a HOST buffer of (y1-y0)*W*3 doubles. */
+int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1,
+                     uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
+                     int precision, double* out_rgb, mcrt_stats* stats);
+
+/* Same, but the framebuffer stays resident in HBM (device pointer, doubles); used by the
+ * multi-GPU all-gather and by the HBM-resident throughput measurement. */
+int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1,
+                         uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
+                         int precision, double* out_rgb_dev, mcrt_stats* stats);
+
+/* Batched Scene::intersect (scene.cpp:151-176): closest hit per ray. `medium_ior` is not
+ * needed by the query. Host buffers. */
+int mcrt_trace_closest(mcrt_ctx* ctx, const mcrt_ray* rays, size_t n, int precision,
+                       mcrt_hit* hits, mcrt_stats* stats);
+
+/* Batched Integrator::sampleRay (integrator.hpp:20): ray i is traced as sample `sample[i]`
+ * of pixel `pixel[i]` (the sampler state the reference keeps thread_local), medium = scene
+ * ior; out_rgb[i][3] receives the radiance estimate. Host buffers. */
+int mcrt_sample_rays(mcrt_ctx* ctx, const mcrt_ray* rays, const uint32_t* pixel,
+                     const uint32_t* sample, size_t n, uint32_t global_seed,
+                     int integrator_kind, int precision, double* out_rgb, mcrt_stats* stats);
+
+/* Test hook for the Owen-scrambled Sobol sampler (sampler.hpp:13-91): for each i, after
+ * initiate(pixel[i]), setIndex(sample[i]) and `n_shuffles` calls of shuffle(), writes the
+ * seven dimensions get<0,7>() as raw uint32 (before the 2^-32 scaling). Host buffers. */
+int mcrt_sampler_stream(mcrt_ctx* ctx, const uint32_t* pixel, const uint32_t* sample, size_t n,
+                        uint32_t n_shuffles, uint32_t global_seed, uint32_t* out_u32x7);
+
+/* Batched LinearOctree<Photon>::knnSearch (linear-octree.cpp:24-117) on the uploaded map
+ * (which: 0 caustic, 1 global). out_index[i][k] photon indices (ordered_data order, unsorted,
+ * 0xFFFFFFFF padded), out_dist2[i][k]; out_count[i] results found. Host buffers. */
+int mcrt_knn_search(mcrt_ctx* ctx, int which, const double* points_xyz, size_t n,
+                    uint32_t* out_index, double* out_dist2, uint32_t* out_count,
+                    mcrt_stats* stats);
+
+/* Tunables (pool size etc.); unknown keys return MCRT_ERR_INVALID. */
+int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCRT_ABI_H */

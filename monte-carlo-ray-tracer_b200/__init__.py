@@ -1,0 +1,427 @@
+"""B200-native path-tracing integrator for the ray/BVH/BSDF hot path of
+linusmossberg/monte-carlo-ray-tracer — Python host mirror over the C ABI (include/mcrt_abi.h).
+
+The names follow the reference's classes for this path:
+    Scene            flattened Scene + BVH          (source/scene/scene.hpp, source/bvh/bvh.hpp)
+    Camera           camera state + sampleImage     (source/camera/camera.cpp:20-145)
+    PathTracer       Integrator::sampleRay, batched (source/integrator/path-tracer/path-tracer.cpp)
+    PhotonMapper     same with photon maps          (source/integrator/photon-mapper/photon-mapper.cpp)
+Everything that computes runs in libmcrt_b200.so on the GPU; this module only marshals buffers.
+There is no CPU fallback: importing works anywhere (so that symbols can be checked), but any compute
+call without the built library or without a CUDA device raises."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcrt_b200.so")
+
+INTEGRATOR_PATH, INTEGRATOR_PHOTON = 0, 1
+PRECISION_F64, PRECISION_F32 = 0, 1
+PRIM_TRIANGLE, PRIM_SPHERE, PRIM_QUADRIC = 0, 1, 2
+NO_PRIM = 0xFFFFFFFF
+
+ABI_SYMBOLS = [
+    "mcrt_abi_version", "mcrt_init", "mcrt_destroy", "mcrt_last_error", "mcrt_scene_upload",
+    "mcrt_photon_upload", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_trace_closest",
+    "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option",
+]
+
+
+class McrtError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------------------------ ctypes structs
+class MaterialRec(C.Structure):
+    _fields_ = [("reflectance", C.c_double * 3), ("specular_reflectance", C.c_double * 3),
+                ("transmittance", C.c_double * 3), ("emittance", C.c_double * 3),
+                ("roughness", C.c_double), ("specular_roughness", C.c_double), ("ior", C.c_double),
+                ("transparency", C.c_double), ("complex_ior_real", C.c_double * 3),
+                ("complex_ior_imag", C.c_double * 3), ("A", C.c_double), ("B", C.c_double),
+                ("a", C.c_double * 2), ("has_complex_ior", C.c_uint32), ("perfect_mirror", C.c_uint32),
+                ("rough", C.c_uint32), ("rough_specular", C.c_uint32), ("opaque", C.c_uint32),
+                ("emissive", C.c_uint32), ("dirac_delta", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+MATERIAL_DTYPE = np.dtype([
+    ("reflectance", "<f8", 3), ("specular_reflectance", "<f8", 3), ("transmittance", "<f8", 3),
+    ("emittance", "<f8", 3), ("roughness", "<f8"), ("specular_roughness", "<f8"), ("ior", "<f8"),
+    ("transparency", "<f8"), ("complex_ior_real", "<f8", 3), ("complex_ior_imag", "<f8", 3),
+    ("A", "<f8"), ("B", "<f8"), ("a", "<f8", 2), ("has_complex_ior", "<u4"), ("perfect_mirror", "<u4"),
+    ("rough", "<u4"), ("rough_specular", "<u4"), ("opaque", "<u4"), ("emissive", "<u4"),
+    ("dirac_delta", "<u4"), ("_pad", "<u4")])
+assert MATERIAL_DTYPE.itemsize == C.sizeof(MaterialRec)
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("n_nodes", C.c_uint32),
+                ("node_bounds", C.c_void_p), ("node_first_prim", C.c_void_p),
+                ("node_prim_count", C.c_void_p), ("node_next_sibling", C.c_void_p),
+                ("n_prims", C.c_uint32),
+                ("prim_type", C.c_void_p), ("prim_index", C.c_void_p), ("prim_material", C.c_void_p),
+                ("prim_area", C.c_void_p),
+                ("n_tris", C.c_uint32),
+                ("tri_v0", C.c_void_p), ("tri_v1", C.c_void_p), ("tri_v2", C.c_void_p),
+                ("tri_e1", C.c_void_p), ("tri_e2", C.c_void_p), ("tri_normal", C.c_void_p),
+                ("tri_vn_index", C.c_void_p),
+                ("n_vertex_normals", C.c_uint32), ("vertex_normals", C.c_void_p),
+                ("n_spheres", C.c_uint32), ("sphere_origin_radius", C.c_void_p),
+                ("n_quadrics", C.c_uint32),
+                ("quadric_Q", C.c_void_p), ("quadric_G", C.c_void_p), ("quadric_bounds", C.c_void_p),
+                ("n_materials", C.c_uint32), ("materials", C.c_void_p),
+                ("n_lights", C.c_uint32), ("light_prim", C.c_void_p), ("light_cdf", C.c_void_p),
+                ("scene_ior", C.c_double)]
+
+
+class CameraRec(C.Structure):
+    _fields_ = [("eye", C.c_double * 3), ("forward", C.c_double * 3), ("left", C.c_double * 3),
+                ("up", C.c_double * 3), ("focal_length", C.c_double), ("sensor_width", C.c_double),
+                ("aperture_radius", C.c_double), ("focus_distance", C.c_double),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("thin_lens", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class HitRec(C.Structure):
+    _fields_ = [("t", C.c_double), ("u", C.c_double), ("v", C.c_double), ("prim", C.c_uint32),
+                ("interpolate", C.c_uint32)]
+
+
+HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("interpolate", "<u4")])
+
+
+class PhotonMapDesc(C.Structure):
+    _fields_ = [("n_octants", C.c_uint32), ("octant_bounds", C.c_void_p), ("octant_start", C.c_void_p),
+                ("octant_count", C.c_void_p), ("octant_next_sibling", C.c_void_p), ("octant_leaf", C.c_void_p),
+                ("n_photons", C.c_uint64), ("photons", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("box_tests", C.c_uint64), ("prim_tests", C.c_uint64), ("knn_queries", C.c_uint64),
+                ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ior_stack_overflows", C.c_uint64), ("max_depth", C.c_uint32), ("_pad", C.c_uint32),
+                ("gpu_ms_total", C.c_double), ("gpu_ms_generate", C.c_double), ("gpu_ms_extend", C.c_double),
+                ("gpu_ms_shade", C.c_double), ("gpu_ms_shadow", C.c_double), ("gpu_ms_knn", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("_")}
+
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library. Raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McrtError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.mcrt_abi_version.restype = C.c_int
+        L.mcrt_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.mcrt_destroy.argtypes = [C.c_void_p]
+        L.mcrt_destroy.restype = None
+        L.mcrt_last_error.argtypes = [C.c_void_p]
+        L.mcrt_last_error.restype = C.c_char_p
+        L.mcrt_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_uint64)]
+        L.mcrt_photon_upload.argtypes = [C.c_void_p, C.POINTER(PhotonMapDesc), C.POINTER(PhotonMapDesc),
+                                         C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        render_args = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                       C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_render_rows.argtypes = render_args
+        L.mcrt_render_rows_dev.argtypes = render_args
+        L.mcrt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                       C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_sampler_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.mcrt_knn_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        if L.mcrt_abi_version() != 1:
+            raise McrtError("libmcrt_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+# ------------------------------------------------------------------------------------ scene packs
+_PACK_DTYPES = {0: np.uint8, 1: np.uint32, 2: np.int32, 3: np.uint64, 4: np.float32, 5: np.float64}
+
+
+def read_pack(path):
+    """Reads a scene pack written by host/exporter.cpp (PackWriter) → dict of numpy arrays."""
+    with open(path, "rb") as f:
+        blob = f.read()
+    if blob[:8] != b"MCRTPK01":
+        raise McrtError(f"{path}: not a scene pack")
+    n, = struct.unpack_from("<I", blob, 8)
+    out = {}
+    for i in range(n):
+        name, dtype, elem_size, count, offset = struct.unpack_from("<32sIIQQ", blob, 16 + 56 * i)
+        name = name.split(b"\0")[0].decode()
+        if dtype == 6:
+            if name != "materials" or elem_size != MATERIAL_DTYPE.itemsize:
+                raise McrtError(f"{path}: unexpected struct entry {name}")
+            arr = np.frombuffer(blob, dtype=MATERIAL_DTYPE, count=count, offset=offset)
+        else:
+            arr = np.frombuffer(blob, dtype=_PACK_DTYPES[dtype], count=count, offset=offset)
+        out[name] = arr.copy()
+    return out
+
+
+class Scene:
+    """Flattened reference Scene (surfaces, materials, emissives, BVH) as float64 arrays."""
+
+    _ARRAYS = ["node_bounds", "node_first_prim", "node_prim_count", "node_next_sibling", "prim_type",
+               "prim_index", "prim_material", "prim_area", "tri_v0", "tri_v1", "tri_v2", "tri_e1", "tri_e2",
+               "tri_normal", "tri_vn_index", "vertex_normals", "sphere_origin_radius", "quadric_Q",
+               "quadric_G", "quadric_bounds", "materials", "light_prim", "light_cdf"]
+
+    def __init__(self, arrays):
+        self.a = {k: np.ascontiguousarray(arrays[k]) for k in self._ARRAYS}
+        self.ior = float(np.asarray(arrays["scene_ior"]).reshape(-1)[0])
+        self.extra = {k: v for k, v in arrays.items() if k not in self._ARRAYS}
+
+    @classmethod
+    def from_pack(cls, path):
+        return cls(read_pack(path))
+
+    @property
+    def n_prims(self):
+        return int(self.a["prim_type"].size)
+
+    @property
+    def n_nodes(self):
+        return int(self.a["node_first_prim"].size)
+
+    @property
+    def n_lights(self):
+        return int(self.a["light_prim"].size)
+
+    def desc(self):
+        a = self.a
+        d = SceneDesc()
+        d.abi_version = 1
+        d.n_nodes = a["node_first_prim"].size
+        d.n_prims = a["prim_type"].size
+        d.n_tris = a["tri_vn_index"].size
+        d.n_vertex_normals = a["vertex_normals"].size // 9
+        d.n_spheres = a["sphere_origin_radius"].size // 4
+        d.n_quadrics = a["quadric_bounds"].size // 6
+        d.n_materials = a["materials"].size
+        d.n_lights = a["light_prim"].size
+        for k in self._ARRAYS:
+            setattr(d, k, _ptr(a[k]))
+        d.scene_ior = self.ior
+        return d
+
+    def cameras(self):
+        """Cameras stored in the pack (the exporter writes the one the scene was opened with)."""
+        cams = []
+        if "camera_f64" in self.extra:
+            cams.append(Camera.from_pack_arrays(self.extra["camera_f64"], self.extra["camera_u32"]))
+        return cams
+
+    def photon_maps(self):
+        e = self.extra
+        if "photon_params" not in e:
+            return None
+        maps = []
+        for prefix in ("caustic", "global"):
+            maps.append({k: e[f"{prefix}_{k}"] for k in
+                         ("octant_bounds", "octant_start", "octant_count", "octant_next", "octant_leaf", "photons")})
+        return maps[0], maps[1], int(e["photon_params"][0]), int(e["photon_params"][1])
+
+
+class Camera:
+    """Camera state after the reference's Camera::Camera (camera.cpp:20-64)."""
+
+    def __init__(self, eye, forward, left, up, focal_length, sensor_width, width, height,
+                 aperture_radius=-1.0, focus_distance=-1.0, thin_lens=False, sqrtspp=1):
+        self.rec = CameraRec()
+        for name, v in (("eye", eye), ("forward", forward), ("left", left), ("up", up)):
+            for i in range(3):
+                getattr(self.rec, name)[i] = float(v[i])
+        self.rec.focal_length = focal_length
+        self.rec.sensor_width = sensor_width
+        self.rec.aperture_radius = aperture_radius
+        self.rec.focus_distance = focus_distance
+        self.rec.width, self.rec.height = int(width), int(height)
+        self.rec.thin_lens = int(bool(thin_lens))
+        self.sqrtspp = int(sqrtspp)
+
+    @classmethod
+    def from_pack_arrays(cls, f64, u32):
+        return cls(f64[0:3], f64[3:6], f64[6:9], f64[9:12], f64[12], f64[13], u32[0], u32[1],
+                   f64[14], f64[15], bool(u32[2]), int(u32[3]))
+
+    @property
+    def width(self):
+        return self.rec.width
+
+    @property
+    def height(self):
+        return self.rec.height
+
+    def resized(self, width, height, sqrtspp=None):
+        c = Camera(self.rec.eye, self.rec.forward, self.rec.left, self.rec.up, self.rec.focal_length,
+                   self.rec.sensor_width, width, height, self.rec.aperture_radius, self.rec.focus_distance,
+                   self.rec.thin_lens, self.sqrtspp if sqrtspp is None else sqrtspp)
+        return c
+
+
+class Integrator:
+    """GPU context + uploaded scene. Mirrors class Integrator (source/integrator/integrator.hpp:7-30):
+    owns the Scene, exposes sampleRay (batched) and is what Camera.sampleImage renders through."""
+
+    kind = INTEGRATOR_PATH
+
+    def __init__(self, scene, device=0, precision=PRECISION_F64, global_seed=0x12345678):
+        self.scene = scene
+        self.precision = precision
+        self.global_seed = global_seed & 0xFFFFFFFF
+        self.ctx = C.c_void_p()
+        rc = lib().mcrt_init(device, C.byref(self.ctx))
+        if rc:
+            self.ctx = C.c_void_p()
+            raise McrtError(f"mcrt_init(device={device}) failed with {rc}: no CUDA device? (there is no CPU fallback)")
+        self.device = device
+        self.h2d_bytes = 0
+        self.upload_scene()
+        self.last_stats = None
+
+    def _check(self, rc):
+        if rc:
+            raise McrtError(f"mcrt error {rc}: {lib().mcrt_last_error(self.ctx).decode()}")
+
+    def set_option(self, key, value):
+        self._check(lib().mcrt_set_option(self.ctx, key.encode(), float(value)))
+
+    def upload_scene(self):
+        d = self.scene.desc()
+        n = C.c_uint64()
+        self._check(lib().mcrt_scene_upload(self.ctx, C.byref(d), C.byref(n)))
+        self.h2d_bytes = n.value
+        return n.value
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            lib().mcrt_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Integrator::sampleRay, batched
+    def sampleRay(self, rays, pixel, sample, precision=None):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(rays), 3))
+        st = Stats()
+        self._check(lib().mcrt_sample_rays(self.ctx, _ptr(rays), _ptr(pixel), _ptr(sample), len(rays),
+                                           self.global_seed, self.kind,
+                                           self.precision if precision is None else precision, _ptr(out), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return out
+
+    # -- Scene::intersect, batched
+    def intersect(self, rays, precision=None):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        st = Stats()
+        self._check(lib().mcrt_trace_closest(self.ctx, _ptr(rays), len(rays),
+                                             self.precision if precision is None else precision, _ptr(hits), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return hits
+
+    # -- Camera::sampleImage for a block of rows (box film), host output
+    def render_rows(self, camera, y0=0, y1=None, sqrtspp=None, precision=None, out=None):
+        y1 = camera.height if y1 is None else y1
+        if out is None:
+            out = np.zeros((y1 - y0, camera.width, 3))
+        st = Stats()
+        self._check(lib().mcrt_render_rows(self.ctx, C.byref(camera.rec), y0, y1,
+                                           camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed, self.kind,
+                                           self.precision if precision is None else precision, _ptr(out), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return out
+
+    # -- same, framebuffer stays in HBM (raw device pointer, float64 [rows*W*3])
+    def render_rows_dev(self, camera, out_dev_ptr, y0=0, y1=None, sqrtspp=None, precision=None):
+        y1 = camera.height if y1 is None else y1
+        st = Stats()
+        self._check(lib().mcrt_render_rows_dev(self.ctx, C.byref(camera.rec), y0, y1,
+                                               camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed,
+                                               self.kind, self.precision if precision is None else precision,
+                                               C.c_void_p(out_dev_ptr), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def sampler_stream(self, pixel, sample, n_shuffles):
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(pixel), 7), dtype=np.uint32)
+        self._check(lib().mcrt_sampler_stream(self.ctx, _ptr(pixel), _ptr(sample), len(pixel), n_shuffles,
+                                              self.global_seed, _ptr(out)))
+        return out
+
+
+class PathTracer(Integrator):
+    kind = INTEGRATOR_PATH
+
+
+class PhotonMapper(Integrator):
+    """Renders with the caustic/global photon maps the CPU photon pass produced (first pass stays on
+    the CPU); maps come from the scene pack or from explicit arrays."""
+    kind = INTEGRATOR_PHOTON
+
+    def __init__(self, scene, device=0, precision=PRECISION_F64, global_seed=0x12345678, photon_maps=None):
+        super().__init__(scene, device, precision, global_seed)
+        maps = photon_maps or scene.photon_maps()
+        if maps is None:
+            raise McrtError("PhotonMapper needs photon maps (scene pack exported with photon_map=True)")
+        self._maps = maps
+        self.upload_photons()
+
+    @staticmethod
+    def _map_desc(m):
+        d = PhotonMapDesc()
+        d.n_octants = m["octant_leaf"].size
+        d.octant_bounds = _ptr(m["octant_bounds"]); d.octant_start = _ptr(m["octant_start"])
+        d.octant_count = _ptr(m["octant_count"]); d.octant_next_sibling = _ptr(m["octant_next"])
+        d.octant_leaf = _ptr(m["octant_leaf"])
+        d.n_photons = m["photons"].size // 8
+        d.photons = _ptr(m["photons"])
+        return d
+
+    def upload_photons(self):
+        caustic, glob, k, dv = self._maps
+        dc, dg = self._map_desc(caustic), self._map_desc(glob)
+        n = C.c_uint64()
+        self._check(lib().mcrt_photon_upload(self.ctx, C.byref(dc), C.byref(dg), k, dv, C.byref(n)))
+        self.k_nearest = k
+        return n.value
+
+    def knn(self, which, points):
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        n, k = len(points), self.k_nearest
+        idx = np.full((n, k), NO_PRIM, dtype=np.uint32); d2 = np.full((n, k), np.inf); cnt = np.zeros(n, dtype=np.uint32)
+        st = Stats()
+        self._check(lib().mcrt_knn_search(self.ctx, which, _ptr(points), n, _ptr(idx), _ptr(d2), _ptr(cnt), C.byref(st)))
+        return idx, d2, cnt
+
+
+def shard_rows(height, rank, world_size):
+    """Row block of `rank`: contiguous blocks, remainder spread over the first ranks."""
+    base, rem = divmod(height, world_size)
+    y0 = rank * base + min(rank, rem)
+    return y0, y0 + base + (1 if rank < rem else 0)

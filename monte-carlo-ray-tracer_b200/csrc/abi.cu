@@ -1,0 +1,814 @@
+// C ABI of the B200 path-tracing integrator (include/mcrt_abi.h): context, scene upload (derives
+// the float64 parity layout and the float32 wide-node layout from the flattened reference scene),
+// the wavefront render loop and the batched sampleRay / Scene::intersect / sampler entry points.
+// There is deliberately no CPU fallback: without a CUDA device every entry point fails.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mcrt_abi.h"
+#include "launch.h"
+#include "photon.h"
+
+using namespace mcrt;
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+        {                                                                                     \
+            ctx->error = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return MCRT_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+namespace
+{
+    template <class R> struct SceneArrays
+    {
+        std::vector<Node<R>> nodes;
+        std::vector<WideChild> wide;
+        std::vector<V4<R>> geom;
+        std::vector<PrimShade<R>> shade;
+        std::vector<V4<R>> vnormals;
+        std::vector<Quadric<R>> quadrics;
+        std::vector<Material<R>> materials;
+        std::vector<Light<R>> lights;
+        DeviceScene<R> dev;
+    };
+
+    template <class R> struct WaveBuffers
+    {
+        PathBuffer<R> buf[2];
+        ShadowQueue<R> shadow;
+        V4<R>* hits = nullptr;
+        uint32_t capacity = 0;
+    };
+}
+
+struct mcrt_ctx
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    bool has_scene = false;
+    std::vector<void*> scene_allocs;
+    DeviceScene<double> scene64;
+    DeviceScene<float> scene32;
+    float scene_scale = 1.0f;
+
+    WaveBuffers<double> wave64;
+    WaveBuffers<float> wave32;
+    std::vector<void*> wave_allocs64, wave_allocs32;
+
+    Counters* d_counters = nullptr;
+    Counters* h_counters = nullptr; // pinned, 2 slots
+    double* d_film = nullptr;
+    size_t film_values = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_poll[2] = { nullptr, nullptr };
+
+    PhotonMaps photon;
+
+    // options
+    uint32_t pool_paths = 1u << 22;
+    int blocks_per_sm = 8;
+    double ray_eps_scale = 1e-5;
+    int poll_interval = 4;
+    int stage_timing = 0;
+};
+
+namespace
+{
+    template <class T>
+    int devAlloc(mcrt_ctx* ctx, std::vector<void*>& track, T** out, size_t count)
+    {
+        *out = nullptr;
+        if (count == 0) count = 1;
+        void* p = nullptr;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        track.push_back(p);
+        *out = static_cast<T*>(p);
+        return MCRT_OK;
+    }
+
+    template <class T>
+    int devUpload(mcrt_ctx* ctx, std::vector<void*>& track, const T** out, const std::vector<T>& v, uint64_t& bytes)
+    {
+        T* p = nullptr;
+        int rc = devAlloc(ctx, track, &p, v.size());
+        if (rc) return rc;
+        if (!v.empty())
+        {
+            CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+            bytes += v.size() * sizeof(T);
+        }
+        *out = p;
+        return MCRT_OK;
+    }
+
+    void freeAll(std::vector<void*>& track)
+    {
+        for (void* p : track) cudaFree(p);
+        track.clear();
+    }
+
+    template <class R> V3<R> v3(const double* p) { return V3<R>((R)p[0], (R)p[1], (R)p[2]); }
+
+    // Build the per-precision host arrays from the float64 description.
+    template <class R>
+    int buildArrays(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<R>& a)
+    {
+        // ---- reference-order nodes
+        a.nodes.resize(s.n_nodes);
+        for (uint32_t i = 0; i < s.n_nodes; i++)
+        {
+            Node<R>& n = a.nodes[i];
+            for (int k = 0; k < 3; k++) { n.bmin[k] = (R)s.node_bounds[6 * i + k]; n.bmax[k] = (R)s.node_bounds[6 * i + 3 + k]; }
+            n.first_prim = s.node_first_prim[i];
+            n.prim_count = s.node_prim_count[i];
+            n.next_sibling = s.node_next_sibling[i];
+            n._pad = 0;
+        }
+
+        // ---- geometry slots + shading records
+        a.geom.resize(3 * (size_t)s.n_prims);
+        a.shade.resize(s.n_prims);
+        for (uint32_t i = 0; i < s.n_prims; i++)
+        {
+            const uint32_t type = s.prim_type[i], idx = s.prim_index[i];
+            PrimShade<R>& ps = a.shade[i];
+            ps.nx = ps.ny = ps.nz = R(0);
+            ps.area = (R)s.prim_area[i];
+            ps.material = s.prim_material[i];
+            ps.vn_index = -1;
+            ps.type = type;
+            ps.light = NO_PRIM;
+            if (ps.material >= s.n_materials) { ctx->error = "prim_material out of range"; return MCRT_ERR_INVALID; }
+            if (type == MCRT_PRIM_TRIANGLE)
+            {
+                if (idx >= s.n_tris) { ctx->error = "triangle index out of range"; return MCRT_ERR_INVALID; }
+                a.geom[3 * i + 0] = V4<R>(v3<R>(s.tri_v0 + 3 * idx), R(PRIM_TRIANGLE));
+                a.geom[3 * i + 1] = V4<R>(v3<R>(s.tri_e1 + 3 * idx), R(0));
+                a.geom[3 * i + 2] = V4<R>(v3<R>(s.tri_e2 + 3 * idx), R(0));
+                ps.nx = (R)s.tri_normal[3 * idx]; ps.ny = (R)s.tri_normal[3 * idx + 1]; ps.nz = (R)s.tri_normal[3 * idx + 2];
+                ps.vn_index = s.tri_vn_index[idx];
+                if (ps.vn_index >= (int32_t)s.n_vertex_normals) { ctx->error = "vertex normal index out of range"; return MCRT_ERR_INVALID; }
+            }
+            else if (type == MCRT_PRIM_SPHERE)
+            {
+                if (idx >= s.n_spheres) { ctx->error = "sphere index out of range"; return MCRT_ERR_INVALID; }
+                const double* sp = s.sphere_origin_radius + 4 * idx;
+                a.geom[3 * i + 0] = V4<R>(v3<R>(sp), R(PRIM_SPHERE));
+                a.geom[3 * i + 1] = V4<R>((R)sp[3], R(0), R(0), R(0));
+                a.geom[3 * i + 2] = V4<R>(R(0), R(0), R(0), R(0));
+            }
+            else if (type == MCRT_PRIM_QUADRIC)
+            {
+                if (idx >= s.n_quadrics) { ctx->error = "quadric index out of range"; return MCRT_ERR_INVALID; }
+                a.geom[3 * i + 0] = V4<R>(R(idx), R(0), R(0), R(PRIM_QUADRIC));
+                a.geom[3 * i + 1] = V4<R>(R(0), R(0), R(0), R(0));
+                a.geom[3 * i + 2] = V4<R>(R(0), R(0), R(0), R(0));
+            }
+            else
+            {
+                ctx->error = "unknown primitive type";
+                return MCRT_ERR_INVALID;
+            }
+        }
+
+        a.vnormals.resize(3 * (size_t)s.n_vertex_normals);
+        for (uint32_t i = 0; i < s.n_vertex_normals; i++)
+            for (int k = 0; k < 3; k++)
+                a.vnormals[3 * i + k] = V4<R>(v3<R>(s.vertex_normals + 9 * i + 3 * k), R(0));
+
+        a.quadrics.resize(s.n_quadrics);
+        for (uint32_t i = 0; i < s.n_quadrics; i++)
+        {
+            for (int k = 0; k < 16; k++) a.quadrics[i].Q[k] = (R)s.quadric_Q[16 * i + k];
+            for (int k = 0; k < 12; k++) a.quadrics[i].G[k] = (R)s.quadric_G[12 * i + k];
+            for (int k = 0; k < 3; k++) { a.quadrics[i].bmin[k] = (R)s.quadric_bounds[6 * i + k]; a.quadrics[i].bmax[k] = (R)s.quadric_bounds[6 * i + 3 + k]; }
+        }
+
+        a.materials.resize(s.n_materials);
+        for (uint32_t i = 0; i < s.n_materials; i++)
+        {
+            const mcrt_material& m = s.materials[i];
+            Material<R>& o = a.materials[i];
+            o.reflectance = v3<R>(m.reflectance);
+            o.specular_reflectance = v3<R>(m.specular_reflectance);
+            o.transmittance = v3<R>(m.transmittance);
+            o.emittance = v3<R>(m.emittance);
+            o.ior_real = v3<R>(m.complex_ior_real);
+            o.ior_imag = v3<R>(m.complex_ior_imag);
+            o.roughness = (R)m.roughness; o.specular_roughness = (R)m.specular_roughness;
+            o.ior = (R)m.ior; o.transparency = (R)m.transparency;
+            o.A = (R)m.A; o.B = (R)m.B; o.ax = (R)m.a[0]; o.ay = (R)m.a[1];
+            o.flags = (m.has_complex_ior ? MAT_COMPLEX_IOR : 0u) | (m.perfect_mirror ? MAT_PERFECT_MIRROR : 0u) |
+                      (m.rough ? MAT_ROUGH : 0u) | (m.rough_specular ? MAT_ROUGH_SPECULAR : 0u) |
+                      (m.opaque ? MAT_OPAQUE : 0u) | (m.emissive ? MAT_EMISSIVE : 0u) |
+                      (m.dirac_delta ? MAT_DIRAC_DELTA : 0u);
+        }
+
+        a.lights.resize(s.n_lights);
+        for (uint32_t i = 0; i < s.n_lights; i++)
+        {
+            const uint32_t prim = s.light_prim[i];
+            if (prim >= s.n_prims) { ctx->error = "light_prim out of range"; return MCRT_ERR_INVALID; }
+            const uint32_t type = s.prim_type[prim], idx = s.prim_index[prim];
+            Light<R>& l = a.lights[i];
+            l.prim = prim; l.type = type;
+            l.cdf = (R)s.light_cdf[i];
+            l.area = (R)s.prim_area[prim];
+            l.emittance = v3<R>(s.materials[s.prim_material[prim]].emittance);
+            l.p0 = l.p1 = l.p2 = l.normal = V3<R>(R(0));
+            if (type == MCRT_PRIM_TRIANGLE)
+            {
+                l.p0 = v3<R>(s.tri_v0 + 3 * idx); l.p1 = v3<R>(s.tri_v1 + 3 * idx); l.p2 = v3<R>(s.tri_v2 + 3 * idx);
+                l.normal = v3<R>(s.tri_normal + 3 * idx);
+            }
+            else if (type == MCRT_PRIM_SPHERE)
+            {
+                l.p0 = v3<R>(s.sphere_origin_radius + 4 * idx);
+                l.p1 = V3<R>((R)s.sphere_origin_radius[4 * idx + 3], R(0), R(0));
+            }
+            else
+            {
+                ctx->error = "quadric lights are not supported by the reference (scene.cpp:125-132)";
+                return MCRT_ERR_INVALID;
+            }
+            a.shade[prim].light = i;
+        }
+        return MCRT_OK;
+    }
+
+    // float32 wide layout: the children of every inner node as consecutive 32-byte records.
+    int buildWide(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<float>& a)
+    {
+        DeviceScene<float>& d = a.dev;
+        d.root_is_leaf = 0; d.root_first_prim = 0; d.root_prim_count = 0; d.n_wide_root = 0;
+        for (int k = 0; k < 3; k++) { d.root_bmin[k] = 0.f; d.root_bmax[k] = 0.f; }
+        if (s.n_nodes == 0) return MCRT_OK;
+        for (int k = 0; k < 3; k++) { d.root_bmin[k] = (float)s.node_bounds[k]; d.root_bmax[k] = (float)s.node_bounds[3 + k]; }
+        if (s.node_prim_count[0])
+        {
+            d.root_is_leaf = 1; d.root_first_prim = s.node_first_prim[0]; d.root_prim_count = s.node_prim_count[0];
+            return MCRT_OK;
+        }
+        auto childrenOf = [&](uint32_t node, std::vector<uint32_t>& out)
+        {
+            out.clear();
+            uint32_t c = node + 1;
+            while (c != 0 && c < s.n_nodes) { out.push_back(c); c = s.node_next_sibling[c]; }
+        };
+        // breadth-first so that siblings' blocks are close together
+        struct Pending { uint32_t node; uint32_t record; }; // record = index of the child record to patch
+        std::vector<uint32_t> kids;
+        std::vector<Pending> queue;
+        childrenOf(0, kids);
+        d.n_wide_root = (uint32_t)kids.size();
+        auto emitBlock = [&](const std::vector<uint32_t>& ks) -> int
+        {
+            if (ks.size() > 8) { ctx->error = "BVH arity > 8 unsupported"; return MCRT_ERR_UNSUPPORTED; }
+            for (uint32_t c : ks)
+            {
+                WideChild w;
+                // conservative float bounds: round outwards so no double-precision hit is lost
+                for (int k = 0; k < 3; k++)
+                {
+                    float lo = (float)s.node_bounds[6 * c + k], hi = (float)s.node_bounds[6 * c + 3 + k];
+                    if ((double)lo > s.node_bounds[6 * c + k]) lo = nextafterf(lo, -INFINITY);
+                    if ((double)hi < s.node_bounds[6 * c + 3 + k]) hi = nextafterf(hi, INFINITY);
+                    w.bmin[k] = lo; w.bmax[k] = hi;
+                }
+                if (s.node_prim_count[c]) { w.a = s.node_first_prim[c]; w.b = s.node_prim_count[c] | WIDE_LEAF; }
+                else { w.a = 0; w.b = 0; queue.push_back({ c, (uint32_t)a.wide.size() }); }
+                a.wide.push_back(w);
+            }
+            return MCRT_OK;
+        };
+        int rc = emitBlock(kids);
+        if (rc) return rc;
+        for (size_t q = 0; q < queue.size(); q++)
+        {
+            const Pending pnd = queue[q];
+            childrenOf(pnd.node, kids);
+            a.wide[pnd.record].a = (uint32_t)a.wide.size();
+            a.wide[pnd.record].b = (uint32_t)kids.size();
+            rc = emitBlock(kids);
+            if (rc) return rc;
+        }
+        return MCRT_OK;
+    }
+
+    template <class R>
+    int uploadArrays(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<R>& a, uint64_t& bytes)
+    {
+        DeviceScene<R>& d = a.dev;
+        int rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.nodes, a.nodes, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.wide, a.wide, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.geom, a.geom, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.shade, a.shade, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.vnormals, a.vnormals, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.quadrics, a.quadrics, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.materials, a.materials, bytes))) return rc;
+        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.lights, a.lights, bytes))) return rc;
+        d.n_nodes = s.n_nodes; d.n_prims = s.n_prims; d.n_lights = s.n_lights;
+        d.scene_ior = (R)s.scene_ior;
+        d.scene_scale = (R)ctx->scene_scale;
+        return MCRT_OK;
+    }
+
+    template <class R>
+    int ensureWave(mcrt_ctx* ctx, WaveBuffers<R>& w, std::vector<void*>& track)
+    {
+        if (w.capacity == ctx->pool_paths) return MCRT_OK;
+        freeAll(track);
+        w.capacity = 0;
+        const size_t n = ctx->pool_paths;
+        int rc;
+        for (int b = 0; b < 2; b++)
+        {
+            if ((rc = devAlloc(ctx, track, &w.buf[b].ray_o, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].ray_d, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].thr, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].iors_a, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].iors_b, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].meta, n))) return rc;
+            if ((rc = devAlloc(ctx, track, &w.buf[b].meta2, n))) return rc;
+        }
+        if ((rc = devAlloc(ctx, track, &w.shadow.o, n))) return rc;
+        if ((rc = devAlloc(ctx, track, &w.shadow.d, n))) return rc;
+        if ((rc = devAlloc(ctx, track, &w.shadow.k, n))) return rc;
+        if ((rc = devAlloc(ctx, track, &w.shadow.meta, n))) return rc;
+        if ((rc = devAlloc(ctx, track, &w.hits, n))) return rc;
+        w.capacity = ctx->pool_paths;
+        return MCRT_OK;
+    }
+
+    int ensureFilm(mcrt_ctx* ctx, size_t values)
+    {
+        if (ctx->film_values >= values && ctx->d_film) return MCRT_OK;
+        if (ctx->d_film) cudaFree(ctx->d_film);
+        ctx->d_film = nullptr; ctx->film_values = 0;
+        CK(cudaMalloc((void**)&ctx->d_film, values * sizeof(double)));
+        ctx->film_values = values;
+        return MCRT_OK;
+    }
+
+    template <class R> DeviceScene<R>& sceneOf(mcrt_ctx* ctx);
+    template <> DeviceScene<double>& sceneOf<double>(mcrt_ctx* ctx) { return ctx->scene64; }
+    template <> DeviceScene<float>& sceneOf<float>(mcrt_ctx* ctx) { return ctx->scene32; }
+    template <class R> WaveBuffers<R>& waveOf(mcrt_ctx* ctx);
+    template <> WaveBuffers<double>& waveOf<double>(mcrt_ctx* ctx) { return ctx->wave64; }
+    template <> WaveBuffers<float>& waveOf<float>(mcrt_ctx* ctx) { return ctx->wave32; }
+    template <class R> std::vector<void*>& waveAllocsOf(mcrt_ctx* ctx);
+    template <> std::vector<void*>& waveAllocsOf<double>(mcrt_ctx* ctx) { return ctx->wave_allocs64; }
+    template <> std::vector<void*>& waveAllocsOf<float>(mcrt_ctx* ctx) { return ctx->wave_allocs32; }
+
+    void fillStats(mcrt_stats* st, const Counters& c, uint64_t iterations, uint64_t launches, double ms)
+    {
+        if (!st) return;
+        std::memset(st, 0, sizeof(*st));
+        st->paths = c.paths;
+        st->extension_rays = c.extension_rays;
+        st->shadow_rays = c.shadow_rays;
+        st->box_tests = c.box_tests;
+        st->prim_tests = c.prim_tests;
+        st->knn_queries = c.knn_queries;
+        st->wavefront_iterations = iterations;
+        st->kernel_launches = launches;
+        st->ior_stack_overflows = c.ior_stack_overflows;
+        st->max_depth = c.max_depth;
+        st->gpu_ms_total = ms;
+    }
+
+    // The wavefront loop shared by mcrt_render_rows(_dev) and mcrt_sample_rays.
+    template <class R>
+    int runWavefront(mcrt_ctx* ctx, const mcrt_camera* cam, uint32_t first_pixel, uint32_t n_pixels, uint32_t spp,
+                     uint64_t total_work, uint32_t global_seed, int integrator, const double* d_user_rays,
+                     const uint32_t* d_user_pixel, const uint32_t* d_user_sample, size_t film_pixels,
+                     double film_weight, double* out_dev, mcrt_stats* stats)
+    {
+        if (!ctx->has_scene) { ctx->error = "no scene uploaded"; return MCRT_ERR_NO_SCENE; }
+        if (integrator == MCRT_INTEGRATOR_PHOTON && !ctx->photon.valid)
+        {
+            ctx->error = "photon-mapped render requested without mcrt_photon_upload";
+            return MCRT_ERR_NO_PHOTONS;
+        }
+        WaveBuffers<R>& wb = waveOf<R>(ctx);
+        int rc;
+        if ((rc = ensureWave(ctx, wb, waveAllocsOf<R>(ctx)))) return rc;
+        if ((rc = ensureFilm(ctx, film_pixels * 3))) return rc;
+        if (integrator == MCRT_INTEGRATOR_PHOTON && (rc = photonEnsureQueue<R>(ctx->photon, ctx->pool_paths, ctx->error))) return rc;
+
+        WaveParams<R> p;
+        std::memset(&p, 0, sizeof(p));
+        p.scene = sceneOf<R>(ctx);
+        if (cam)
+        {
+            for (int k = 0; k < 3; k++) { }
+            p.camera.eye = v3<R>(cam->eye); p.camera.forward = v3<R>(cam->forward);
+            p.camera.left = v3<R>(cam->left); p.camera.up = v3<R>(cam->up);
+            p.camera.focal_length = (R)cam->focal_length; p.camera.sensor_width = (R)cam->sensor_width;
+            p.camera.aperture_radius = (R)cam->aperture_radius; p.camera.focus_distance = (R)cam->focus_distance;
+            p.camera.width = cam->width; p.camera.height = cam->height; p.camera.thin_lens = cam->thin_lens;
+        }
+        p.buf[0] = wb.buf[0]; p.buf[1] = wb.buf[1];
+        p.shadow = wb.shadow;
+        p.hits = wb.hits;
+        p.counters = ctx->d_counters;
+        p.film = ctx->d_film;
+        p.user_rays = d_user_rays; p.user_pixel = d_user_pixel; p.user_sample = d_user_sample;
+        p.capacity = wb.capacity;
+        p.global_seed = global_seed;
+        p.spp = spp;
+        p.first_pixel = first_pixel;
+        p.n_pixels = n_pixels;
+        p.integrator = (uint32_t)integrator;
+        p.ray_eps = Mode<R>::parity ? (R)1e-9 : (R)(ctx->ray_eps_scale * ctx->scene_scale);
+
+        PhotonLaunchArgs<R> pm_args;
+        if (integrator == MCRT_INTEGRATOR_PHOTON) pm_args = photonLaunchArgs<R>(ctx->photon);
+
+        cudaStream_t s = ctx->stream;
+        const int grid = ctx->sm_count * ctx->blocks_per_sm;
+
+        Counters init;
+        std::memset(&init, 0, sizeof(init));
+        init.total_work = total_work;
+        ctx->h_counters[0] = init;
+        CK(cudaMemcpyAsync(ctx->d_counters, &ctx->h_counters[0], sizeof(Counters), cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ctx->d_film, 0, film_pixels * 3 * sizeof(double), s));
+
+        CK(cudaEventRecord(ctx->ev_start, s));
+        uint64_t launches = 0, iterations = 0;
+
+        Launch<R>::generate(p, 0, grid, s);
+        launchAdvance(ctx->d_counters, s);
+        launches += 2;
+
+        // Enqueue iterations ahead of the GPU; poll the queue counters through pinned memory every
+        // poll_interval iterations with one poll of look-ahead, so the device never waits on the host.
+        int pending[2] = { 0, 0 };
+        int slot = 0;
+        bool done = false;
+        while (!done)
+        {
+            for (int k = 0; k < ctx->poll_interval; k++)
+            {
+                const int cur = (int)(iterations & 1u);
+                Launch<R>::extend(p, cur, grid, s);
+                if (integrator == MCRT_INTEGRATOR_PHOTON)
+                {
+                    photonShade<R>(p, pm_args, cur, grid, s);
+                    launches += 1;
+                }
+                else
+                {
+                    Launch<R>::shade(p, cur, grid, s);
+                }
+                Launch<R>::shadow(p, grid, s);
+                Launch<R>::generate(p, cur ^ 1, grid, s);
+                launchAdvance(ctx->d_counters, s);
+                launches += 5;
+                iterations++;
+            }
+            CK(cudaMemcpyAsync(&ctx->h_counters[slot], ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(ctx->ev_poll[slot], s));
+            pending[slot] = 1;
+            const int other = slot ^ 1;
+            if (pending[other])
+            {
+                CK(cudaEventSynchronize(ctx->ev_poll[other]));
+                const Counters& c = ctx->h_counters[other];
+                if (c.n_cur == 0 && c.next_work >= c.total_work) done = true;
+                pending[other] = 0;
+            }
+            slot = other;
+        }
+
+        launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
+        launches += 1;
+        CK(cudaEventRecord(ctx->ev_stop, s));
+        CK(cudaMemcpyAsync(&ctx->h_counters[0], ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        const Counters& c = ctx->h_counters[0];
+        fillStats(stats, c, iterations, launches, ms);
+        if (c.traversal_overflow)
+        {
+            ctx->error = "traversal stack/heap overflow: result would differ from the reference";
+            return MCRT_ERR_UNSUPPORTED;
+        }
+        return MCRT_OK;
+    }
+
+    int renderDispatch(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
+                       uint32_t global_seed, int integrator_kind, int precision, double* out_dev, mcrt_stats* stats)
+    {
+        if (!camera || y1 <= y0 || y1 > camera->height || sqrtspp == 0 || camera->width == 0)
+        {
+            ctx->error = "mcrt_render_rows: invalid camera / row range / sqrtspp";
+            return MCRT_ERR_INVALID;
+        }
+        const uint64_t n_pixels64 = (uint64_t)camera->width * (y1 - y0);
+        if (n_pixels64 > 0xFFFFFFFFull) { ctx->error = "row block too large"; return MCRT_ERR_INVALID; }
+        const uint32_t n_pixels = (uint32_t)n_pixels64;
+        const uint32_t spp = sqrtspp * sqrtspp;
+        const uint64_t total = (uint64_t)n_pixels * spp;
+        if (precision == MCRT_PRECISION_F64)
+            return runWavefront<double>(ctx, camera, y0 * camera->width, n_pixels, spp, total, global_seed, integrator_kind,
+                                        nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
+        if (precision == MCRT_PRECISION_F32)
+            return runWavefront<float>(ctx, camera, y0 * camera->width, n_pixels, spp, total, global_seed, integrator_kind,
+                                       nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
+        ctx->error = "unknown precision";
+        return MCRT_ERR_INVALID;
+    }
+}
+
+extern "C"
+{
+
+int mcrt_abi_version(void) { return MCRT_ABI_VERSION; }
+
+int mcrt_init(int device, mcrt_ctx** out_ctx)
+{
+    if (!out_ctx) return MCRT_ERR_INVALID;
+    *out_ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MCRT_ERR_CUDA;
+    mcrt_ctx* ctx = new mcrt_ctx();
+    ctx->device = device;
+    auto fail = [&](int rc) { mcrt_destroy(ctx); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    if (cudaMalloc((void**)&ctx->d_counters, sizeof(Counters)) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    if (cudaMallocHost((void**)&ctx->h_counters, 2 * sizeof(Counters)) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    *out_ctx = ctx;
+    return MCRT_OK;
+}
+
+void mcrt_destroy(mcrt_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    freeAll(ctx->scene_allocs);
+    freeAll(ctx->wave_allocs64);
+    freeAll(ctx->wave_allocs32);
+    photonFree(ctx->photon);
+    if (ctx->d_film) cudaFree(ctx->d_film);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    for (int i = 0; i < 2; i++) if (ctx->ev_poll[i]) cudaEventDestroy(ctx->ev_poll[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mcrt_last_error(const mcrt_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : "null context";
+}
+
+int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
+{
+    if (!ctx || !key) return MCRT_ERR_INVALID;
+    std::string k(key);
+    if (k == "pool_paths") { if (value < 1024 || value > 268435456.0) return MCRT_ERR_INVALID; ctx->pool_paths = (uint32_t)value; }
+    else if (k == "blocks_per_sm") { if (value < 1 || value > 32) return MCRT_ERR_INVALID; ctx->blocks_per_sm = (int)value; }
+    else if (k == "ray_eps_scale") { if (value <= 0) return MCRT_ERR_INVALID; ctx->ray_eps_scale = value; }
+    else if (k == "poll_interval") { if (value < 1 || value > 1024) return MCRT_ERR_INVALID; ctx->poll_interval = (int)value; }
+    else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
+    return MCRT_OK;
+}
+
+int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d_bytes)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!scene || scene->abi_version != MCRT_ABI_VERSION) { ctx->error = "scene description missing or ABI version mismatch"; return MCRT_ERR_INVALID; }
+    if (scene->n_prims == 0 || scene->n_materials == 0) { ctx->error = "empty scene"; return MCRT_ERR_INVALID; }
+    if (scene->n_prims >= (1u << 24)) { ctx->error = "more than 2^24 primitives"; return MCRT_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(ctx->device));
+    const mcrt_scene_desc& s = *scene;
+
+    // structural validation of the BVH links (a malformed tree must not hang the device)
+    for (uint32_t i = 0; i < s.n_nodes; i++)
+    {
+        if (s.node_next_sibling[i] != 0 && (s.node_next_sibling[i] <= i || s.node_next_sibling[i] >= s.n_nodes))
+        { ctx->error = "node_next_sibling must point forward"; return MCRT_ERR_INVALID; }
+        if ((uint64_t)s.node_first_prim[i] + s.node_prim_count[i] > s.n_prims)
+        { ctx->error = "node primitive range out of bounds"; return MCRT_ERR_INVALID; }
+        if (s.node_prim_count[i] == 0 && i + 1 >= s.n_nodes)
+        { ctx->error = "inner node without children"; return MCRT_ERR_INVALID; }
+    }
+    for (uint32_t i = 1; i < s.n_lights; i++)
+    {
+        if (s.light_cdf[i] < s.light_cdf[i - 1]) { ctx->error = "light_cdf must be non-decreasing"; return MCRT_ERR_INVALID; }
+    }
+
+    freeAll(ctx->scene_allocs);
+    ctx->has_scene = false;
+
+    // scene scale for the fast mode's ray offsets
+    double scale = 0.0;
+    auto grow = [&](const double* p, int n) { for (int i = 0; i < n; i++) { double v = p[i] < 0 ? -p[i] : p[i]; if (v < 1e300 && v > scale) scale = v; } };
+    if (s.n_nodes) grow(s.node_bounds, 6);
+    else
+    {
+        grow(s.tri_v0, 3 * s.n_tris); grow(s.tri_v1, 3 * s.n_tris); grow(s.tri_v2, 3 * s.n_tris);
+        for (uint32_t i = 0; i < s.n_spheres; i++) { double m = 0; for (int k = 0; k < 3; k++) { double v = s.sphere_origin_radius[4 * i + k]; v = v < 0 ? -v : v; if (v > m) m = v; } m += s.sphere_origin_radius[4 * i + 3]; if (m > scale) scale = m; }
+        grow(s.quadric_bounds, 6 * s.n_quadrics);
+    }
+    ctx->scene_scale = scale > 0.0 ? (float)scale : 1.0f;
+
+    uint64_t bytes = 0;
+    int rc;
+    {
+        SceneArrays<double> a;
+        if ((rc = buildArrays(ctx, s, a))) return rc;
+        std::memset(&a.dev, 0, sizeof(a.dev));
+        if ((rc = uploadArrays(ctx, s, a, bytes))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream)); // host vectors die at scope exit
+        ctx->scene64 = a.dev;
+    }
+    {
+        SceneArrays<float> a;
+        if ((rc = buildArrays(ctx, s, a))) return rc;
+        std::memset(&a.dev, 0, sizeof(a.dev));
+        if ((rc = buildWide(ctx, s, a))) return rc;
+        if ((rc = uploadArrays(ctx, s, a, bytes))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->scene32 = a.dev;
+    }
+    ctx->has_scene = true;
+    if (h2d_bytes) *h2d_bytes = bytes;
+    return MCRT_OK;
+}
+
+int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, const mcrt_photon_map_desc* global_map,
+                       uint32_t k_nearest, uint32_t direct_visualization, uint64_t* h2d_bytes)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!caustic_map || !global_map || k_nearest == 0) { ctx->error = "mcrt_photon_upload: invalid arguments"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    uint64_t bytes = 0;
+    int rc = photonUpload(ctx->photon, *caustic_map, *global_map, k_nearest, direct_visualization, ctx->stream, bytes, ctx->error);
+    if (h2d_bytes) *h2d_bytes = bytes;
+    return rc;
+}
+
+int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
+                         uint32_t global_seed, int integrator_kind, int precision, double* out_rgb_dev, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!out_rgb_dev) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    return renderDispatch(ctx, camera, y0, y1, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
+                     uint32_t global_seed, int integrator_kind, int precision, double* out_rgb, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!out_rgb || !camera || y1 <= y0) { ctx->error = "mcrt_render_rows: invalid arguments"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t values = (size_t)camera->width * (y1 - y0) * 3;
+    double* d_out = nullptr;
+    CK(cudaMalloc((void**)&d_out, values * sizeof(double)));
+    int rc = renderDispatch(ctx, camera, y0, y1, sqrtspp, global_seed, integrator_kind, precision, d_out, stats);
+    if (rc == MCRT_OK)
+    {
+        cudaError_t e = cudaMemcpy(out_rgb, d_out, values * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { ctx->error = cudaGetErrorString(e); rc = MCRT_ERR_CUDA; }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+int mcrt_sample_rays(mcrt_ctx* ctx, const mcrt_ray* rays, const uint32_t* pixel, const uint32_t* sample, size_t n,
+                     uint32_t global_seed, int integrator_kind, int precision, double* out_rgb, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (n == 0) return MCRT_OK;
+    if (!rays || !pixel || !sample || !out_rgb || n > 0xFFFFFFFFull) { ctx->error = "mcrt_sample_rays: invalid arguments"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    double* d_rays = nullptr; uint32_t* d_pixel = nullptr; uint32_t* d_sample = nullptr; double* d_out = nullptr;
+    int rc = MCRT_OK;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_pixel); cudaFree(d_sample); cudaFree(d_out); };
+    if (cudaMalloc((void**)&d_rays, n * 6 * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&d_pixel, n * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_sample, n * 4) != cudaSuccess || cudaMalloc((void**)&d_out, n * 3 * sizeof(double)) != cudaSuccess)
+    { cleanup(); ctx->error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
+    static_assert(sizeof(mcrt_ray) == 6 * sizeof(double), "mcrt_ray must be 6 doubles");
+    cudaMemcpyAsync(d_rays, rays, n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_pixel, pixel, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_sample, sample, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (precision == MCRT_PRECISION_F64)
+        rc = runWavefront<double>(ctx, nullptr, 0, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
+    else if (precision == MCRT_PRECISION_F32)
+        rc = runWavefront<float>(ctx, nullptr, 0, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
+    else { ctx->error = "unknown precision"; rc = MCRT_ERR_INVALID; }
+    if (rc == MCRT_OK && cudaMemcpy(out_rgb, d_out, n * 3 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+    { ctx->error = "copy back failed"; rc = MCRT_ERR_CUDA; }
+    cleanup();
+    return rc;
+}
+
+int mcrt_trace_closest(mcrt_ctx* ctx, const mcrt_ray* rays, size_t n, int precision, mcrt_hit* hits, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (n == 0) return MCRT_OK;
+    if (!rays || !hits) { ctx->error = "mcrt_trace_closest: null buffer"; return MCRT_ERR_INVALID; }
+    if (!ctx->has_scene) { ctx->error = "no scene uploaded"; return MCRT_ERR_NO_SCENE; }
+    CK(cudaSetDevice(ctx->device));
+    double* d_rays = nullptr; double* d_tuv = nullptr; uint32_t* d_prim = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_tuv); cudaFree(d_prim); };
+    if (cudaMalloc((void**)&d_rays, n * 6 * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&d_tuv, n * 3 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_prim, n * 4) != cudaSuccess)
+    { cleanup(); ctx->error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
+    cudaStream_t s = ctx->stream;
+    cudaMemcpyAsync(d_rays, rays, n * 6 * sizeof(double), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), s);
+    const int grid = ctx->sm_count * ctx->blocks_per_sm;
+    cudaEventRecord(ctx->ev_start, s);
+    if (precision == MCRT_PRECISION_F64) Launch<double>::traceUser(ctx->scene64, d_rays, n, d_tuv, d_prim, ctx->d_counters, grid, s);
+    else if (precision == MCRT_PRECISION_F32) Launch<float>::traceUser(ctx->scene32, d_rays, n, d_tuv, d_prim, ctx->d_counters, grid, s);
+    else { cleanup(); ctx->error = "unknown precision"; return MCRT_ERR_INVALID; }
+    cudaEventRecord(ctx->ev_stop, s);
+    std::vector<double> tuv(n * 3);
+    std::vector<uint32_t> prim(n);
+    cudaMemcpyAsync(tuv.data(), d_tuv, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(prim.data(), d_prim, n * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&ctx->h_counters[0], ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) { ctx->error = cudaGetErrorString(e); return MCRT_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+    fillStats(stats, ctx->h_counters[0], 0, 1, ms);
+    const bool have_vn = true;
+    (void)have_vn;
+    for (size_t i = 0; i < n; i++)
+    {
+        hits[i].t = tuv[3 * i]; hits[i].u = tuv[3 * i + 1]; hits[i].v = tuv[3 * i + 2];
+        hits[i].prim = prim[i];
+        hits[i].interpolate = 0;
+    }
+    if (ctx->h_counters[0].traversal_overflow) { ctx->error = "traversal stack/heap overflow"; return MCRT_ERR_UNSUPPORTED; }
+    return MCRT_OK;
+}
+
+int mcrt_sampler_stream(mcrt_ctx* ctx, const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles,
+                        uint32_t global_seed, uint32_t* out_u32x7)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (n == 0) return MCRT_OK;
+    if (!pixel || !sample || !out_u32x7) { ctx->error = "mcrt_sampler_stream: null buffer"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    uint32_t* d_pixel = nullptr; uint32_t* d_sample = nullptr; uint32_t* d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pixel); cudaFree(d_sample); cudaFree(d_out); };
+    if (cudaMalloc((void**)&d_pixel, n * 4) != cudaSuccess || cudaMalloc((void**)&d_sample, n * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_out, n * 28) != cudaSuccess)
+    { cleanup(); ctx->error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
+    cudaStream_t s = ctx->stream;
+    cudaMemcpyAsync(d_pixel, pixel, n * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_sample, sample, n * 4, cudaMemcpyHostToDevice, s);
+    launchSamplerStream(d_pixel, d_sample, n, n_shuffles, global_seed, d_out, s);
+    cudaMemcpyAsync(out_u32x7, d_out, n * 28, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) { ctx->error = cudaGetErrorString(e); return MCRT_ERR_CUDA; }
+    return MCRT_OK;
+}
+
+int mcrt_knn_search(mcrt_ctx* ctx, int which, const double* points_xyz, size_t n, uint32_t* out_index, double* out_dist2,
+                    uint32_t* out_count, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (n == 0) return MCRT_OK;
+    if (!points_xyz || !out_index || !out_dist2 || !out_count || (which != 0 && which != 1))
+    { ctx->error = "mcrt_knn_search: invalid arguments"; return MCRT_ERR_INVALID; }
+    if (!ctx->photon.valid) { ctx->error = "no photon maps uploaded"; return MCRT_ERR_NO_PHOTONS; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = photonKnnUser(ctx->photon, which, points_xyz, n, out_index, out_dist2, out_count, ctx->sm_count, ctx->stream, ctx->error);
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->knn_queries = n; }
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,578 @@
+// Wavefront path tracer: one kernel per stage over compacted queues that live in HBM.
+//
+// Stage kernels (each a grid-stride "persistent" launch sized to the SM count; queue lengths are
+// read from device memory so the host enqueues iterations without synchronising):
+//   k_generate  Camera::samplePixel ray generation (source/camera/camera.cpp:66-99) for the next
+//               (pixel, sample) work items, appended behind the survivors of the last bounce
+//   k_extend    Scene::intersect for every live path            (source/scene/scene.cpp:151-176)
+//   k_shade     one iteration of PathTracer::sampleRay's loop   (source/integrator/path-tracer/
+//               path-tracer.cpp:21-50): miss/sky, Interaction, sampleEmissive, the light-sampling
+//               half of sampleDirect, sampleBSDF, throughput, absorb (Russian roulette),
+//               RefractionHistory::update; survivors are compacted into the other path buffer with
+//               warp-aggregated appends, NEE candidates into the shadow queue
+//   k_shadow    the visibility half of Integrator::sampleDirect (source/integrator/
+//               integrator.cpp:68-86): closest-hit query, "hit that very light", MIS weight
+//   k_advance   queue bookkeeping between iterations (one thread)
+//
+// Path state is ping-ponged between two compact buffers (no index indirection: every access is a
+// coalesced 16/32-byte vector load/store). Radiance contributions are scattered straight into the
+// float64 film with RED.ADD.F64, adjacent lanes hitting adjacent pixels.
+#pragma once
+
+#include "bsdf.cuh"
+#include "intersect.cuh"
+
+namespace mcrt
+{
+    constexpr int IOR_STACK_CAPACITY = 8; // iors[0] is implicit (scene ior); 7 stored entries
+
+    struct Counters
+    {
+        uint32_t n_cur, n_next, n_shadow, n_gen;
+        unsigned long long next_work, total_work;
+        // statistics
+        unsigned long long paths, extension_rays, shadow_rays, box_tests, prim_tests, knn_queries;
+        unsigned long long ior_stack_overflows;
+        uint32_t traversal_overflow, max_depth;
+        uint32_t n_knn, _pad;
+    };
+
+    template <class R> struct PathBuffer
+    {
+        V4<R>* ray_o;    // start.xyz, medium_ior
+        V4<R>* ray_d;    // direction.xyz, refraction_scale
+        V4<R>* thr;      // throughput.xyz, ls.bsdf_pdf
+        V4<R>* iors_a;   // ls.select_probability, iors[1..3]
+        V4<R>* iors_b;   // iors[4..7]
+        uint4* meta;     // pixel, sample, depth | diffuse_depth<<16, refraction_level
+        uint4* meta2;    // ls.light prim, ior_count | dirac<<8, film_index, source prim (fast mode)
+    };
+
+    template <class R> struct ShadowQueue
+    {
+        V4<R>* o;        // start.xyz, bsdf_pdf
+        V4<R>* d;        // direction.xyz, area * cos_light
+        V4<R>* k;        // bsdf_absIdotN * Le * throughput, select_probability
+        uint4* meta;     // light prim, film_index, source prim, -
+    };
+
+    template <class R> struct WaveParams
+    {
+        DeviceScene<R> scene;
+        DeviceCamera<R> camera;
+        PathBuffer<R> buf[2];
+        ShadowQueue<R> shadow;
+        V4<R>* hits;           // t,u,v,prim
+        Counters* counters;
+        double* film;          // [n_film][3]
+        // user-supplied rays (mcrt_sample_rays); null for camera rendering
+        const double* user_rays;
+        const uint32_t* user_pixel;
+        const uint32_t* user_sample;
+        uint32_t capacity;
+        uint32_t global_seed;
+        uint32_t spp;
+        uint32_t first_pixel;   // y0 * width
+        uint32_t n_pixels;      // pixels in this rank's rows
+        uint32_t integrator;    // MCRT_INTEGRATOR_*
+        R ray_eps;              // C::EPSILON in parity mode; scale-aware in fast mode
+    };
+
+    // ------------------------------------------------------------------------------------------
+    template <class R> struct Mode;
+    template <> struct Mode<double> { static constexpr bool parity = true; };
+    template <> struct Mode<float> { static constexpr bool parity = false; };
+
+    template <class R>
+    MCRT_D Hit<R> traceClosest(const DeviceScene<R>& sc, const V3<R>& o, const V3<R>& d, uint32_t skip_prim,
+                               TraceCounters& cnt, uint32_t& overflow)
+    {
+        RayQ<R> rq;
+        rq.o = o; rq.d = d; rq.inv_d = R(1) / d;
+        if constexpr (Mode<R>::parity)
+        {
+            return traverseReferenceOrder(sc, rq, cnt, overflow);
+        }
+        else
+        {
+            return traverseWide(sc, rq, skip_prim, cnt, overflow);
+        }
+    }
+
+    MCRT_D void filmAdd(double* film, uint32_t index, double r, double g, double b)
+    {
+        if (r != 0.0) atomicAdd(&film[3 * (size_t)index + 0], r);
+        if (g != 0.0) atomicAdd(&film[3 * (size_t)index + 1], g);
+        if (b != 0.0) atomicAdd(&film[3 * (size_t)index + 2], b);
+    }
+
+    template <class R>
+    MCRT_D void filmAddV(double* film, uint32_t index, const V3<R>& v)
+    {
+        filmAdd(film, index, (double)v.x, (double)v.y, (double)v.z);
+    }
+
+    // Warp-aggregated append: one atomic per warp, lanes get consecutive slots.
+    MCRT_D uint32_t warpAppend(uint32_t* counter, bool pred)
+    {
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, pred); // callers keep the warp converged
+        if (!pred) return 0xFFFFFFFFu;
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        return base + __popc(mask & ((1u << lane) - 1u));
+    }
+
+    MCRT_D void flushStats(Counters* c, const TraceCounters& cnt, unsigned long long rays, bool shadow, uint32_t overflow)
+    {
+        // block-level reduction through warp shuffles, then one atomic per warp
+        unsigned long long b = cnt.box_tests, p = cnt.prim_tests, r = rays;
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            b += __shfl_down_sync(0xFFFFFFFFu, b, off);
+            p += __shfl_down_sync(0xFFFFFFFFu, p, off);
+            r += __shfl_down_sync(0xFFFFFFFFu, r, off);
+        }
+        if ((threadIdx.x & 31u) == 0)
+        {
+            if (b) atomicAdd(&c->box_tests, b);
+            if (p) atomicAdd(&c->prim_tests, p);
+            if (r) atomicAdd(shadow ? &c->shadow_rays : &c->extension_rays, r);
+        }
+        if (overflow) atomicOr(&c->traversal_overflow, 1u);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Camera ray for (pixel, sample): camera.cpp:66-95
+    template <class R>
+    MCRT_D void cameraRay(const DeviceCamera<R>& c, R scene_ior, uint32_t pixel, const SamplerState& smp,
+                          V3<R>& start, V3<R>& direction)
+    {
+        const uint32_t x = pixel % c.width, y = pixel / c.width;
+        R pixel_size = c.sensor_width / R(c.width);
+        R half_w = R(c.width) * R(0.5), half_h = R(c.height) * R(0.5);
+        R u[2];
+        samplerGet<R, DIM_PIXEL, 2>(smp, u);
+        R px = R(x) + u[0], py = R(y) + u[1];
+        R lx = pixel_size * (half_w - px), ly = pixel_size * (half_h - py);
+        direction = normalize(c.forward * c.focal_length + c.left * lx + c.up * ly);
+        start = c.eye;
+        if (c.thin_lens)
+        {
+            R ul[2];
+            samplerGet<R, DIM_LENS, 2>(smp, ul);
+            // Sampling::uniformDisk, sampling.hpp:30-34
+            R azimuth = ul[1] * Consts<R>::TWO_PI;
+            R sn, cs;
+            msincos(azimuth, &sn, &cs);
+            R su = msqrt(ul[0]);
+            R ax = (cs * su) * c.aperture_radius, ay = (sn * su) * c.aperture_radius;
+            V3<R> focus_point = start + direction * (c.focus_distance / dot(direction, c.forward));
+            V3<R> s2 = c.eye + c.left * ax + c.up * ay;
+            direction = normalize(focus_point - s2);
+            start = s2;
+        }
+    }
+
+    template <class R>
+    __global__ void __launch_bounds__(256) k_generate(WaveParams<R> p, int next)
+    {
+        Counters* c = p.counters;
+        const uint32_t n_next = c->n_next;
+        const unsigned long long remaining = c->total_work - c->next_work;
+        const uint32_t room = p.capacity - n_next;
+        const uint32_t count = remaining < (unsigned long long)room ? (uint32_t)remaining : room;
+        if (blockIdx.x == 0 && threadIdx.x == 0) c->n_gen = count;
+        const unsigned long long base_work = c->next_work;
+        const PathBuffer<R>& out = p.buf[next];
+
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x)
+        {
+            const unsigned long long w = base_work + j;
+            uint32_t pixel, sample, film_index;
+            V3<R> start, direction;
+            if (p.user_rays)
+            {
+                pixel = p.user_pixel[w];
+                sample = p.user_sample[w];
+                film_index = (uint32_t)w;
+                const double* r = p.user_rays + 6 * w;
+                start = V3<R>((R)r[0], (R)r[1], (R)r[2]);
+                direction = V3<R>((R)r[3], (R)r[4], (R)r[5]);
+            }
+            else
+            {
+                // sample-major over this rank's pixels: adjacent lanes = adjacent pixels
+                const uint32_t local = (uint32_t)(w % p.n_pixels);
+                sample = (uint32_t)(w / p.n_pixels);
+                pixel = p.first_pixel + local;
+                film_index = local;
+                SamplerState smp = SamplerState::make(p.global_seed, pixel, sample, 0u);
+                cameraRay(p.camera, p.scene.scene_ior, pixel, smp, start, direction);
+            }
+            const uint32_t slot = n_next + j;
+            out.ray_o[slot] = V4<R>(start, p.scene.scene_ior);
+            out.ray_d[slot] = V4<R>(direction, R(1));
+            out.thr[slot] = V4<R>(R(1), R(1), R(1), R(0));
+            out.iors_a[slot] = V4<R>(R(0), R(0), R(0), R(0));
+            out.meta[slot] = make_uint4(pixel, sample, 0u, 0u);
+            out.meta2[slot] = make_uint4(NO_PRIM, 1u, film_index, NO_PRIM);
+        }
+    }
+
+    inline __global__ void k_advance(Counters* c)
+    {
+        c->n_cur = c->n_next + c->n_gen;
+        c->next_work += c->n_gen;
+        c->paths += c->n_gen;
+        c->n_next = 0;
+        c->n_gen = 0;
+        c->n_shadow = 0;
+        c->n_knn = 0;
+    }
+
+    template <class R>
+    __global__ void __launch_bounds__(256) k_extend(WaveParams<R> p, int cur)
+    {
+        const uint32_t n = p.counters->n_cur;
+        const PathBuffer<R>& in = p.buf[cur];
+        TraceCounters cnt = { 0u, 0u };
+        uint32_t overflow = 0;
+        unsigned long long rays = 0;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        {
+            const V4<R> ro = in.ray_o[i];
+            const V4<R> rd = in.ray_d[i];
+            uint32_t skip = NO_PRIM;
+            if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
+            Hit<R> h = traceClosest(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
+            p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
+            rays++;
+        }
+        flushStats(p.counters, cnt, rays, false, overflow);
+    }
+
+    // Light sample: Surface::operator()(u,v) and Surface::normal (triangle.cpp:93-102,
+    // sphere.cpp:37-49)
+    template <class R>
+    MCRT_D void sampleLightPoint(const Light<R>& l, R u, R v, V3<R>& pos, V3<R>& normal)
+    {
+        if (l.type == PRIM_TRIANGLE)
+        {
+            R su = msqrt(u);
+            pos = (R(1) - su) * l.p0 + (R(1) - v) * su * l.p1 + v * su * l.p2;
+            normal = l.normal;
+        }
+        else
+        {
+            R z = R(1) - R(2) * u;
+            R r = msqrt(R(1) - pow2(z));
+            R phi = Consts<R>::TWO_PI * v;
+            R sn, cs;
+            msincos(phi, &sn, &cs);
+            pos = l.p0 + l.p1.x * V3<R>(r * cs, r * sn, z);
+            normal = (pos - l.p0) / l.p1.x;
+        }
+    }
+
+    template <class R> MCRT_D R powerHeuristic(R a_pdf, R b_pdf)
+    {
+        R a2 = a_pdf * a_pdf;
+        return a2 / (a2 + b_pdf * b_pdf);
+    }
+
+    // Scene::skyColor, scene.cpp:219-223
+    template <class R> MCRT_D V3<R> skyColor(const V3<R>& dir)
+    {
+        R d = R(0) * dir.x + R(1) * dir.y + R(0) * dir.z;
+        R fy = (R(1) + masin(d) / Consts<R>::PI) / R(2);
+        return mix(V3<R>(R(1), R(0.5), R(0)), V3<R>(R(0), R(0.5), R(1)), fy);
+    }
+
+    template <class R>
+    __global__ void __launch_bounds__(128) k_shade(WaveParams<R> p, int cur)
+    {
+        Counters* c = p.counters;
+        const uint32_t n = c->n_cur;
+        const PathBuffer<R>& in = p.buf[cur];
+        const PathBuffer<R>& out = p.buf[cur ^ 1];
+        const DeviceScene<R>& sc = p.scene;
+        uint32_t local_max_depth = 0;
+        uint32_t stack_overflows = 0;
+
+        const uint32_t n_rounded = (n + 31u) & ~31u; // keep warps converged for the ballots
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x)
+        {
+            bool alive = i < n;
+            bool want_shadow = false;
+
+            PathRay<R> ray, nray;
+            V3<R> throughput;
+            uint4 meta, meta2;
+            R ls_bsdf_pdf = R(0), ls_select = R(0);
+            uint32_t ls_light = NO_PRIM, ior_count = 1, hit_prim = NO_PRIM;
+            R iors[IOR_STACK_CAPACITY];
+            // shadow candidate
+            V3<R> sh_o, sh_d, sh_k;
+            R sh_bsdf_pdf = R(0), sh_area_cos = R(0), sh_select = R(0);
+            uint32_t sh_light = NO_PRIM;
+
+            if (alive)
+            {
+                const V4<R> ro = in.ray_o[i], rd = in.ray_d[i], th = in.thr[i], hv = p.hits[i];
+                meta = in.meta[i]; meta2 = in.meta2[i];
+                ray.start = ro.xyz(); ray.medium_ior = ro.w;
+                ray.direction = rd.xyz(); ray.refraction_scale = rd.w;
+                throughput = th.xyz(); ls_bsdf_pdf = th.w;
+                ray.depth = meta.z & 0xFFFFu; ray.diffuse_depth = meta.z >> 16;
+                ray.refraction_level = (int32_t)meta.w;
+                ls_light = meta2.x;
+                ior_count = meta2.y & 0xFFu;
+                ray.dirac_delta = (meta2.y >> 8) & 1u;
+                ray.refraction = false;
+                const uint32_t film_index = meta2.z;
+
+                const V4<R> ia_ = in.iors_a[i];
+                ls_select = ia_.x;
+                iors[0] = sc.scene_ior;
+                if (ior_count > 1)
+                {
+                    iors[1] = ia_.y; iors[2] = ia_.z; iors[3] = ia_.w;
+                    if (ior_count > 4)
+                    {
+                        const V4<R> ib_ = in.iors_b[i];
+                        iors[4] = ib_.x; iors[5] = ib_.y; iors[6] = ib_.z; iors[7] = ib_.w;
+                    }
+                }
+
+                if (ray.depth > local_max_depth) local_max_depth = ray.depth;
+
+                Hit<R> hit;
+                hit.t = hv.x; hit.u = hv.y; hit.v = hv.z;
+                hit.prim = hv.w < R(0) ? NO_PRIM : (uint32_t)hv.w;
+                hit_prim = hit.prim;
+
+                if (hit.prim == NO_PRIM)
+                {
+                    // path-tracer.cpp:27-30; the photon mapper adds no sky (photon-mapper.cpp:292-295)
+                    if (p.integrator == 0) filmAddV(p.film, film_index, skyColor(ray.direction) * throughput);
+                    alive = false;
+                }
+                else
+                {
+                    // Sampler::shuffle() was called depth+1 times (path-tracer.cpp:23)
+                    const SamplerState smp = SamplerState::make(p.global_seed, meta.x, meta.y, ray.depth + 1u);
+
+                    // RefractionHistory::externalIOR, ray.cpp:95-98
+                    int ext_idx = ray.refraction_level - 1;
+                    ext_idx = ext_idx < 0 ? 0 : (ext_idx > (int)ior_count - 1 ? (int)ior_count - 1 : ext_idx);
+                    const R external_ior = iors[ext_idx];
+
+                    Interaction<R> ia;
+                    buildInteraction(ia, sc, hit, ray, external_ior, smp);
+                    const Material<R>& m = *ia.material;
+                    const PrimShade<R> ps = sc.shade[hit.prim];
+
+                    // ---- Integrator::sampleEmissive, integrator.cpp:93-110
+                    if ((m.flags & MAT_EMISSIVE) && !ia.inside)
+                    {
+                        if (ray.depth == 0 || ray.dirac_delta)
+                        {
+                            filmAddV(p.film, film_index, m.emittance * throughput);
+                        }
+                        else if (ls_light == hit.prim)
+                        {
+                            R cos_light_theta = dot(ia.out, ia.normal);
+                            R light_pdf = pow2(ia.t) / (ps.area * cos_light_theta);
+                            R mis_weight = powerHeuristic(ls_bsdf_pdf, light_pdf);
+                            filmAddV(p.film, film_index, (mis_weight * m.emittance / ls_select) * throughput);
+                        }
+                    }
+
+                    // ---- Integrator::sampleDirect up to the visibility query, integrator.cpp:31-66
+                    if (sc.n_lights == 0 || (m.flags & MAT_DIRAC_DELTA))
+                    {
+                        ls_light = NO_PRIM;
+                    }
+                    else
+                    {
+                        R u[3];
+                        samplerGet<R, DIM_LIGHT, 3>(smp, u);
+                        // Sampling::weightedIdx, sampling.hpp:13-28
+                        uint32_t left = 0, right = sc.n_lights - 1;
+                        while (left < right)
+                        {
+                            uint32_t middle = (left + right) / 2;
+                            if (sc.lights[middle].cdf < u[2]) left = middle + 1; else right = middle;
+                        }
+                        const Light<R>& L = sc.lights[left];
+                        ls_select = L.cdf;
+                        if (left > 0) ls_select -= sc.lights[left - 1].cdf;
+                        ls_light = L.prim;
+
+                        V3<R> light_pos, light_normal;
+                        sampleLightPoint(L, u[0], u[1], light_pos, light_normal);
+                        V3<R> s_start = ia.position + ia.normal * p.ray_eps;
+                        V3<R> s_dir = normalize(light_pos - s_start);
+                        R cos_light_theta = dot(-s_dir, light_normal);
+                        if (cos_light_theta > R(0))
+                        {
+                            bool ok = true;
+                            R cos_theta = dot(s_dir, ia.normal);
+                            if (cos_theta <= R(0))
+                            {
+                                if ((m.flags & MAT_OPAQUE) || cos_theta == R(0)) ok = false;
+                                else
+                                {
+                                    s_start = ia.position - ia.normal * p.ray_eps;
+                                    s_dir = normalize(light_pos - s_start);
+                                }
+                            }
+                            if (ok)
+                            {
+                                V3<R> bsdf_absIdotN; R bsdf_pdf;
+                                if (ia.bsdfWorld(bsdf_absIdotN, s_dir, bsdf_pdf))
+                                {
+                                    want_shadow = true;
+                                    sh_o = s_start; sh_d = s_dir;
+                                    sh_k = bsdf_absIdotN * L.emittance * throughput;
+                                    sh_bsdf_pdf = bsdf_pdf;
+                                    sh_area_cos = L.area * cos_light_theta;
+                                    sh_select = ls_select;
+                                    sh_light = L.prim;
+                                }
+                            }
+                        }
+                    }
+
+                    // ---- Interaction::sampleBSDF, throughput, absorb: path-tracer.cpp:37-47
+                    V3<R> bsdf_absIdotN;
+                    if (!sampleBSDF(ia, ray, smp, p.ray_eps, false, bsdf_absIdotN, ls_bsdf_pdf, nray))
+                    {
+                        alive = false;
+                    }
+                    else
+                    {
+                        throughput *= bsdf_absIdotN / ls_bsdf_pdf;
+                        // Integrator::absorb, integrator.cpp:112-129
+                        R survive = compMax(throughput) * nray.refraction_scale;
+                        if (survive == R(0))
+                        {
+                            alive = false;
+                        }
+                        else if (nray.diffuse_depth > 3u || nray.depth > 16u)
+                        {
+                            survive = gmin(R(0.95), survive);
+                            R ua;
+                            samplerGet<R, DIM_ABSORB, 1>(smp, &ua);
+                            if (survive <= ua) alive = false;
+                            else throughput /= survive;
+                        }
+                    }
+
+                    if (alive)
+                    {
+                        // RefractionHistory::update, ray.cpp:80-93
+                        if (nray.refraction_level > 0)
+                        {
+                            if (nray.refraction_level == (int32_t)ior_count)
+                            {
+                                if (ior_count < (uint32_t)IOR_STACK_CAPACITY) iors[ior_count++] = nray.medium_ior;
+                                else stack_overflows++;
+                            }
+                            else if (nray.refraction_level < (int32_t)ior_count - 1)
+                            {
+                                ior_count--;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // ---- compaction: survivors → next path buffer, NEE candidates → shadow queue
+            const uint32_t slot = warpAppend(&c->n_next, alive);
+            if (alive)
+            {
+                out.ray_o[slot] = V4<R>(nray.start, nray.medium_ior);
+                out.ray_d[slot] = V4<R>(nray.direction, nray.refraction_scale);
+                out.thr[slot] = V4<R>(throughput, ls_bsdf_pdf);
+                out.iors_a[slot] = V4<R>(ls_select, iors[1], iors[2], iors[3]);
+                if (ior_count > 4) out.iors_b[slot] = V4<R>(iors[4], iors[5], iors[6], iors[7]);
+                out.meta[slot] = make_uint4(meta.x, meta.y, (nray.depth & 0xFFFFu) | (nray.diffuse_depth << 16),
+                                            (uint32_t)nray.refraction_level);
+                out.meta2[slot] = make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
+                                             sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
+            }
+            const uint32_t sslot = warpAppend(&c->n_shadow, want_shadow);
+            if (want_shadow)
+            {
+                p.shadow.o[sslot] = V4<R>(sh_o, sh_bsdf_pdf);
+                p.shadow.d[sslot] = V4<R>(sh_d, sh_area_cos);
+                p.shadow.k[sslot] = V4<R>(sh_k, sh_select);
+                p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
+                                                  sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, 0u);
+            }
+        }
+
+        if (local_max_depth) atomicMax(&c->max_depth, local_max_depth);
+        if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
+    }
+
+    template <class R>
+    __global__ void __launch_bounds__(256) k_shadow(WaveParams<R> p)
+    {
+        const uint32_t n = p.counters->n_shadow;
+        TraceCounters cnt = { 0u, 0u };
+        uint32_t overflow = 0;
+        unsigned long long rays = 0;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        {
+            const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
+            const uint4 sm = p.shadow.meta[i];
+            Hit<R> h = traceClosest(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            rays++;
+            // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
+            if (h.prim == sm.x)
+            {
+                const V4<R> sk = p.shadow.k[i];
+                R light_pdf = pow2(h.t) / sd.w;
+                R mis_weight = powerHeuristic(light_pdf, so.w);
+                filmAddV(p.film, sm.y, sk.xyz() * (mis_weight / (light_pdf * sk.w)));
+            }
+        }
+        flushStats(p.counters, cnt, rays, true, overflow);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Batched Scene::intersect on caller rays (mcrt_trace_closest)
+    template <class R>
+    __global__ void __launch_bounds__(256) k_trace_user(DeviceScene<R> sc, const double* rays6, size_t n, double* out_tuv,
+                                                        uint32_t* out_prim, Counters* c)
+    {
+        TraceCounters cnt = { 0u, 0u };
+        uint32_t overflow = 0;
+        unsigned long long rays = 0;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        {
+            const double* r = rays6 + 6 * i;
+            Hit<R> h = traceClosest(sc, V3<R>((R)r[0], (R)r[1], (R)r[2]), V3<R>((R)r[3], (R)r[4], (R)r[5]), NO_PRIM, cnt, overflow);
+            out_tuv[3 * i + 0] = (double)h.t; out_tuv[3 * i + 1] = (double)h.u; out_tuv[3 * i + 2] = (double)h.v;
+            out_prim[i] = h.prim;
+            rays++;
+        }
+        flushStats(c, cnt, rays, false, overflow);
+    }
+
+    // Film::Splat::get for the box filter: mean of the samples, clamped at 0 (film.cpp:106-113)
+    inline __global__ void k_resolve_film(const double* film, double* out, size_t n_values, double weight)
+    {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x)
+        {
+            // res / w with w = spp (every sample deposits weight 1), then glm::max(., 0.0)
+            double v = film[i] / weight;
+            out[i] = (v < 0.0) ? 0.0 : v;
+        }
+    }
+}

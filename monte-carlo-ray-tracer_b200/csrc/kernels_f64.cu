@@ -1,0 +1,35 @@
+// Parity mode: float64, reference operation order. Compiled with --fmad=false (the reference's
+// CPU build performs no FMA contraction, /root/reference/CMakeLists.txt:16-21).
+#define MCRT_REAL double
+#include "kernels_impl.cuh"
+
+namespace mcrt
+{
+    void launchAdvance(Counters* c, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(c); }
+
+    void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s)
+    {
+        k_resolve_film<<<grid, 256, 0, s>>>(film, out, n_values, weight);
+    }
+
+    __global__ void k_sampler_stream(const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles,
+                                     uint32_t global_seed, uint32_t* out)
+    {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        {
+            SamplerState s = SamplerState::make(global_seed, pixel[i], sample[i], n_shuffles);
+            uint32_t raw[7];
+            s.raw<0x7Fu>(raw);
+            for (int d = 0; d < 7; d++) out[7 * i + d] = raw[d];
+        }
+    }
+
+    void launchSamplerStream(const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles,
+                             uint32_t global_seed, uint32_t* out, cudaStream_t s)
+    {
+        int grid = (int)((n + 255) / 256);
+        if (grid > 1184) grid = 1184;
+        if (grid < 1) grid = 1;
+        k_sampler_stream<<<grid, 256, 0, s>>>(pixel, sample, n, n_shuffles, global_seed, out);
+    }
+}

@@ -1,0 +1,27 @@
+// Shared body of kernels_f64.cu / kernels_f32.cu: defines Launch<MCRT_REAL>.
+#include "launch.h"
+
+namespace mcrt
+{
+    template <> void Launch<MCRT_REAL>::generate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
+    {
+        k_generate<MCRT_REAL><<<grid, 256, 0, s>>>(p, next);
+    }
+    template <> void Launch<MCRT_REAL>::extend(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
+    {
+        k_extend<MCRT_REAL><<<grid, 256, 0, s>>>(p, cur);
+    }
+    template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
+    {
+        k_shade<MCRT_REAL><<<grid * 2, 128, 0, s>>>(p, cur);
+    }
+    template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
+    {
+        k_shadow<MCRT_REAL><<<grid, 256, 0, s>>>(p);
+    }
+    template <> void Launch<MCRT_REAL>::traceUser(const DeviceScene<MCRT_REAL>& sc, const double* rays6, size_t n,
+                                                  double* out_tuv, uint32_t* out_prim, Counters* c, int grid, cudaStream_t s)
+    {
+        k_trace_user<MCRT_REAL><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c);
+    }
+}

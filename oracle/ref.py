@@ -1,0 +1,146 @@
+"""ORACLE / TEST INFRASTRUCTURE — ctypes binding of oracle/_ref/libmcrt_ref.so (the unmodified
+reference compiled by oracle/build_ref.py). Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; the product never does."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libmcrt_ref.so")
+SCENES_DIR = os.path.join(HERE, "_ref", "scenes")
+REFERENCE_SCENES_DIR = "/root/reference/scenes"
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def scenes_dir():
+    """Full asset tree when the reference checkout is present, else the copies made by build_ref."""
+    return REFERENCE_SCENES_DIR if os.path.isdir(REFERENCE_SCENES_DIR) else SCENES_DIR
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libmcrt_ref.so missing: run python oracle/build_ref.py")
+        L = C.CDLL(LIB_PATH)
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_set_seed.argtypes = [C.c_uint32]
+        L.ref_get_seed.restype = C.c_uint32
+        L.ref_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 6
+        L.ref_render.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ref_sample_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.ref_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_sampler_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+        L.ref_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_export_pack.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_fresnel_dielectric.restype = C.c_double
+        L.ref_fresnel_dielectric.argtypes = [C.c_double] * 3
+        L.ref_fresnel_conductor.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.ref_ggx_reflection.restype = C.c_double
+        L.ref_ggx_reflection.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        L.ref_ggx_transmission.restype = C.c_double
+        L.ref_ggx_transmission.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        L.ref_ggx_visible_microfacet.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def set_seed(seed):
+    lib().ref_set_seed(seed & 0xFFFFFFFF)
+
+
+class RefScene:
+    """A reference Camera (+ PathTracer or PhotonMapper) built from a scene JSON with overrides."""
+
+    def __init__(self, scene_file, overrides=None, camera_idx=0, photon_map=False, scenes=None):
+        err = C.create_string_buffer(512)
+        self.h = lib().ref_open((scenes or scenes_dir()).encode(), scene_file.encode(),
+                                json.dumps(overrides or {}).encode(), camera_idx, int(photon_map), err, 512)
+        if not self.h:
+            raise RuntimeError("ref_open failed: " + err.value.decode())
+        v = [C.c_uint32() for _ in range(6)]
+        lib().ref_info(self.h, *[C.byref(x) for x in v])
+        self.width, self.height, self.sqrtspp, self.n_prims, self.n_nodes, self.n_lights = [x.value for x in v]
+
+    def close(self):
+        if self.h:
+            lib().ref_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, threads=1, y0=0, y1=None):
+        """-> (rgb float64 [rows, W, 3], seconds, total_rays, shadow_rays)"""
+        y1 = self.height if y1 is None else y1
+        out = np.zeros((y1 - y0, self.width, 3), dtype=np.float64)
+        sec, rays, sh = C.c_double(), C.c_uint64(), C.c_uint64()
+        rc = lib().ref_render(self.h, threads, y0, y1, _p(out), C.byref(sec), C.byref(rays), C.byref(sh))
+        if rc:
+            raise RuntimeError("ref_render failed")
+        return out, sec.value, rays.value, sh.value
+
+    def sample_pixels(self, pixel, sample, radiance=True, rays=True):
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        n = len(pixel)
+        rgb = np.zeros((n, 3)) if radiance else None
+        r6 = np.zeros((n, 6)) if rays else None
+        lib().ref_sample_pixels(self.h, _p(pixel), _p(sample), n, _p(rgb), _p(r6))
+        return rgb, r6
+
+    def sample_rays(self, rays6, pixel, sample):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        rgb = np.zeros((len(pixel), 3))
+        lib().ref_sample_rays(self.h, _p(rays6), _p(pixel), _p(sample), len(pixel), _p(rgb))
+        return rgb
+
+    def trace(self, rays6):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        n = len(rays6)
+        t = np.zeros(n); prim = np.zeros(n, dtype=np.uint32); uv = np.zeros((n, 2)); ip = np.zeros(n, dtype=np.uint8)
+        lib().ref_trace(self.h, _p(rays6), n, _p(t), _p(prim), _p(uv), _p(ip))
+        return t, prim, uv, ip
+
+    def knn(self, which, points, k):
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        n = len(points)
+        ph = np.zeros((n, k, 8), dtype=np.float32); d2 = np.full((n, k), np.inf); cnt = np.zeros(n, dtype=np.uint32)
+        rc = lib().ref_knn(self.h, which, _p(points), n, k, _p(ph), _p(d2), _p(cnt))
+        if rc:
+            raise RuntimeError("ref_knn: scene was not opened with photon_map=True")
+        return ph, d2, cnt
+
+    def export_pack(self, path):
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        if lib().ref_export_pack(self.h, path.encode()):
+            raise RuntimeError("ref_export_pack failed")
+        return path
+
+
+def sampler_stream(pixel, sample, n_shuffles):
+    pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+    sample = np.ascontiguousarray(sample, dtype=np.uint32)
+    out = np.zeros((len(pixel), 7), dtype=np.uint32)
+    lib().ref_sampler_stream(_p(pixel), _p(sample), len(pixel), n_shuffles, _p(out))
+    return out

@@ -1,0 +1,147 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.py from /root/reference). Run in the build container only; the GPU box has no
+/root/reference and just reads the files this script wrote.
+
+For every case: a scene pack (flattened Scene/BVH/materials/lights/camera as the reference built
+them) and an .npz with reference outputs at the pinned seed:
+    image        Film::scan of a full Camera render (1 thread)                     [H, W, 3] f64
+    ps_pixel/ps_sample/ps_rays/ps_rgb
+                 random (pixel, sample) pairs: camera ray of Camera::samplePixel and the radiance
+                 Integrator::sampleRay returned for it
+    tr_rays/tr_t/tr_prim/tr_uv/tr_interp
+                 Scene::intersect on camera rays + random rays through the scene bounds
+    total_rays/shadow_rays   Scene::intersect call counts of the full render
+plus sampler_kat.npz (Sampler streams) and bsdf_kat.npz (Fresnel / GGX values).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref  # noqa: E402
+
+SEED = 0x12345678
+
+# id -> (scene json, overrides, photon_map)
+CASES = {
+    # BASELINE config 1 exactly: hexagon_room_diffuse 256x256, 4 spp, binary_sah/16
+    "c1_hexagon_diffuse_256": ("hexagon_room_diffuse.json",
+                               dict(width=256, height=256, sqrtspp=2, bvh_type="binary_sah", bins_per_axis=16), False),
+    # BASELINE config 2 scene/BVH, down-scaled: glass, scene ior 1.75, triangle quad light
+    "c2_hexagon_room_96": ("hexagon_room.json",
+                           dict(width=96, height=54, sqrtspp=2, bvh_type="quaternary_sah"), False),
+    # octree BVH (the shipped default) on the same scene
+    "hexagon_room_octree_64": ("hexagon_room.json", dict(width=64, height=48, sqrtspp=1), False),
+    "oren_nayar_64": ("oren_nayar_test.json", dict(width=64, height=48, sqrtspp=2), False),
+    "ggx_64": ("ggx_test.json", dict(width=64, height=48, sqrtspp=2), False),
+    "ior_test_nobvh_64": ("ior_test.json", dict(width=64, height=48, sqrtspp=2), False),
+    "quadric_64": ("quadric.json", dict(width=64, height=48, sqrtspp=2), False),
+    "veach_mis_64": ("veach_mis.json", dict(width=64, height=48, sqrtspp=2), False),
+    "metals_64": ("metals.json", dict(width=64, height=48, sqrtspp=2), False),
+}
+
+
+def make_case(cid, scene_file, overrides, photon_map, rng):
+    ref.set_seed(SEED)
+    s = ref.RefScene(scene_file, overrides, photon_map=photon_map)
+    pack = os.path.join(HERE, cid + ".mcrtpack")
+    s.export_pack(pack)
+
+    image, _, total_rays, shadow_rays = s.render(threads=1)
+
+    n_ps = 4096
+    spp = s.sqrtspp ** 2
+    ps_pixel = rng.integers(0, s.width * s.height, n_ps).astype(np.uint32)
+    ps_sample = rng.integers(0, spp, n_ps).astype(np.uint32)
+    ps_rgb, ps_rays = s.sample_pixels(ps_pixel, ps_sample)
+
+    # rays for the traversal KAT: the camera rays above + random segments through the camera-visible
+    # region (origins/targets jittered around primary hit points)
+    t0, prim0, _, _ = s.trace(ps_rays)
+    hit = prim0 != 0xFFFFFFFF
+    pts = ps_rays[hit, :3] + ps_rays[hit, 3:] * t0[hit, None]
+    if len(pts) >= 2:
+        a = pts[rng.integers(0, len(pts), 4096)] + rng.normal(0, 0.05, (4096, 3))
+        b = pts[rng.integers(0, len(pts), 4096)] + rng.normal(0, 0.05, (4096, 3))
+        d = b - a
+        nrm = np.linalg.norm(d, axis=1, keepdims=True)
+        ok = nrm[:, 0] > 1e-6
+        extra = np.concatenate([a[ok], d[ok] / nrm[ok]], axis=1)
+        tr_rays = np.concatenate([ps_rays, extra], axis=0)
+    else:
+        tr_rays = ps_rays
+    tr_t, tr_prim, tr_uv, tr_interp = s.trace(tr_rays)
+
+    np.savez_compressed(os.path.join(HERE, cid + ".npz"),
+                        seed=np.uint32(SEED), width=np.uint32(s.width), height=np.uint32(s.height),
+                        sqrtspp=np.uint32(s.sqrtspp), image=image,
+                        ps_pixel=ps_pixel, ps_sample=ps_sample, ps_rays=ps_rays, ps_rgb=ps_rgb,
+                        tr_rays=tr_rays, tr_t=tr_t, tr_prim=tr_prim, tr_uv=tr_uv, tr_interp=tr_interp,
+                        total_rays=np.uint64(total_rays), shadow_rays=np.uint64(shadow_rays))
+    print(f"{cid}: prims={s.n_prims} nodes={s.n_nodes} lights={s.n_lights} rays={total_rays} "
+          f"(shadow {shadow_rays}) mean={image.mean():.6f} miss={np.mean(~hit):.3f}")
+    s.close()
+
+
+def make_sampler_kat(rng):
+    ref.set_seed(SEED)
+    n = 8192
+    pixel = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    pixel[:64] = np.arange(64)
+    sample = rng.integers(0, 2 ** 16, n).astype(np.uint32)
+    sample[:64] = np.arange(64)
+    sample[64:96] = 0xFFFFFFFF - np.arange(32)
+    out = {}
+    for ns in (0, 1, 2, 5, 17, 81):
+        out[f"stream_{ns}"] = ref.sampler_stream(pixel, sample, ns)
+    np.savez_compressed(os.path.join(HERE, "sampler_kat.npz"), seed=np.uint32(SEED), pixel=pixel, sample=sample, **out)
+    print("sampler_kat: ", {k: v.shape for k, v in out.items()})
+
+
+def make_bsdf_kat(rng):
+    import ctypes as C
+    L = ref.lib()
+    n = 2048
+    n1 = rng.uniform(1.0, 2.5, n); n2 = rng.uniform(1.0, 3.5, n); c = rng.uniform(0.0, 1.0, n)
+    fd = np.array([L.ref_fresnel_dielectric(a, b, x) for a, b, x in zip(n1, n2, c)])
+    real = rng.uniform(0.1, 3.0, (n, 3)); imag = rng.uniform(0.5, 8.0, (n, 3))
+    fc = np.zeros((n, 3))
+    for i in range(n):
+        L.ref_fresnel_conductor(n1[i], real[i].ctypes.data, imag[i].ctypes.data, c[i], fc[i].ctypes.data)
+
+    def hemi(k, sign=1.0):
+        v = rng.normal(size=(k, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v[:, 2] = sign * np.abs(v[:, 2]) + sign * 1e-3
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    wo = hemi(n); wi_r = hemi(n); wi_t = hemi(n, -1.0)
+    alpha = rng.uniform(0.02, 0.8, n)
+    gr = np.zeros(n); gr_pdf = np.zeros(n); gt = np.zeros(n); gt_pdf = np.zeros(n); vm = np.zeros((n, 3))
+    uv = rng.uniform(0, 1, (n, 2))
+    pdf = C.c_double()
+    for i in range(n):
+        gr[i] = L.ref_ggx_reflection(wi_r[i].ctypes.data, wo[i].ctypes.data, alpha[i], C.byref(pdf)); gr_pdf[i] = pdf.value
+        gt[i] = L.ref_ggx_transmission(wi_t[i].ctypes.data, wo[i].ctypes.data, n1[i], n2[i], alpha[i], C.byref(pdf)); gt_pdf[i] = pdf.value
+        L.ref_ggx_visible_microfacet(uv[i, 0], uv[i, 1], wo[i].ctypes.data, alpha[i], vm[i].ctypes.data)
+    np.savez_compressed(os.path.join(HERE, "bsdf_kat.npz"), n1=n1, n2=n2, cos=c, fresnel_dielectric=fd,
+                        ior_real=real, ior_imag=imag, fresnel_conductor=fc, wo=wo, wi_r=wi_r, wi_t=wi_t,
+                        alpha=alpha, ggx_refl=gr, ggx_refl_pdf=gr_pdf, ggx_trans=gt, ggx_trans_pdf=gt_pdf,
+                        uv=uv, ggx_vndf=vm)
+    print("bsdf_kat: n =", n)
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    rng = np.random.default_rng(20260923)
+    for cid, (scene_file, overrides, pm) in CASES.items():
+        if only and cid not in only:
+            continue
+        make_case(cid, scene_file, overrides, pm, rng)
+    if not only or "sampler_kat" in only:
+        make_sampler_kat(rng)
+    if not only or "bsdf_kat" in only:
+        make_bsdf_kat(rng)
