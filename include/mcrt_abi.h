@@ -161,7 +161,10 @@ typedef struct mcrt_stats {
     uint32_t max_depth;
     uint32_t _pad;
     double gpu_ms_total;       /* CUDA-event time of the render, first launch → last          */
+    /* per-stage sums of CUDA-event times; filled only with option "stage_timing" = 1 */
     double gpu_ms_generate, gpu_ms_extend, gpu_ms_shade, gpu_ms_shadow, gpu_ms_knn;
+    uint64_t extend_launches, shadow_launches;
+    uint64_t shadow_box_tests, shadow_prim_tests; /* k_shadow's share of box_tests / prim_tests */
 } mcrt_stats;
 
 typedef struct mcrt_ctx mcrt_ctx;
@@ -196,6 +199,14 @@ int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint
 int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1,
                          uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
                          int precision, double* out_rgb_dev, mcrt_stats* stats);
+
+/* Interleaved row sharding for multi-GPU renders: renders image rows
+ * y_first + k*y_step for k in [0, n_rows) into out_rgb_dev[k*W + x][3] (device pointer). Every
+ * rank gets statistically identical rows, so per-rank cost is balanced. */
+int mcrt_render_rows_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first,
+                                 uint32_t y_step, uint32_t n_rows, uint32_t sqrtspp,
+                                 uint32_t global_seed, int integrator_kind, int precision,
+                                 double* out_rgb_dev, mcrt_stats* stats);
 
 /* Batched Scene::intersect (scene.cpp:151-176): closest hit per ray. `medium_ior` is not
  * needed by the query. Host buffers. */

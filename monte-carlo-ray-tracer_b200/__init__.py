@@ -25,7 +25,8 @@ NO_PRIM = 0xFFFFFFFF
 
 ABI_SYMBOLS = [
     "mcrt_abi_version", "mcrt_init", "mcrt_destroy", "mcrt_last_error", "mcrt_scene_upload",
-    "mcrt_photon_upload", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_trace_closest",
+    "mcrt_photon_upload", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
+    "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option",
 ]
 
@@ -103,7 +104,9 @@ class Stats(C.Structure):
                 ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ior_stack_overflows", C.c_uint64), ("max_depth", C.c_uint32), ("_pad", C.c_uint32),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_generate", C.c_double), ("gpu_ms_extend", C.c_double),
-                ("gpu_ms_shade", C.c_double), ("gpu_ms_shadow", C.c_double), ("gpu_ms_knn", C.c_double)]
+                ("gpu_ms_shade", C.c_double), ("gpu_ms_shadow", C.c_double), ("gpu_ms_knn", C.c_double),
+                ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("shadow_box_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("_")}
@@ -132,6 +135,8 @@ def lib():
                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_render_rows.argtypes = render_args
         L.mcrt_render_rows_dev.argtypes = render_args
+        L.mcrt_render_rows_strided_dev.argtypes = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
@@ -363,6 +368,17 @@ class Integrator:
                                                camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed,
                                                self.kind, self.precision if precision is None else precision,
                                                C.c_void_p(out_dev_ptr), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    # -- interleaved rows y_first + k*y_step (multi-GPU sharding), framebuffer in HBM
+    def render_rows_strided_dev(self, camera, out_dev_ptr, y_first, y_step, n_rows, sqrtspp=None, precision=None):
+        st = Stats()
+        self._check(lib().mcrt_render_rows_strided_dev(self.ctx, C.byref(camera.rec), y_first, y_step, n_rows,
+                                                       camera.sqrtspp if sqrtspp is None else sqrtspp,
+                                                       self.global_seed, self.kind,
+                                                       self.precision if precision is None else precision,
+                                                       C.c_void_p(out_dev_ptr), C.byref(st)))
         self.last_stats = st.as_dict()
         return self.last_stats
 

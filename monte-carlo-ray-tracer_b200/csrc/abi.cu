@@ -72,6 +72,9 @@ struct mcrt_ctx
 
     PhotonMaps photon;
 
+    std::vector<cudaEvent_t> stage_events; // 5 per wavefront iteration when stage_timing is on
+    std::vector<uint8_t> prim_interpolates; // host copy: ordered prim has vertex normals
+
     // options
     uint32_t pool_paths = 1u << 22;
     int blocks_per_sm = 8;
@@ -384,11 +387,13 @@ namespace
         st->ior_stack_overflows = c.ior_stack_overflows;
         st->max_depth = c.max_depth;
         st->gpu_ms_total = ms;
+        st->shadow_box_tests = c.shadow_box_tests;
+        st->shadow_prim_tests = c.shadow_prim_tests;
     }
 
     // The wavefront loop shared by mcrt_render_rows(_dev) and mcrt_sample_rays.
     template <class R>
-    int runWavefront(mcrt_ctx* ctx, const mcrt_camera* cam, uint32_t first_pixel, uint32_t n_pixels, uint32_t spp,
+    int runWavefront(mcrt_ctx* ctx, const mcrt_camera* cam, uint32_t row_first, uint32_t row_step, uint32_t n_pixels, uint32_t spp,
                      uint64_t total_work, uint32_t global_seed, int integrator, const double* d_user_rays,
                      const uint32_t* d_user_pixel, const uint32_t* d_user_sample, size_t film_pixels,
                      double film_weight, double* out_dev, mcrt_stats* stats)
@@ -410,7 +415,6 @@ namespace
         p.scene = sceneOf<R>(ctx);
         if (cam)
         {
-            for (int k = 0; k < 3; k++) { }
             p.camera.eye = v3<R>(cam->eye); p.camera.forward = v3<R>(cam->forward);
             p.camera.left = v3<R>(cam->left); p.camera.up = v3<R>(cam->up);
             p.camera.focal_length = (R)cam->focal_length; p.camera.sensor_width = (R)cam->sensor_width;
@@ -426,7 +430,8 @@ namespace
         p.capacity = wb.capacity;
         p.global_seed = global_seed;
         p.spp = spp;
-        p.first_pixel = first_pixel;
+        p.row_first = row_first;
+        p.row_step = row_step;
         p.n_pixels = n_pixels;
         p.integrator = (uint32_t)integrator;
         p.ray_eps = Mode<R>::parity ? (R)1e-9 : (R)(ctx->ray_eps_scale * ctx->scene_scale);
@@ -461,7 +466,20 @@ namespace
             for (int k = 0; k < ctx->poll_interval; k++)
             {
                 const int cur = (int)(iterations & 1u);
+                cudaEvent_t* ev = nullptr;
+                if (ctx->stage_timing)
+                {
+                    while (ctx->stage_events.size() < 5 * (iterations + 1))
+                    {
+                        cudaEvent_t e;
+                        CK(cudaEventCreate(&e));
+                        ctx->stage_events.push_back(e);
+                    }
+                    ev = &ctx->stage_events[5 * iterations];
+                    cudaEventRecord(ev[0], s);
+                }
                 Launch<R>::extend(p, cur, grid, s);
+                if (ev) cudaEventRecord(ev[1], s);
                 if (integrator == MCRT_INTEGRATOR_PHOTON)
                 {
                     photonShade<R>(p, pm_args, cur, grid, s);
@@ -471,9 +489,12 @@ namespace
                 {
                     Launch<R>::shade(p, cur, grid, s);
                 }
+                if (ev) cudaEventRecord(ev[2], s);
                 Launch<R>::shadow(p, grid, s);
+                if (ev) cudaEventRecord(ev[3], s);
                 Launch<R>::generate(p, cur ^ 1, grid, s);
                 launchAdvance(ctx->d_counters, s);
+                if (ev) cudaEventRecord(ev[4], s);
                 launches += 5;
                 iterations++;
             }
@@ -501,6 +522,23 @@ namespace
         CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
         const Counters& c = ctx->h_counters[0];
         fillStats(stats, c, iterations, launches, ms);
+        if (stats)
+        {
+            stats->extend_launches = iterations;
+            stats->shadow_launches = iterations;
+            if (ctx->stage_timing)
+            {
+                for (uint64_t it = 0; it < iterations; it++)
+                {
+                    cudaEvent_t* ev = &ctx->stage_events[5 * it];
+                    float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
+                    cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]);
+                    cudaEventElapsedTime(&t23, ev[2], ev[3]); cudaEventElapsedTime(&t34, ev[3], ev[4]);
+                    stats->gpu_ms_extend += t01; stats->gpu_ms_shade += t12;
+                    stats->gpu_ms_shadow += t23; stats->gpu_ms_generate += t34;
+                }
+            }
+        }
         if (c.traversal_overflow)
         {
             ctx->error = "traversal stack/heap overflow: result would differ from the reference";
@@ -509,24 +547,26 @@ namespace
         return MCRT_OK;
     }
 
-    int renderDispatch(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
-                       uint32_t global_seed, int integrator_kind, int precision, double* out_dev, mcrt_stats* stats)
+    int renderDispatch(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step, uint32_t n_rows,
+                       uint32_t sqrtspp, uint32_t global_seed, int integrator_kind, int precision, double* out_dev,
+                       mcrt_stats* stats)
     {
-        if (!camera || y1 <= y0 || y1 > camera->height || sqrtspp == 0 || camera->width == 0)
+        if (!camera || n_rows == 0 || y_step == 0 || sqrtspp == 0 || camera->width == 0 || sqrtspp > 65535u ||
+            (uint64_t)y_first + (uint64_t)(n_rows - 1) * y_step >= camera->height)
         {
             ctx->error = "mcrt_render_rows: invalid camera / row range / sqrtspp";
             return MCRT_ERR_INVALID;
         }
-        const uint64_t n_pixels64 = (uint64_t)camera->width * (y1 - y0);
+        const uint64_t n_pixels64 = (uint64_t)camera->width * n_rows;
         if (n_pixels64 > 0xFFFFFFFFull) { ctx->error = "row block too large"; return MCRT_ERR_INVALID; }
         const uint32_t n_pixels = (uint32_t)n_pixels64;
         const uint32_t spp = sqrtspp * sqrtspp;
         const uint64_t total = (uint64_t)n_pixels * spp;
         if (precision == MCRT_PRECISION_F64)
-            return runWavefront<double>(ctx, camera, y0 * camera->width, n_pixels, spp, total, global_seed, integrator_kind,
+            return runWavefront<double>(ctx, camera, y_first, y_step, n_pixels, spp, total, global_seed, integrator_kind,
                                         nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
         if (precision == MCRT_PRECISION_F32)
-            return runWavefront<float>(ctx, camera, y0 * camera->width, n_pixels, spp, total, global_seed, integrator_kind,
+            return runWavefront<float>(ctx, camera, y_first, y_step, n_pixels, spp, total, global_seed, integrator_kind,
                                        nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
         ctx->error = "unknown precision";
         return MCRT_ERR_INVALID;
@@ -576,6 +616,7 @@ void mcrt_destroy(mcrt_ctx* ctx)
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     for (int i = 0; i < 2; i++) if (ctx->ev_poll[i]) cudaEventDestroy(ctx->ev_poll[i]);
+    for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -593,6 +634,7 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "blocks_per_sm") { if (value < 1 || value > 32) return MCRT_ERR_INVALID; ctx->blocks_per_sm = (int)value; }
     else if (k == "ray_eps_scale") { if (value <= 0) return MCRT_ERR_INVALID; ctx->ray_eps_scale = value; }
     else if (k == "poll_interval") { if (value < 1 || value > 1024) return MCRT_ERR_INVALID; ctx->poll_interval = (int)value; }
+    else if (k == "stage_timing") { ctx->stage_timing = value != 0.0; }
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }
@@ -655,6 +697,9 @@ int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->scene32 = a.dev;
     }
+    ctx->prim_interpolates.assign(s.n_prims, 0);
+    for (uint32_t i = 0; i < s.n_prims; i++)
+        if (s.prim_type[i] == MCRT_PRIM_TRIANGLE && s.tri_vn_index[s.prim_index[i]] >= 0) ctx->prim_interpolates[i] = 1;
     ctx->has_scene = true;
     if (h2d_bytes) *h2d_bytes = bytes;
     return MCRT_OK;
@@ -678,7 +723,18 @@ int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, 
     if (!ctx) return MCRT_ERR_INVALID;
     if (!out_rgb_dev) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
-    return renderDispatch(ctx, camera, y0, y1, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+    if (y1 <= y0) { ctx->error = "empty row range"; return MCRT_ERR_INVALID; }
+    return renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_render_rows_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step,
+                                 uint32_t n_rows, uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
+                                 int precision, double* out_rgb_dev, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!out_rgb_dev) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    return renderDispatch(ctx, camera, y_first, y_step, n_rows, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
 }
 
 int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
@@ -690,7 +746,7 @@ int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint
     const size_t values = (size_t)camera->width * (y1 - y0) * 3;
     double* d_out = nullptr;
     CK(cudaMalloc((void**)&d_out, values * sizeof(double)));
-    int rc = renderDispatch(ctx, camera, y0, y1, sqrtspp, global_seed, integrator_kind, precision, d_out, stats);
+    int rc = renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, d_out, stats);
     if (rc == MCRT_OK)
     {
         cudaError_t e = cudaMemcpy(out_rgb, d_out, values * sizeof(double), cudaMemcpyDeviceToHost);
@@ -718,9 +774,9 @@ int mcrt_sample_rays(mcrt_ctx* ctx, const mcrt_ray* rays, const uint32_t* pixel,
     cudaMemcpyAsync(d_pixel, pixel, n * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_sample, sample, n * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (precision == MCRT_PRECISION_F64)
-        rc = runWavefront<double>(ctx, nullptr, 0, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
+        rc = runWavefront<double>(ctx, nullptr, 0, 1, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
     else if (precision == MCRT_PRECISION_F32)
-        rc = runWavefront<float>(ctx, nullptr, 0, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
+        rc = runWavefront<float>(ctx, nullptr, 0, 1, 0, 1, n, global_seed, integrator_kind, d_rays, d_pixel, d_sample, n, 1.0, d_out, stats);
     else { ctx->error = "unknown precision"; rc = MCRT_ERR_INVALID; }
     if (rc == MCRT_OK && cudaMemcpy(out_rgb, d_out, n * 3 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
     { ctx->error = "copy back failed"; rc = MCRT_ERR_CUDA; }
@@ -761,13 +817,15 @@ int mcrt_trace_closest(mcrt_ctx* ctx, const mcrt_ray* rays, size_t n, int precis
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
     fillStats(stats, ctx->h_counters[0], 0, 1, ms);
-    const bool have_vn = true;
-    (void)have_vn;
     for (size_t i = 0; i < n; i++)
     {
-        hits[i].t = tuv[3 * i]; hits[i].u = tuv[3 * i + 1]; hits[i].v = tuv[3 * i + 2];
+        // Intersection::uv is only set when the triangle has vertex normals (triangle.cpp:57-61)
+        const bool interp = prim[i] != NO_PRIM && ctx->prim_interpolates[prim[i]];
+        hits[i].t = tuv[3 * i];
+        hits[i].u = interp ? tuv[3 * i + 1] : 0.0;
+        hits[i].v = interp ? tuv[3 * i + 2] : 0.0;
         hits[i].prim = prim[i];
-        hits[i].interpolate = 0;
+        hits[i].interpolate = interp ? 1u : 0u;
     }
     if (ctx->h_counters[0].traversal_overflow) { ctx->error = "traversal stack/heap overflow"; return MCRT_ERR_UNSUPPORTED; }
     return MCRT_OK;

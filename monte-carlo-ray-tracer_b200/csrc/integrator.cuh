@@ -32,6 +32,7 @@ namespace mcrt
         unsigned long long next_work, total_work;
         // statistics
         unsigned long long paths, extension_rays, shadow_rays, box_tests, prim_tests, knn_queries;
+        unsigned long long shadow_box_tests, shadow_prim_tests; // the k_shadow share of box/prim tests
         unsigned long long ior_stack_overflows;
         uint32_t traversal_overflow, max_depth;
         uint32_t n_knn, _pad;
@@ -72,8 +73,9 @@ namespace mcrt
         uint32_t capacity;
         uint32_t global_seed;
         uint32_t spp;
-        uint32_t first_pixel;   // y0 * width
-        uint32_t n_pixels;      // pixels in this rank's rows
+        uint32_t row_first;     // first image row of this render
+        uint32_t row_step;      // distance between consecutive rendered rows (1 = contiguous block)
+        uint32_t n_pixels;      // pixels in this render (rows * width)
         uint32_t integrator;    // MCRT_INTEGRATOR_*
         R ray_eps;              // C::EPSILON in parity mode; scale-aware in fast mode
     };
@@ -139,6 +141,8 @@ namespace mcrt
         {
             if (b) atomicAdd(&c->box_tests, b);
             if (p) atomicAdd(&c->prim_tests, p);
+            if (shadow && b) atomicAdd(&c->shadow_box_tests, b);
+            if (shadow && p) atomicAdd(&c->shadow_prim_tests, p);
             if (r) atomicAdd(shadow ? &c->shadow_rays : &c->extension_rays, r);
         }
         if (overflow) atomicOr(&c->traversal_overflow, 1u);
@@ -207,7 +211,8 @@ namespace mcrt
                 // sample-major over this rank's pixels: adjacent lanes = adjacent pixels
                 const uint32_t local = (uint32_t)(w % p.n_pixels);
                 sample = (uint32_t)(w / p.n_pixels);
-                pixel = p.first_pixel + local;
+                const uint32_t row = local / p.camera.width, col = local - row * p.camera.width;
+                pixel = (p.row_first + row * p.row_step) * p.camera.width + col;
                 film_index = local;
                 SamplerState smp = SamplerState::make(p.global_seed, pixel, sample, 0u);
                 cameraRay(p.camera, p.scene.scene_ior, pixel, smp, start, direction);
