@@ -1,0 +1,88 @@
+// See gpu_integrator.hpp. Compile with -fno-access-control against /root/reference/{source,lib/*}.
+#include "gpu_integrator.hpp"
+
+#include "camera/camera.hpp"
+#include "integrator/integrator.hpp"
+#include "integrator/photon-mapper/photon-mapper.hpp"
+#include "sampling/sampler.hpp"
+
+namespace mcrt_host
+{
+    void GpuRenderer::check(int rc, const char* what) const
+    {
+        if (rc != MCRT_OK)
+        {
+            throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " +
+                                     (ctx_ ? mcrt_last_error(ctx_) : "no context"));
+        }
+    }
+
+    GpuRenderer::GpuRenderer(const Camera& camera, int device, int precision)
+        : precision_(precision), integrator_kind_(MCRT_INTEGRATOR_PATH), global_seed_(Sampler::global_seed)
+    {
+        int rc = mcrt_init(device, &ctx_);
+        if (rc != MCRT_OK) throw std::runtime_error("mcrt_init failed: no CUDA device (there is no CPU fallback)");
+
+        FlatScene flat;
+        flattenScene(camera.integrator->scene, flat);
+        mcrt_scene_desc desc = flat.desc();
+        uint64_t bytes = 0;
+        check(mcrt_scene_upload(ctx_, &desc, &bytes), "mcrt_scene_upload");
+        h2d_bytes_ += bytes;
+
+        if (auto* pm = dynamic_cast<const PhotonMapper*>(camera.integrator.get()))
+        {
+            FlatPhotonMap caustic, global;
+            flattenPhotonMap(*pm, 0, caustic);
+            flattenPhotonMap(*pm, 1, global);
+            uint32_t k = 0, dv = 0;
+            photonMapParams(*pm, k, dv);
+            mcrt_photon_map_desc dc = caustic.desc(), dg = global.desc();
+            check(mcrt_photon_upload(ctx_, &dc, &dg, k, dv, &bytes), "mcrt_photon_upload");
+            h2d_bytes_ += bytes;
+            integrator_kind_ = MCRT_INTEGRATOR_PHOTON;
+        }
+    }
+
+    GpuRenderer::~GpuRenderer()
+    {
+        mcrt_destroy(ctx_);
+    }
+
+    std::vector<double> GpuRenderer::renderRows(const Camera& camera, uint32_t y0, uint32_t y1)
+    {
+        // default film only: Filter::box with radius 0.5 deposits each sample into exactly one
+        // pixel with weight 1 (film.cpp:13-17,61-79)
+        if (camera.film.radius != 0.5 || !camera.film.filter_cache.empty())
+        {
+            throw std::runtime_error("GpuRenderer: only the default box film is on the GPU path");
+        }
+        mcrt_camera cam = flattenCamera(camera);
+        std::vector<double> out((size_t)cam.width * (y1 - y0) * 3);
+        check(mcrt_render_rows(ctx_, &cam, y0, y1, (uint32_t)camera.sqrtspp, global_seed_, integrator_kind_,
+                               precision_, out.data(), &stats_), "mcrt_render_rows");
+        return out;
+    }
+
+    void GpuRenderer::sampleImage(Camera& camera)
+    {
+        const uint32_t W = (uint32_t)camera.image.width, H = (uint32_t)camera.image.height;
+        std::vector<double> rgb = renderRows(camera, 0, H);
+        for (uint32_t y = 0; y < H; y++)
+            for (uint32_t x = 0; x < W; x++)
+            {
+                const double* p = &rgb[((size_t)y * W + x) * 3];
+                camera.image(x, y) = glm::dvec3(p[0], p[1], p[2]); // what film.scan(x, y) would return
+            }
+    }
+
+    std::vector<double> GpuRenderer::sampleRays(const std::vector<mcrt_ray>& rays, const std::vector<uint32_t>& pixel,
+                                                const std::vector<uint32_t>& sample)
+    {
+        if (rays.size() != pixel.size() || rays.size() != sample.size()) throw std::invalid_argument("sampleRays: size mismatch");
+        std::vector<double> out(rays.size() * 3);
+        check(mcrt_sample_rays(ctx_, rays.data(), pixel.data(), sample.data(), rays.size(), global_seed_,
+                               integrator_kind_, precision_, out.data(), &stats_), "mcrt_sample_rays");
+        return out;
+    }
+}

@@ -1,0 +1,60 @@
+// GpuPathTracer / GpuPhotonMapper: the reference-side adapters that put the B200 path behind the
+// reference's own Integrator interface (source/integrator/integrator.hpp:7-30).
+//
+//   Camera camera(j, option);                       // unchanged reference code: loads the Scene,
+//                                                   // builds the BVH (+ photon maps) on the CPU
+//   mcrt_host::GpuRenderer gpu(camera);             // flattens + uploads what the reference built
+//   gpu.sampleImage(camera);                        // replaces Camera::sampleImage (camera.cpp:101-145)
+//   camera.saveImage();                             // unchanged: exposure, tonemap, TGA
+//
+// Compiled with -fno-access-control against the reference headers (Camera::integrator, Camera::film
+// and Sampler::global_seed are private there).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mcrt_abi.h"
+#include "exporter.hpp"
+
+class Camera;
+
+namespace mcrt_host
+{
+    class GpuRenderer
+    {
+    public:
+        // Takes the Scene (and photon maps, if the camera was built with a PhotonMapper) that the
+        // reference constructed and uploads them to CUDA device `device`.
+        explicit GpuRenderer(const Camera& camera, int device = 0, int precision = MCRT_PRECISION_F64);
+        ~GpuRenderer();
+        GpuRenderer(const GpuRenderer&) = delete;
+        GpuRenderer& operator=(const GpuRenderer&) = delete;
+
+        // Camera::sampleImage: renders every row and stores Film::scan-equivalent values in
+        // camera.image(x, y). Throws if the camera uses a non-box film (not on the GPU path).
+        void sampleImage(Camera& camera);
+
+        // Rows [y0, y1) as float64 RGB, row-major.
+        std::vector<double> renderRows(const Camera& camera, uint32_t y0, uint32_t y1);
+
+        // Batched Integrator::sampleRay: ray i is sample `sample[i]` of pixel `pixel[i]`.
+        std::vector<double> sampleRays(const std::vector<mcrt_ray>& rays, const std::vector<uint32_t>& pixel,
+                                       const std::vector<uint32_t>& sample);
+
+        const mcrt_stats& lastStats() const { return stats_; }
+        uint64_t uploadedBytes() const { return h2d_bytes_; }
+
+    private:
+        void check(int rc, const char* what) const;
+
+        mcrt_ctx* ctx_ = nullptr;
+        int precision_;
+        int integrator_kind_;
+        uint32_t global_seed_;
+        mcrt_stats stats_{};
+        uint64_t h2d_bytes_ = 0;
+    };
+}
