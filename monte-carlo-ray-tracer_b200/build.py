@@ -18,7 +18,6 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("kernels_f64.cu", ["--fmad=false"]),
     ("kernels_f32.cu", []),
-    ("photon_stub.cu", []),
     ("abi.cu", []),
 ]
 

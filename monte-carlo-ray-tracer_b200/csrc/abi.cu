@@ -9,7 +9,6 @@
 
 #include "mcrt_abi.h"
 #include "launch.h"
-#include "photon.h"
 
 using namespace mcrt;
 
@@ -70,7 +69,13 @@ struct mcrt_ctx
     size_t film_values = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_poll[2] = { nullptr, nullptr };
 
-    PhotonMaps photon;
+    // photon maps (PhotonMapper::caustic_map / global_map) + k-NN query queues
+    bool has_photons = false;
+    std::vector<void*> photon_allocs;
+    DevicePhotonMap photon_map[2];
+    uint32_t k_nearest = 0, direct_visualization = 0;
+    void* knn_queue64 = nullptr; void* knn_queue32 = nullptr;
+    uint32_t knn_capacity64 = 0, knn_capacity32 = 0;
 
     std::vector<cudaEvent_t> stage_events; // 5 per wavefront iteration when stage_timing is on
     std::vector<uint8_t> prim_interpolates; // host copy: ordered prim has vertex normals
@@ -399,7 +404,7 @@ namespace
                      double film_weight, double* out_dev, mcrt_stats* stats)
     {
         if (!ctx->has_scene) { ctx->error = "no scene uploaded"; return MCRT_ERR_NO_SCENE; }
-        if (integrator == MCRT_INTEGRATOR_PHOTON && !ctx->photon.valid)
+        if (integrator == MCRT_INTEGRATOR_PHOTON && !ctx->has_photons)
         {
             ctx->error = "photon-mapped render requested without mcrt_photon_upload";
             return MCRT_ERR_NO_PHOTONS;
@@ -408,7 +413,21 @@ namespace
         int rc;
         if ((rc = ensureWave(ctx, wb, waveAllocsOf<R>(ctx)))) return rc;
         if ((rc = ensureFilm(ctx, film_pixels * 3))) return rc;
-        if (integrator == MCRT_INTEGRATOR_PHOTON && (rc = photonEnsureQueue<R>(ctx->photon, ctx->pool_paths, ctx->error))) return rc;
+        KnnQuery<R>* knn_queue = nullptr;
+        const uint32_t knn_capacity = 2u * ctx->pool_paths; // a path emits at most caustic + global per bounce
+        if (integrator == MCRT_INTEGRATOR_PHOTON)
+        {
+            void*& q = Mode<R>::parity ? ctx->knn_queue64 : ctx->knn_queue32;
+            uint32_t& cap = Mode<R>::parity ? ctx->knn_capacity64 : ctx->knn_capacity32;
+            if (cap != knn_capacity)
+            {
+                if (q) cudaFree(q);
+                q = nullptr; cap = 0;
+                CK(cudaMalloc(&q, (size_t)knn_capacity * sizeof(KnnQuery<R>)));
+                cap = knn_capacity;
+            }
+            knn_queue = static_cast<KnnQuery<R>*>(q);
+        }
 
         WaveParams<R> p;
         std::memset(&p, 0, sizeof(p));
@@ -436,8 +455,14 @@ namespace
         p.integrator = (uint32_t)integrator;
         p.ray_eps = Mode<R>::parity ? (R)1e-9 : (R)(ctx->ray_eps_scale * ctx->scene_scale);
 
-        PhotonLaunchArgs<R> pm_args;
-        if (integrator == MCRT_INTEGRATOR_PHOTON) pm_args = photonLaunchArgs<R>(ctx->photon);
+        if (integrator == MCRT_INTEGRATOR_PHOTON)
+        {
+            p.pm.map[0] = ctx->photon_map[0]; p.pm.map[1] = ctx->photon_map[1];
+            p.pm.queries = knn_queue;
+            p.pm.k_nearest = ctx->k_nearest;
+            p.pm.direct_visualization = ctx->direct_visualization;
+            p.pm.query_capacity = knn_capacity;
+        }
 
         cudaStream_t s = ctx->stream;
         const int grid = ctx->sm_count * ctx->blocks_per_sm;
@@ -482,7 +507,8 @@ namespace
                 if (ev) cudaEventRecord(ev[1], s);
                 if (integrator == MCRT_INTEGRATOR_PHOTON)
                 {
-                    photonShade<R>(p, pm_args, cur, grid, s);
+                    Launch<R>::shadePhoton(p, cur, grid, s);
+                    Launch<R>::knn(p, grid, s);
                     launches += 1;
                 }
                 else
@@ -609,7 +635,9 @@ void mcrt_destroy(mcrt_ctx* ctx)
     freeAll(ctx->scene_allocs);
     freeAll(ctx->wave_allocs64);
     freeAll(ctx->wave_allocs32);
-    photonFree(ctx->photon);
+    freeAll(ctx->photon_allocs);
+    if (ctx->knn_queue64) cudaFree(ctx->knn_queue64);
+    if (ctx->knn_queue32) cudaFree(ctx->knn_queue32);
     if (ctx->d_film) cudaFree(ctx->d_film);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -710,11 +738,59 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, c
 {
     if (!ctx) return MCRT_ERR_INVALID;
     if (!caustic_map || !global_map || k_nearest == 0) { ctx->error = "mcrt_photon_upload: invalid arguments"; return MCRT_ERR_INVALID; }
+    if (k_nearest > 1024) { ctx->error = "k_nearest_photons > 1024 unsupported"; return MCRT_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(ctx->device));
+    freeAll(ctx->photon_allocs);
+    ctx->has_photons = false;
     uint64_t bytes = 0;
-    int rc = photonUpload(ctx->photon, *caustic_map, *global_map, k_nearest, direct_visualization, ctx->stream, bytes, ctx->error);
+    const mcrt_photon_map_desc* maps[2] = { caustic_map, global_map };
+    for (int w = 0; w < 2; w++)
+    {
+        const mcrt_photon_map_desc& m = *maps[w];
+        if (m.n_photons >= 0xFFFFFFFFull) { ctx->error = "photon map with >= 2^32 photons unsupported"; return MCRT_ERR_UNSUPPORTED; }
+        std::vector<DeviceOctant> oct(m.n_octants);
+        for (uint32_t i = 0; i < m.n_octants; i++)
+        {
+            DeviceOctant& o = oct[i];
+            for (int k = 0; k < 3; k++) { o.bmin[k] = m.octant_bounds[6 * i + k]; o.bmax[k] = m.octant_bounds[6 * i + 3 + k]; }
+            o.start = m.octant_start[i]; o.count = m.octant_count[i];
+            o.leaf = m.octant_leaf[i];
+            o.n_children = 0;
+            for (int k = 0; k < 8; k++) o.children[k] = OCTANT_NULL;
+            if (o.start + o.count > m.n_photons) { ctx->error = "octant photon range out of bounds"; return MCRT_ERR_INVALID; }
+            if (!o.leaf)
+            {
+                // children = node+1 followed along next_sibling (linear-octree.cpp:88-103)
+                uint32_t c = i + 1;
+                while (c != OCTANT_NULL)
+                {
+                    if (c <= i || c >= m.n_octants || o.n_children >= 8) { ctx->error = "malformed octree links"; return MCRT_ERR_INVALID; }
+                    o.children[o.n_children++] = c;
+                    c = m.octant_next_sibling[c];
+                }
+            }
+        }
+        const DeviceOctant* d_oct = nullptr;
+        int rc = devUpload(ctx, ctx->photon_allocs, &d_oct, oct, bytes);
+        if (rc) return rc;
+        float4* d_ph = nullptr;
+        if ((rc = devAlloc(ctx, ctx->photon_allocs, &d_ph, (size_t)m.n_photons * 2))) return rc;
+        if (m.n_photons)
+        {
+            CK(cudaMemcpyAsync(d_ph, m.photons, (size_t)m.n_photons * 32, cudaMemcpyHostToDevice, ctx->stream));
+            bytes += m.n_photons * 32;
+        }
+        CK(cudaStreamSynchronize(ctx->stream)); // `oct` dies at scope exit
+        ctx->photon_map[w].octants = d_oct;
+        ctx->photon_map[w].photons = d_ph;
+        ctx->photon_map[w].n_octants = m.n_octants;
+        ctx->photon_map[w].n_photons = m.n_photons;
+    }
+    ctx->k_nearest = k_nearest;
+    ctx->direct_visualization = direct_visualization;
+    ctx->has_photons = true;
     if (h2d_bytes) *h2d_bytes = bytes;
-    return rc;
+    return MCRT_OK;
 }
 
 int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,
@@ -862,11 +938,35 @@ int mcrt_knn_search(mcrt_ctx* ctx, int which, const double* points_xyz, size_t n
     if (n == 0) return MCRT_OK;
     if (!points_xyz || !out_index || !out_dist2 || !out_count || (which != 0 && which != 1))
     { ctx->error = "mcrt_knn_search: invalid arguments"; return MCRT_ERR_INVALID; }
-    if (!ctx->photon.valid) { ctx->error = "no photon maps uploaded"; return MCRT_ERR_NO_PHOTONS; }
+    if (!ctx->has_photons) { ctx->error = "no photon maps uploaded"; return MCRT_ERR_NO_PHOTONS; }
     CK(cudaSetDevice(ctx->device));
-    int rc = photonKnnUser(ctx->photon, which, points_xyz, n, out_index, out_dist2, out_count, ctx->sm_count, ctx->stream, ctx->error);
-    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->knn_queries = n; }
-    return rc;
+    const uint32_t k = ctx->k_nearest;
+    double* d_pts = nullptr; uint32_t* d_idx = nullptr; double* d_d2 = nullptr; uint32_t* d_cnt = nullptr; uint32_t* d_flag = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pts); cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_cnt); cudaFree(d_flag); };
+    if (cudaMalloc((void**)&d_pts, n * 24) != cudaSuccess || cudaMalloc((void**)&d_idx, n * k * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_d2, n * k * 8) != cudaSuccess || cudaMalloc((void**)&d_cnt, n * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_flag, 4) != cudaSuccess)
+    { cleanup(); ctx->error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
+    cudaStream_t s = ctx->stream;
+    cudaMemcpyAsync(d_pts, points_xyz, n * 24, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_flag, 0, 4, s);
+    cudaEventRecord(ctx->ev_start, s);
+    launchKnnUser(ctx->photon_map[which], k, d_pts, n, d_idx, d_d2, d_cnt, d_flag, ctx->sm_count * ctx->blocks_per_sm, s);
+    cudaEventRecord(ctx->ev_stop, s);
+    uint32_t flag = 0;
+    cudaMemcpyAsync(out_index, d_idx, n * k * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_dist2, d_d2, n * k * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_count, d_cnt, n * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) { ctx->error = cudaGetErrorString(e); return MCRT_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->knn_queries = n; stats->gpu_ms_total = ms; stats->gpu_ms_knn = ms; }
+    if (flag) { ctx->error = "k-NN frontier overflow"; return MCRT_ERR_UNSUPPORTED; }
+    return MCRT_OK;
 }
 
 } // extern "C"

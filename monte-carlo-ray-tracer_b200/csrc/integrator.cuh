@@ -21,6 +21,7 @@
 
 #include "bsdf.cuh"
 #include "intersect.cuh"
+#include "photon.cuh"
 
 namespace mcrt
 {
@@ -78,6 +79,7 @@ namespace mcrt
         uint32_t n_pixels;      // pixels in this render (rows * width)
         uint32_t integrator;    // MCRT_INTEGRATOR_*
         R ray_eps;              // C::EPSILON in parity mode; scale-aware in fast mode
+        PhotonParams<R> pm;     // photon maps + k-NN query queue (photon-mapped renders only)
     };
 
     // ------------------------------------------------------------------------------------------
@@ -227,7 +229,7 @@ namespace mcrt
         }
     }
 
-    inline __global__ void k_advance(Counters* c)
+    static __global__ void k_advance(Counters* c)
     {
         c->n_cur = c->n_next + c->n_gen;
         c->next_work += c->n_gen;
@@ -296,7 +298,7 @@ namespace mcrt
         return mix(V3<R>(R(1), R(0.5), R(0)), V3<R>(R(0), R(0.5), R(1)), fy);
     }
 
-    template <class R>
+    template <class R, int KIND>
     __global__ void __launch_bounds__(128) k_shade(WaveParams<R> p, int cur)
     {
         Counters* c = p.counters;
@@ -312,6 +314,8 @@ namespace mcrt
         {
             bool alive = i < n;
             bool want_shadow = false;
+            uint32_t want_knn = 0;   // 0 none, 1 caustic, 2 caustic + global
+            KnnQuery<R> knn_q;
 
             PathRay<R> ray, nray;
             V3<R> throughput;
@@ -362,7 +366,7 @@ namespace mcrt
                 if (hit.prim == NO_PRIM)
                 {
                     // path-tracer.cpp:27-30; the photon mapper adds no sky (photon-mapper.cpp:292-295)
-                    if (p.integrator == 0) filmAddV(p.film, film_index, skyColor(ray.direction) * throughput);
+                    if constexpr (KIND == 0) filmAddV(p.film, film_index, skyColor(ray.direction) * throughput);
                     alive = false;
                 }
                 else
@@ -396,8 +400,43 @@ namespace mcrt
                         }
                     }
 
+                    // ---- PhotonMapper::sampleRay control flow, photon-mapper.cpp:299-332
+                    bool do_direct = true, do_bsdf = true;
+                    if constexpr (KIND == 1)
+                    {
+                        if (ia.dirac_delta)
+                        {
+                            do_direct = false;
+                            if (!ray.dirac_delta && ray.depth != 0) { do_bsdf = false; alive = false; }
+                        }
+                        else
+                        {
+                            want_knn = 1; // caustic estimate at every non-delta hit
+                            if (!p.pm.direct_visualization && (ray.dirac_delta || ray.depth == 0))
+                            {
+                                // delay the global evaluation: direct light + one more bounce
+                            }
+                            else
+                            {
+                                want_knn = 2; // + global estimate, then the path ends
+                                do_direct = false; do_bsdf = false; alive = false;
+                            }
+                        }
+                        if (want_knn)
+                        {
+                            knn_q.pos_n1 = V4<R>(ia.position, ia.n1);
+                            knn_q.nrm_n2 = V4<R>(ia.shading_cs.c2, ia.n2);
+                            knn_q.out_rf = V4<R>(ia.out, ia.Rf);
+                            knn_q.weight_t = V4<R>(throughput, ia.T);
+                            knn_q.meta = make_uint4(ps.material, film_index, ia.inside ? 1u : 0u, 0u);
+                        }
+                    }
+
                     // ---- Integrator::sampleDirect up to the visibility query, integrator.cpp:31-66
-                    if (sc.n_lights == 0 || (m.flags & MAT_DIRAC_DELTA))
+                    if (!do_direct)
+                    {
+                    }
+                    else if (sc.n_lights == 0 || (m.flags & MAT_DIRAC_DELTA))
                     {
                         ls_light = NO_PRIM;
                     }
@@ -454,7 +493,10 @@ namespace mcrt
 
                     // ---- Interaction::sampleBSDF, throughput, absorb: path-tracer.cpp:37-47
                     V3<R> bsdf_absIdotN;
-                    if (!sampleBSDF(ia, ray, smp, p.ray_eps, false, bsdf_absIdotN, ls_bsdf_pdf, nray))
+                    if (!do_bsdf)
+                    {
+                    }
+                    else if (!sampleBSDF(ia, ray, smp, p.ray_eps, false, bsdf_absIdotN, ls_bsdf_pdf, nray))
                     {
                         alive = false;
                     }
@@ -519,6 +561,19 @@ namespace mcrt
                 p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
                                                   sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, 0u);
             }
+
+            if constexpr (KIND == 1)
+            {
+                // k-NN queries: caustic map always, global map when the path ends here
+                const uint32_t q0 = warpAppend(&c->n_knn, want_knn >= 1);
+                if (want_knn >= 1 && q0 < p.pm.query_capacity) p.pm.queries[q0] = knn_q;
+                const uint32_t q1 = warpAppend(&c->n_knn, want_knn == 2);
+                if (want_knn == 2 && q1 < p.pm.query_capacity)
+                {
+                    knn_q.meta.z |= 2u;
+                    p.pm.queries[q1] = knn_q;
+                }
+            }
         }
 
         if (local_max_depth) atomicMax(&c->max_depth, local_max_depth);
@@ -550,6 +605,108 @@ namespace mcrt
         flushStats(p.counters, cnt, rays, true, overflow);
     }
 
+
+    // ------------------------------------------------------------------------------------------
+    // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.
+    template <class R>
+    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK) k_knn(WaveParams<R> p)
+    {
+        extern __shared__ __align__(16) unsigned char knn_smem[];
+        const uint32_t n = min(p.counters->n_knn, p.pm.query_capacity);
+        const uint32_t k = p.pm.k_nearest;
+        const KnnShared sh = knnSharedFor(knn_smem, (k + 31u) & ~31u);
+        const unsigned lane = threadIdx.x & 31u;
+        const uint32_t warps_total = gridDim.x * KNN_WARPS_PER_BLOCK;
+        uint32_t overflow = 0;
+        for (uint32_t q = blockIdx.x * KNN_WARPS_PER_BLOCK + (threadIdx.x >> 5); q < n; q += warps_total)
+        {
+            const KnnQuery<R> qr = p.pm.queries[q];
+            const uint32_t which = (qr.meta.z >> 1) & 1u;
+            const DevicePhotonMap& map = p.pm.map[which];
+            double res_max;
+            const uint32_t found = knnSearchWarp(map, k, (double)qr.pos_n1.x, (double)qr.pos_n1.y, (double)qr.pos_n1.z,
+                                                 sh, &res_max, &overflow);
+            if (found == 0) continue;
+
+            // rebuild the Interaction fields Interaction::BSDF reads
+            Interaction<R> ia;
+            ia.type = IA_DIFFUSE;
+            ia.n1 = qr.pos_n1.w; ia.n2 = qr.nrm_n2.w; ia.Rf = qr.out_rf.w; ia.T = qr.weight_t.w;
+            ia.material = &p.scene.materials[qr.meta.x];
+            ia.out = qr.out_rf.xyz();
+            ia.shading_cs = Frame<R>(qr.nrm_n2.xyz());
+            ia.inside = qr.meta.z & 1u;
+
+            const R top_d2 = (R)res_max;
+            const R inv_max_r2 = R(1) / top_d2;
+            V3<R> sum(R(0));
+            for (uint32_t s = lane; s < found; s += 32)
+            {
+                const uint32_t idx = sh.res_idx[s];
+                const float4 a = __ldg(&map.photons[2 * (size_t)idx]);
+                const float4 b = __ldg(&map.photons[2 * (size_t)idx + 1]);
+                V3<R> bsdf_absIdotN; R bsdf_pdf;
+                if (ia.bsdfWorld(bsdf_absIdotN, photonDir<R>(b.z, b.w), bsdf_pdf))
+                {
+                    const V3<R> flux((R)a.x, (R)a.y, (R)a.z);
+                    if (which == 0)
+                    {
+                        // cone filter, photon-mapper.cpp:383-386
+                        R wp = gmax(R(0), R(1) - msqrt((R)sh.res_d2[s] * inv_max_r2));
+                        sum += (flux * bsdf_absIdotN * wp) / bsdf_pdf;
+                    }
+                    else
+                    {
+                        sum += flux * bsdf_absIdotN / bsdf_pdf;
+                    }
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1)
+            {
+                sum.x += __shfl_xor_sync(0xFFFFFFFFu, sum.x, off);
+                sum.y += __shfl_xor_sync(0xFFFFFFFFu, sum.y, off);
+                sum.z += __shfl_xor_sync(0xFFFFFFFFu, sum.z, off);
+            }
+            if (lane == 0)
+            {
+                V3<R> radiance = which == 0 ? R(3) * sum * inv_max_r2 * Consts<R>::INV_PI
+                                            : sum / (top_d2 * Consts<R>::PI);
+                filmAddV(p.film, qr.meta.y, radiance * qr.weight_t.xyz());
+            }
+            __syncwarp();
+        }
+        if (lane == 0)
+        {
+            if (overflow) atomicOr(&p.counters->traversal_overflow, 1u);
+        }
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.counters->knn_queries, (unsigned long long)n);
+    }
+
+    // Batched LinearOctree::knnSearch on caller points (mcrt_knn_search): results sorted by the host.
+    static __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK) k_knn_user(DevicePhotonMap map, uint32_t k, const double* points,
+                                                                          size_t n, uint32_t* out_index, double* out_d2,
+                                                                          uint32_t* out_count, uint32_t* overflow_flag)
+    {
+        extern __shared__ __align__(16) unsigned char knn_smem[];
+        const KnnShared sh = knnSharedFor(knn_smem, (k + 31u) & ~31u);
+        const unsigned lane = threadIdx.x & 31u;
+        const size_t warps_total = (size_t)gridDim.x * KNN_WARPS_PER_BLOCK;
+        uint32_t overflow = 0;
+        for (size_t q = (size_t)blockIdx.x * KNN_WARPS_PER_BLOCK + (threadIdx.x >> 5); q < n; q += warps_total)
+        {
+            double res_max;
+            const uint32_t found = knnSearchWarp(map, k, points[3 * q], points[3 * q + 1], points[3 * q + 2], sh, &res_max, &overflow);
+            for (uint32_t s = lane; s < k; s += 32)
+            {
+                out_index[q * k + s] = s < found ? sh.res_idx[s] : 0xFFFFFFFFu;
+                out_d2[q * k + s] = s < found ? sh.res_d2[s] : 1.7976931348623157e308;
+            }
+            if (lane == 0) out_count[q] = found;
+            __syncwarp();
+        }
+        if (overflow && lane == 0) atomicOr(overflow_flag, 1u);
+    }
+
     // ------------------------------------------------------------------------------------------
     // Batched Scene::intersect on caller rays (mcrt_trace_closest)
     template <class R>
@@ -571,7 +728,7 @@ namespace mcrt
     }
 
     // Film::Splat::get for the box filter: mean of the samples, clamped at 0 (film.cpp:106-113)
-    inline __global__ void k_resolve_film(const double* film, double* out, size_t n_values, double weight)
+    static __global__ void k_resolve_film(const double* film, double* out, size_t n_values, double weight)
     {
         for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x)
         {

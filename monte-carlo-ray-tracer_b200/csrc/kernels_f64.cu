@@ -12,6 +12,12 @@ namespace mcrt
         k_resolve_film<<<grid, 256, 0, s>>>(film, out, n_values, weight);
     }
 
+    void launchKnnUser(const DevicePhotonMap& map, uint32_t k, const double* points, size_t n, uint32_t* out_index,
+                       double* out_d2, uint32_t* out_count, uint32_t* overflow_flag, int grid, cudaStream_t s)
+    {
+        k_knn_user<<<grid, 32 * KNN_WARPS_PER_BLOCK, knnSharedBytes(k), s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag);
+    }
+
     __global__ void k_sampler_stream(const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles,
                                      uint32_t global_seed, uint32_t* out)
     {

@@ -13,7 +13,15 @@ namespace mcrt
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        k_shade<MCRT_REAL><<<grid * 2, 128, 0, s>>>(p, cur);
+        k_shade<MCRT_REAL, 0><<<grid * 2, 128, 0, s>>>(p, cur);
+    }
+    template <> void Launch<MCRT_REAL>::shadePhoton(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
+    {
+        k_shade<MCRT_REAL, 1><<<grid * 2, 128, 0, s>>>(p, cur);
+    }
+    template <> void Launch<MCRT_REAL>::knn(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
+    {
+        k_knn<MCRT_REAL><<<grid * 2, 32 * KNN_WARPS_PER_BLOCK, knnSharedBytes(p.pm.k_nearest), s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {

@@ -1,0 +1,269 @@
+// Photon-map lookup on the device: LinearOctree<Photon>::knnSearch
+// (source/octree/linear-octree.cpp:24-117) as a warp-cooperative kernel, and the radiance estimates
+// of PhotonMapper::estimateGlobalRadiance / estimateCausticRadiance
+// (source/integrator/photon-mapper/photon-mapper.cpp:343-391).
+//
+// One warp per query. The k nearest photons are unique (distances are float64 of float32 positions),
+// so any exact search returns the reference's set; the estimate then only differs by summation
+// order. The warp keeps
+//   * the k current results (distance2, photon index) in shared memory, unsorted, with the running
+//     maximum found by a warp reduction (the reference's bounded max-heap, linear-octree.cpp:60-84);
+//   * the best-first frontier of octants (the reference's `to_visit` heap, :39-46) as an unsorted
+//     array popped by a warp-parallel arg-min;
+//   * the pruning radius max_distance2 with the reference's two tightening rules (:82, :96-100).
+// Leaves (and inner octants holding <= k photons, :51-54) stream their contiguous photon range 32
+// photons = 1 KB per step, coalesced; children of an inner octant are tested by lanes 0..7 at once.
+#pragma once
+
+#include "bsdf.cuh"
+
+namespace mcrt
+{
+    constexpr uint32_t OCTANT_NULL = 0xFFFFFFFFu;
+    constexpr int KNN_FRONTIER = 256;
+    constexpr int KNN_WARPS_PER_BLOCK = 4;
+
+    struct alignas(16) DeviceOctant
+    {
+        double bmin[3], bmax[3];
+        unsigned long long start, count;
+        uint32_t children[8];   // OCTANT_NULL padded (derived from the next_sibling chain at upload)
+        uint32_t n_children, leaf;
+    };
+
+    struct DevicePhotonMap
+    {
+        const DeviceOctant* octants;
+        const float4* photons;  // 2 per photon: {flux.xyz, pos.x}, {pos.y, pos.z, phi, theta}
+        uint32_t n_octants, _pad;
+        unsigned long long n_photons;
+    };
+
+    // What k_shade hands to k_knn: the Interaction fields Interaction::BSDF needs, the weight
+    // (path throughput) and where to deposit.
+    template <class R> struct KnnQuery
+    {
+        V4<R> pos_n1;        // position.xyz, n1
+        V4<R> nrm_n2;        // shading normal.xyz, n2
+        V4<R> out_rf;        // out.xyz, R (specular reflect probability)
+        V4<R> weight_t;      // throughput.xyz, T (transparency)
+        uint4 meta;          // material, film_index, flags (bit0 inside, bit1 map: 0 caustic 1 global), -
+    };
+
+    template <class R> struct PhotonParams
+    {
+        DevicePhotonMap map[2];
+        KnnQuery<R>* queries;
+        uint32_t k_nearest, direct_visualization, query_capacity, _pad;
+    };
+
+    MCRT_D double octantDistance2(const DeviceOctant& o, double px, double py, double pz)
+    {
+        // BoundingBox::distance2, bounding-box.cpp:43-47
+        double dx = gmax(gmax(o.bmin[0] - px, px - o.bmax[0]), 0.0);
+        double dy = gmax(gmax(o.bmin[1] - py, py - o.bmax[1]), 0.0);
+        double dz = gmax(gmax(o.bmin[2] - pz, pz - o.bmax[2]), 0.0);
+        return dx * dx + dy * dy + dz * dz;
+    }
+
+    MCRT_D double octantMaxDistance2(const DeviceOctant& o, double px, double py, double pz)
+    {
+        // BoundingBox::max_distance2, bounding-box.cpp:50-54
+        double dx = gmax(o.bmax[0] - px, px - o.bmin[0]);
+        double dy = gmax(o.bmax[1] - py, py - o.bmin[1]);
+        double dz = gmax(o.bmax[2] - pz, pz - o.bmin[2]);
+        return dx * dx + dy * dy + dz * dz;
+    }
+
+    struct KnnShared
+    {
+        double* res_d2;       // [k_pad]
+        uint32_t* res_idx;    // [k_pad]
+        double* fr_d2;        // [KNN_FRONTIER]
+        uint32_t* fr_node;    // [KNN_FRONTIER]
+    };
+
+    MCRT_D double warpMaxD(double v)
+    {
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
+        return v;
+    }
+
+    // Warp-cooperative search. Distances are always float64, as in the reference
+    // (glm::distance2(data.pos(), p) on dvec3). Returns the number of results (<= k); the results
+    // are left in sh.res_*; *res_max is the largest distance2 among them.
+    MCRT_D uint32_t knnSearchWarp(const DevicePhotonMap& map, uint32_t k, double px, double py, double pz,
+                                  const KnnShared& sh, double* res_max, uint32_t* overflow)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        *res_max = 0.0;
+        if (map.n_octants == 0 || map.n_photons == 0) return 0;
+        if ((unsigned long long)k > map.n_photons) k = (uint32_t)map.n_photons;
+
+        uint32_t n_found = 0;
+        double max_d2 = 1.7976931348623157e308;
+        double cur_max = 0.0;        // max distance2 among stored results (valid once n_found == k)
+        uint32_t n_frontier = 0;
+        uint32_t cur = 0;
+        double cur_d2 = octantDistance2(map.octants[0], px, py, pz);
+        (void)cur_d2;
+
+        while (true)
+        {
+            const DeviceOctant* node = &map.octants[cur];
+            const unsigned long long count = node->count;
+            if (node->leaf || count <= (unsigned long long)k)
+            {
+                const unsigned long long start = node->start, end = start + count;
+                for (unsigned long long base = start; base < end; base += 32)
+                {
+                    const unsigned long long idx = base + lane;
+                    double d2 = 0.0;
+                    bool cand = false;
+                    if (idx < end)
+                    {
+                        const float4 a = __ldg(&map.photons[2 * idx]);
+                        const float4 b = __ldg(&map.photons[2 * idx + 1]);
+                        // distance2(data.pos(), p) = length2(p - pos)
+                        double dx = px - (double)a.w, dy = py - (double)b.x, dz = pz - (double)b.y;
+                        d2 = dx * dx + dy * dy + dz * dz;
+                        cand = d2 <= max_d2;
+                    }
+                    unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand);
+                    while (ballot)
+                    {
+                        const int src = __ffs(ballot) - 1;
+                        ballot &= ballot - 1;
+                        const double cd2 = __shfl_sync(0xFFFFFFFFu, d2, src);
+                        const uint32_t cidx = (uint32_t)(base + src);
+                        if (n_found < k)
+                        {
+                            if (lane == 0) { sh.res_d2[n_found] = cd2; sh.res_idx[n_found] = cidx; }
+                            n_found++;
+                            __syncwarp();
+                            if (n_found == k)
+                            {
+                                double m = 0.0;
+                                for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                                cur_max = warpMaxD(m);
+                                if (cur_max < max_d2) max_d2 = cur_max;
+                            }
+                        }
+                        else if (cd2 <= max_d2)
+                        {
+                            // pop_push: replace the farthest of the k results (linear-octree.cpp:79)
+                            uint32_t slot = 0xFFFFFFFFu;
+                            for (uint32_t s = lane; s < k; s += 32) if (sh.res_d2[s] == cur_max) slot = s;
+                            const unsigned has = __ballot_sync(0xFFFFFFFFu, slot != 0xFFFFFFFFu);
+                            const int owner = __ffs(has) - 1;
+                            if ((int)lane == owner) { sh.res_d2[slot] = cd2; sh.res_idx[slot] = cidx; }
+                            __syncwarp();
+                            double m = 0.0;
+                            for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            cur_max = warpMaxD(m);
+                            if (cur_max < max_d2) max_d2 = cur_max;
+                        }
+                    }
+                }
+            }
+            else
+            {
+                // children: lanes 0..7 each take one (linear-octree.cpp:88-103)
+                const uint32_t nc = node->n_children;
+                uint32_t child = OCTANT_NULL;
+                double d2 = 0.0, md2 = 1.7976931348623157e308;
+                bool push = false;
+                if (lane < nc)
+                {
+                    child = node->children[lane];
+                    const DeviceOctant& cn = map.octants[child];
+                    d2 = octantDistance2(cn, px, py, pz);
+                    push = d2 <= max_d2;
+                    if (push && cn.count >= (unsigned long long)k) md2 = octantMaxDistance2(cn, px, py, pz);
+                }
+                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, push);
+                if (push)
+                {
+                    const uint32_t slot = n_frontier + __popc(ballot & ((1u << lane) - 1u));
+                    if (slot < (uint32_t)KNN_FRONTIER) { sh.fr_d2[slot] = d2; sh.fr_node[slot] = child; }
+                    else *overflow = 1;
+                }
+                n_frontier += __popc(ballot);
+                if (n_frontier > (uint32_t)KNN_FRONTIER) n_frontier = KNN_FRONTIER;
+                // tighten with the farthest corner of any accepted child holding >= k photons
+                double m = md2;
+                for (int off = 4; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+                m = __shfl_sync(0xFFFFFFFFu, m, 0);
+                if (m < max_d2) max_d2 = m;
+                __syncwarp();
+            }
+
+            if (n_frontier == 0) break;
+            // pop the nearest octant: warp arg-min over the unsorted frontier
+            double best = 1.7976931348623157e308;
+            uint32_t best_slot = 0xFFFFFFFFu;
+            for (uint32_t s = lane; s < n_frontier; s += 32)
+            {
+                const double v = sh.fr_d2[s];
+                if (v < best || best_slot == 0xFFFFFFFFu) { best = v; best_slot = s; }
+            }
+            for (int off = 16; off > 0; off >>= 1)
+            {
+                const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+                const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, best_slot, off);
+                if (os != 0xFFFFFFFFu && (best_slot == 0xFFFFFFFFu || ob < best || (ob == best && os < best_slot))) { best = ob; best_slot = os; }
+            }
+            if (best > max_d2) break; // linear-octree.cpp:113
+            cur = sh.fr_node[best_slot];
+            __syncwarp();
+            if (lane == 0)
+            {
+                sh.fr_d2[best_slot] = sh.fr_d2[n_frontier - 1];
+                sh.fr_node[best_slot] = sh.fr_node[n_frontier - 1];
+            }
+            n_frontier--;
+            __syncwarp();
+        }
+
+        if (n_found < k)
+        {
+            double m = 0.0;
+            for (uint32_t s = lane; s < n_found; s += 32) m = fmax(m, sh.res_d2[s]);
+            cur_max = warpMaxD(m);
+        }
+        *res_max = cur_max;
+        return n_found;
+    }
+
+    MCRT_D KnnShared knnSharedFor(unsigned char* smem, uint32_t k_pad)
+    {
+        const unsigned warp = threadIdx.x >> 5;
+        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12;
+        unsigned char* base = smem + warp * ((per_warp + 15) & ~(size_t)15);
+        KnnShared sh;
+        sh.res_d2 = reinterpret_cast<double*>(base);
+        sh.fr_d2 = sh.res_d2 + k_pad;
+        sh.res_idx = reinterpret_cast<uint32_t*>(sh.fr_d2 + KNN_FRONTIER);
+        sh.fr_node = sh.res_idx + k_pad;
+        return sh;
+    }
+
+    inline size_t knnSharedBytes(uint32_t k)
+    {
+        const uint32_t k_pad = (k + 31u) & ~31u;
+        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12;
+        return KNN_WARPS_PER_BLOCK * ((per_warp + 15) & ~(size_t)15);
+    }
+
+    // Photon::dir(), photon.hpp:19-27: std::sin/std::cos of the *float* angles (float overloads),
+    // products in double. The float results are obtained by rounding the double functions, which is
+    // what glibc's sinf/cosf return in all but vanishingly rare double-rounding cases.
+    template <class R>
+    MCRT_D V3<R> photonDir(float phi, float theta)
+    {
+        float st = (float)sin((double)theta), ct = (float)cos((double)theta);
+        float sp = (float)sin((double)phi), cp = (float)cos((double)phi);
+        double sin_theta = (double)st;
+        return V3<R>((R)(sin_theta * (double)cp), (R)(sin_theta * (double)sp), (R)(double)ct);
+    }
+}

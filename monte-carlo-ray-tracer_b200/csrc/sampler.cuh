@@ -31,7 +31,7 @@ namespace mcrt
     struct SobolTable { uint32_t v[6][32]; };
 
     // Joe & Kuo "new-joe-kuo-6.21201", dimensions 2-7: degree s, coefficient bits a, initial m_i.
-    constexpr SobolTable makeSobolTable()
+    MCRT_HD constexpr SobolTable makeSobolTable()
     {
         const uint32_t deg[6] = { 1, 2, 3, 3, 4, 4 };
         const uint32_t poly[6] = { 0, 1, 1, 2, 1, 4 };

@@ -43,6 +43,10 @@ CASES = {
     "quadric_64": ("quadric.json", dict(width=64, height=48, sqrtspp=2), False),
     "veach_mis_64": ("veach_mis.json", dict(width=64, height=48, sqrtspp=2), False),
     "metals_64": ("metals.json", dict(width=64, height=48, sqrtspp=2), False),
+    # photon-mapped render (PhotonMapper::sampleRay + k-NN estimates); maps built by the reference's
+    # CPU photon pass with 1 thread, shipped inside the pack
+    "pm_hexagon_room_64": ("hexagon_room.json", dict(width=64, height=48, sqrtspp=2, emissions=4000,
+                                                      num_render_threads=1), True),
 }
 
 
@@ -77,7 +81,20 @@ def make_case(cid, scene_file, overrides, photon_map, rng):
         tr_rays = ps_rays
     tr_t, tr_prim, tr_uv, tr_interp = s.trace(tr_rays)
 
-    np.savez_compressed(os.path.join(HERE, cid + ".npz"),
+    extra = {}
+    if photon_map:
+        # LinearOctree::knnSearch KAT: query points = primary hit points (+ jitter)
+        q = pts[rng.integers(0, len(pts), 256)] + rng.normal(0, 0.02, (256, 3))
+        k = 50
+        for which, name in ((0, "caustic"), (1, "global")):
+            ph, d2, cnt = s.knn(which, q, k)
+            extra[f"knn_{name}_d2"] = d2
+            extra[f"knn_{name}_count"] = cnt
+            extra[f"knn_{name}_pos"] = ph[:, :, 3:6]
+        extra["knn_points"] = q
+        extra["knn_k"] = np.uint32(k)
+
+    np.savez_compressed(os.path.join(HERE, cid + ".npz"), photon_map=np.uint8(photon_map), **extra,
                         seed=np.uint32(SEED), width=np.uint32(s.width), height=np.uint32(s.height),
                         sqrtspp=np.uint32(s.sqrtspp), image=image,
                         ps_pixel=ps_pixel, ps_sample=ps_sample, ps_rays=ps_rays, ps_rgb=ps_rgb,
