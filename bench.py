@@ -183,9 +183,10 @@ def run_gpu_arm(args):
         pt.set_option("pool_paths", args.pool)
     pt.set_option("stage_timing", 1)
 
+    mdist = importlib.import_module("monte-carlo-ray-tracer_b200.distributed")
     W, H = cam.width, cam.height
-    n_rows = len(range(rank, H, world))
-    max_rows = len(range(0, H, world))
+    _, _, n_rows = mdist.interleaved_rows(rank, world, H)
+    max_rows = mdist.max_rows(world, H)
     dev = torch.device("cuda", local_rank)
     local = torch.zeros((max_rows, W, 3), dtype=torch.float64, device=dev)
     gathered = torch.zeros((world, max_rows, W, 3), dtype=torch.float64, device=dev) if world > 1 else None
@@ -203,10 +204,7 @@ def run_gpu_arm(args):
         ms = st["gpu_ms_total"]
         if world > 1:
             ev0.record()
-            dist.all_gather_into_tensor(gathered, local)
-            # row k*world + r  <-  gathered[r, k]
-            frame = gathered.permute(1, 0, 2, 3).reshape(max_rows * world, W, 3)[:H]
-            frame = frame.contiguous()
+            frame = mdist.gather_frame(local, H, world, out=gathered)
             ev1.record()
             ev1.synchronize()
             ms += ev0.elapsed_time(ev1)
@@ -242,8 +240,7 @@ def run_gpu_arm(args):
             st = pt.last_stats
         else:
             st = pt.render_rows_strided_dev(cam, local.data_ptr(), rank, world, n_rows)
-            dist.all_gather_into_tensor(gathered, local)
-            frame = gathered.permute(1, 0, 2, 3).reshape(max_rows * world, W, 3)[:H]
+            frame = mdist.gather_frame(local, H, world, out=gathered)
             host_frame.copy_(frame, non_blocking=False)
         return h2d, st
 
