@@ -16,7 +16,7 @@ import struct
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcrt_b200.so")
+LIB_PATH = os.environ.get("MCRT_LIB", os.path.join(HERE, "libmcrt_b200.so"))  # MCRT_LIB: tuning variants
 
 INTEGRATOR_PATH, INTEGRATOR_PHOTON = 0, 1
 PRECISION_F64, PRECISION_F32 = 0, 1

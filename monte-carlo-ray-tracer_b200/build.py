@@ -30,8 +30,12 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(force=False, verbose=False):
-    objdir = os.path.join(HERE, "build")
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """defines/suffix: tuning variants, e.g. build(defines=["-DMCRT_TRACE_MINBLOCKS=3"], suffix="_t3")
+    writes libmcrt_b200_t3.so (select it at run time with MCRT_LIB)."""
+    global LIB
+    lib = os.path.join(HERE, f"libmcrt_b200{suffix}.so")
+    objdir = os.path.join(HERE, "build" + suffix)
     os.makedirs(objdir, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mcrt_abi.h")]
     newest = max(os.path.getmtime(d) for d in deps)
@@ -40,17 +44,19 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, src[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
-            cmd = ["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = ["nvcc"] + ARCH + COMMON + list(defines) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
             jobs.append(cmd)
     with cf.ThreadPoolExecutor(max_workers=4) as ex:
         outs = list(ex.map(_run, jobs))
     if verbose:
         for o in outs:
             sys.stderr.write(o)
-    if jobs or not os.path.exists(LIB):
-        _run(["nvcc"] + ARCH + ["-shared", "-o", LIB] + objs)
-    return LIB
+    if jobs or not os.path.exists(lib):
+        _run(["nvcc"] + ARCH + ["-shared", "-o", lib] + objs)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    suf = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, suffix=suf[0] if suf else ""))

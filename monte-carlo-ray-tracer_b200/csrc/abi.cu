@@ -80,7 +80,14 @@ struct mcrt_ctx
     std::vector<cudaEvent_t> stage_events; // 5 per wavefront iteration when stage_timing is on
     std::vector<uint8_t> prim_interpolates; // host copy: ordered prim has vertex normals
 
+    // ray-coherence sort buffers (shared by both precisions)
+    std::vector<void*> sort_allocs;
+    RaySort sort{};
+    uint32_t sort_capacity = 0;
+    double scene_bmin[3] = { 0, 0, 0 }, scene_bmax[3] = { 1, 1, 1 };
+
     // options
+    int sort_rays = 1;
     uint32_t pool_paths = 1u << 22;
     int blocks_per_sm = 8;
     double ray_eps_scale = 1e-5;
@@ -357,6 +364,30 @@ namespace
         return MCRT_OK;
     }
 
+    int ensureSort(mcrt_ctx* ctx)
+    {
+        if (ctx->sort_capacity == ctx->pool_paths) return MCRT_OK;
+        freeAll(ctx->sort_allocs);
+        ctx->sort_capacity = 0;
+        const size_t n = ctx->pool_paths;
+        int rc;
+        RaySort& r = ctx->sort;
+        for (int b = 0; b < 2; b++)
+        {
+            if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.path_key[b], n))) return rc;
+            if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.path_rank[b], n))) return rc;
+        }
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.path_order, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_key, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_rank, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_order, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_path, (size_t)SORT_BINS))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_shadow, (size_t)SORT_BINS))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.bin_start, (size_t)SORT_BINS))) return rc;
+        ctx->sort_capacity = ctx->pool_paths;
+        return MCRT_OK;
+    }
+
     int ensureFilm(mcrt_ctx* ctx, size_t values)
     {
         if (ctx->film_values >= values && ctx->d_film) return MCRT_OK;
@@ -429,6 +460,8 @@ namespace
             knn_queue = static_cast<KnnQuery<R>*>(q);
         }
 
+        cudaStream_t s = ctx->stream;
+        const int grid = ctx->sm_count * ctx->blocks_per_sm;
         WaveParams<R> p;
         std::memset(&p, 0, sizeof(p));
         p.scene = sceneOf<R>(ctx);
@@ -454,6 +487,18 @@ namespace
         p.n_pixels = n_pixels;
         p.integrator = (uint32_t)integrator;
         p.ray_eps = Mode<R>::parity ? (R)1e-9 : (R)(ctx->ray_eps_scale * ctx->scene_scale);
+        std::memset(&p.sort, 0, sizeof(p.sort));
+        if (ctx->sort_rays)
+        {
+            if ((rc = ensureSort(ctx))) return rc;
+            p.sort = ctx->sort;
+            for (int k = 0; k < 3; k++)
+            {
+                const double ext = ctx->scene_bmax[k] - ctx->scene_bmin[k];
+                p.sort.key_min[k] = (float)ctx->scene_bmin[k];
+                p.sort.key_scale[k] = ext > 0.0 ? (float)(16.0 / ext) : 0.0f;
+            }
+        }
 
         if (integrator == MCRT_INTEGRATOR_PHOTON)
         {
@@ -464,15 +509,24 @@ namespace
             p.pm.query_capacity = knn_capacity;
         }
 
-        cudaStream_t s = ctx->stream;
-        const int grid = ctx->sm_count * ctx->blocks_per_sm;
-
         Counters init;
         std::memset(&init, 0, sizeof(init));
         init.total_work = total_work;
         ctx->h_counters[0] = init;
         CK(cudaMemcpyAsync(ctx->d_counters, &ctx->h_counters[0], sizeof(Counters), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ctx->d_film, 0, film_pixels * 3 * sizeof(double), s));
+        const bool sorting = ctx->sort_rays != 0;
+        if (sorting)
+        {
+            CK(cudaMemsetAsync(p.sort.hist_path, 0, SORT_BINS * sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(p.sort.hist_shadow, 0, SORT_BINS * sizeof(uint32_t), s));
+        }
+        auto sortPaths = [&](int buffer)
+        {
+            launchSortScan(p.sort.hist_path, p.sort.bin_start, s);
+            launchSortScatter(p.sort.path_key[buffer], p.sort.path_rank[buffer], p.sort.bin_start, p.sort.path_order,
+                              &ctx->d_counters->n_cur, grid, s);
+        };
 
         CK(cudaEventRecord(ctx->ev_start, s));
         uint64_t launches = 0, iterations = 0;
@@ -480,6 +534,7 @@ namespace
         Launch<R>::generate(p, 0, grid, s);
         launchAdvance(ctx->d_counters, s);
         launches += 2;
+        if (sorting) { sortPaths(0); launches += 2; }
 
         // Enqueue iterations ahead of the GPU; poll the queue counters through pinned memory every
         // poll_interval iterations with one poll of look-ahead, so the device never waits on the host.
@@ -516,10 +571,18 @@ namespace
                     Launch<R>::shade(p, cur, grid, s);
                 }
                 if (ev) cudaEventRecord(ev[2], s);
+                if (sorting)
+                {
+                    launchSortScan(p.sort.hist_shadow, p.sort.bin_start, s);
+                    launchSortScatter(p.sort.shadow_key, p.sort.shadow_rank, p.sort.bin_start, p.sort.shadow_order,
+                                      &ctx->d_counters->n_shadow, grid, s);
+                    launches += 2;
+                }
                 Launch<R>::shadow(p, grid, s);
                 if (ev) cudaEventRecord(ev[3], s);
                 Launch<R>::generate(p, cur ^ 1, grid, s);
                 launchAdvance(ctx->d_counters, s);
+                if (sorting) { sortPaths(cur ^ 1); launches += 2; }
                 if (ev) cudaEventRecord(ev[4], s);
                 launches += 5;
                 iterations++;
@@ -635,6 +698,7 @@ void mcrt_destroy(mcrt_ctx* ctx)
     freeAll(ctx->scene_allocs);
     freeAll(ctx->wave_allocs64);
     freeAll(ctx->wave_allocs32);
+    freeAll(ctx->sort_allocs);
     freeAll(ctx->photon_allocs);
     if (ctx->knn_queue64) cudaFree(ctx->knn_queue64);
     if (ctx->knn_queue32) cudaFree(ctx->knn_queue32);
@@ -663,6 +727,7 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "ray_eps_scale") { if (value <= 0) return MCRT_ERR_INVALID; ctx->ray_eps_scale = value; }
     else if (k == "poll_interval") { if (value < 1 || value > 1024) return MCRT_ERR_INVALID; ctx->poll_interval = (int)value; }
     else if (k == "stage_timing") { ctx->stage_timing = value != 0.0; }
+    else if (k == "sort_rays") { ctx->sort_rays = value != 0.0; }
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }
@@ -705,6 +770,29 @@ int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d
         grow(s.quadric_bounds, 6 * s.n_quadrics);
     }
     ctx->scene_scale = scale > 0.0 ? (float)scale : 1.0f;
+    {
+        // bounds for the sort key grid: root node box, or the union of primitive extents without a BVH
+        double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+        auto add = [&](const double* q) { for (int k = 0; k < 3; k++) { if (q[k] < lo[k]) lo[k] = q[k]; if (q[k] > hi[k]) hi[k] = q[k]; } };
+        if (s.n_nodes) { add(s.node_bounds); add(s.node_bounds + 3); }
+        else
+        {
+            for (uint32_t i = 0; i < s.n_tris; i++) { add(s.tri_v0 + 3 * i); add(s.tri_v1 + 3 * i); add(s.tri_v2 + 3 * i); }
+            for (uint32_t i = 0; i < s.n_spheres; i++)
+            {
+                const double* sp = s.sphere_origin_radius + 4 * i;
+                double a[3] = { sp[0] - sp[3], sp[1] - sp[3], sp[2] - sp[3] }, b[3] = { sp[0] + sp[3], sp[1] + sp[3], sp[2] + sp[3] };
+                add(a); add(b);
+            }
+            for (uint32_t i = 0; i < s.n_quadrics; i++) { add(s.quadric_bounds + 6 * i); add(s.quadric_bounds + 6 * i + 3); }
+        }
+        for (int k = 0; k < 3; k++)
+        {
+            const bool ok = lo[k] <= hi[k] && lo[k] > -1e290 && hi[k] < 1e290;
+            ctx->scene_bmin[k] = ok ? lo[k] : -1.0;
+            ctx->scene_bmax[k] = ok ? hi[k] : 1.0;
+        }
+    }
 
     uint64_t bytes = 0;
     int rc;

@@ -23,6 +23,14 @@
 #include "intersect.cuh"
 #include "photon.cuh"
 
+// launch-bound knobs (overridable at build time for tuning experiments)
+#ifndef MCRT_TRACE_MINBLOCKS
+#define MCRT_TRACE_MINBLOCKS 2
+#endif
+#ifndef MCRT_SHADE_MINBLOCKS
+#define MCRT_SHADE_MINBLOCKS 2
+#endif
+
 namespace mcrt
 {
     constexpr int IOR_STACK_CAPACITY = 8; // iors[0] is implicit (scene ior); 7 stored entries
@@ -58,6 +66,55 @@ namespace mcrt
         uint4* meta;     // light prim, film_index, source prim, -
     };
 
+    // Ray-coherence sort. Incoherent secondary rays run the traversal kernels at ~10 of 32 lanes
+    // active (ncu, r1 baseline) while coherent primary rays reach 31; so every queue is re-ordered
+    // each bounce by a 17-bit key = direction class (cube face + 2 sign bits) | Morton code of the
+    // origin cell (16^3 grid over the scene bounds). It is a counting sort: the producer kernel takes
+    // rank = atomicAdd(&hist[key], 1) when it appends an entry, k_sort_scan turns the histogram into
+    // bin starts (and zeroes it), k_sort_scatter writes order[bin_start[key] + rank] = entry. The
+    // consumers index their queue through `order`; state stays where it was written.
+    constexpr uint32_t SORT_KEY_BITS = 17;
+    constexpr uint32_t SORT_BINS = 1u << SORT_KEY_BITS;
+
+    struct RaySort
+    {
+        uint32_t* path_key[2];   // per path buffer
+        uint32_t* path_rank[2];
+        uint32_t* path_order;    // permutation of the current path buffer (null: identity)
+        uint32_t* shadow_key;
+        uint32_t* shadow_rank;
+        uint32_t* shadow_order;
+        uint32_t* hist_path;     // [SORT_BINS]
+        uint32_t* hist_shadow;   // [SORT_BINS]
+        uint32_t* bin_start;     // [SORT_BINS] scratch
+        float key_min[3], key_scale[3]; // origin -> cell: (o - key_min) * key_scale in [0, 16)
+    };
+
+    MCRT_D uint32_t spreadBits4(uint32_t v) // 4 bits -> every third bit
+    {
+        return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+    }
+
+    template <class R>
+    MCRT_D uint32_t rayKey(const RaySort& rs, const V3<R>& o, const V3<R>& d)
+    {
+        float cx = ((float)o.x - rs.key_min[0]) * rs.key_scale[0];
+        float cy = ((float)o.y - rs.key_min[1]) * rs.key_scale[1];
+        float cz = ((float)o.z - rs.key_min[2]) * rs.key_scale[2];
+        uint32_t ix = (uint32_t)fminf(fmaxf(cx, 0.0f), 15.0f);
+        uint32_t iy = (uint32_t)fminf(fmaxf(cy, 0.0f), 15.0f);
+        uint32_t iz = (uint32_t)fminf(fmaxf(cz, 0.0f), 15.0f);
+        uint32_t cell = spreadBits4(ix) | (spreadBits4(iy) << 1) | (spreadBits4(iz) << 2);
+        float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+        float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+        uint32_t face, s0, s1;
+        if (ax >= ay && ax >= az) { face = dx < 0.0f ? 1u : 0u; s0 = dy < 0.0f; s1 = dz < 0.0f; }
+        else if (ay >= az)        { face = dy < 0.0f ? 3u : 2u; s0 = dx < 0.0f; s1 = dz < 0.0f; }
+        else                      { face = dz < 0.0f ? 5u : 4u; s0 = dx < 0.0f; s1 = dy < 0.0f; }
+        uint32_t dir = (face << 2) | (s0 << 1) | s1;   // 24 classes in 5 bits
+        return (dir << 12) | cell;
+    }
+
     template <class R> struct WaveParams
     {
         DeviceScene<R> scene;
@@ -80,6 +137,7 @@ namespace mcrt
         uint32_t integrator;    // MCRT_INTEGRATOR_*
         R ray_eps;              // C::EPSILON in parity mode; scale-aware in fast mode
         PhotonParams<R> pm;     // photon maps + k-NN query queue (photon-mapped renders only)
+        RaySort sort;           // coherence sort of the path / shadow queues (null order = disabled)
     };
 
     // ------------------------------------------------------------------------------------------
@@ -226,6 +284,12 @@ namespace mcrt
             out.iors_a[slot] = V4<R>(R(0), R(0), R(0), R(0));
             out.meta[slot] = make_uint4(pixel, sample, 0u, 0u);
             out.meta2[slot] = make_uint4(NO_PRIM, 1u, film_index, NO_PRIM);
+            if (p.sort.path_order)
+            {
+                const uint32_t key = rayKey(p.sort, start, direction);
+                p.sort.path_key[next][slot] = key;
+                p.sort.path_rank[next][slot] = atomicAdd(&p.sort.hist_path[key], 1u);
+            }
         }
     }
 
@@ -241,15 +305,17 @@ namespace mcrt
     }
 
     template <class R>
-    __global__ void __launch_bounds__(256) k_extend(WaveParams<R> p, int cur)
+    __global__ void __launch_bounds__(256, MCRT_TRACE_MINBLOCKS) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
         TraceCounters cnt = { 0u, 0u };
         uint32_t overflow = 0;
         unsigned long long rays = 0;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        const uint32_t* order = p.sort.path_order;
+        for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
+            const uint32_t i = order ? order[ii] : ii;
             const V4<R> ro = in.ray_o[i];
             const V4<R> rd = in.ray_d[i];
             uint32_t skip = NO_PRIM;
@@ -299,7 +365,7 @@ namespace mcrt
     }
 
     template <class R, int KIND>
-    __global__ void __launch_bounds__(128) k_shade(WaveParams<R> p, int cur)
+    __global__ void __launch_bounds__(128, MCRT_SHADE_MINBLOCKS) k_shade(WaveParams<R> p, int cur)
     {
         Counters* c = p.counters;
         const uint32_t n = c->n_cur;
@@ -310,9 +376,11 @@ namespace mcrt
         uint32_t stack_overflows = 0;
 
         const uint32_t n_rounded = (n + 31u) & ~31u; // keep warps converged for the ballots
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x)
+        const uint32_t* order = p.sort.path_order;
+        for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n_rounded; ii += gridDim.x * blockDim.x)
         {
-            bool alive = i < n;
+            bool alive = ii < n;
+            const uint32_t i = (alive && order) ? order[ii] : ii;
             bool want_shadow = false;
             uint32_t want_knn = 0;   // 0 none, 1 caustic, 2 caustic + global
             KnnQuery<R> knn_q;
@@ -551,6 +619,12 @@ namespace mcrt
                                             (uint32_t)nray.refraction_level);
                 out.meta2[slot] = make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
                                              sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
+                if (order)
+                {
+                    const uint32_t key = rayKey(p.sort, nray.start, nray.direction);
+                    p.sort.path_key[cur ^ 1][slot] = key;
+                    p.sort.path_rank[cur ^ 1][slot] = atomicAdd(&p.sort.hist_path[key], 1u);
+                }
             }
             const uint32_t sslot = warpAppend(&c->n_shadow, want_shadow);
             if (want_shadow)
@@ -560,6 +634,12 @@ namespace mcrt
                 p.shadow.k[sslot] = V4<R>(sh_k, sh_select);
                 p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
                                                   sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, 0u);
+                if (p.sort.shadow_order)
+                {
+                    const uint32_t key = rayKey(p.sort, sh_o, sh_d);
+                    p.sort.shadow_key[sslot] = key;
+                    p.sort.shadow_rank[sslot] = atomicAdd(&p.sort.hist_shadow[key], 1u);
+                }
             }
 
             if constexpr (KIND == 1)
@@ -581,14 +661,16 @@ namespace mcrt
     }
 
     template <class R>
-    __global__ void __launch_bounds__(256) k_shadow(WaveParams<R> p)
+    __global__ void __launch_bounds__(256, MCRT_TRACE_MINBLOCKS) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
         TraceCounters cnt = { 0u, 0u };
         uint32_t overflow = 0;
         unsigned long long rays = 0;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        const uint32_t* order = p.sort.shadow_order;
+        for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
+            const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
             Hit<R> h = traceClosest(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
@@ -605,6 +687,65 @@ namespace mcrt
         flushStats(p.counters, cnt, rays, true, overflow);
     }
 
+
+
+    // ------------------------------------------------------------------------------------------
+    // Counting-sort helpers. k_sort_scan: exclusive prefix sum of the SORT_BINS-entry histogram into
+    // bin_start, zeroing the histogram for the next bounce (one 1024-thread CTA: 128 bins per thread,
+    // 512 KB read once). k_sort_scatter: order[bin_start[key] + rank] = entry.
+    static __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* hist, uint32_t* bin_start)
+    {
+        __shared__ uint32_t warp_sums[32];
+        constexpr uint32_t PER_THREAD = SORT_BINS / 1024;
+        const uint32_t t = threadIdx.x, base = t * PER_THREAD;
+        uint32_t local[PER_THREAD];
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (uint32_t k = 0; k < PER_THREAD; k += 4)
+        {
+            const uint4 v = *reinterpret_cast<const uint4*>(hist + base + k);
+            local[k] = v.x; local[k + 1] = v.y; local[k + 2] = v.z; local[k + 3] = v.w;
+            sum += v.x + v.y + v.z + v.w;
+            *reinterpret_cast<uint4*>(hist + base + k) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // block exclusive scan of `sum`
+        uint32_t incl = sum;
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if ((t & 31u) >= (uint32_t)off) incl += v;
+        }
+        if ((t & 31u) == 31u) warp_sums[t >> 5] = incl;
+        __syncthreads();
+        if (t < 32)
+        {
+            uint32_t w = warp_sums[t], wi = w;
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+                if (t >= (uint32_t)off) wi += v;
+            }
+            warp_sums[t] = wi - w;
+        }
+        __syncthreads();
+        uint32_t run = warp_sums[t >> 5] + incl - sum;
+#pragma unroll 8
+        for (uint32_t k = 0; k < PER_THREAD; k++)
+        {
+            bin_start[base + k] = run;
+            run += local[k];
+        }
+    }
+
+    static __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* key, const uint32_t* rank, const uint32_t* bin_start,
+                                                                 uint32_t* order, const uint32_t* n_ptr)
+    {
+        const uint32_t n = *n_ptr;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        {
+            order[bin_start[key[i]] + rank[i]] = i;
+        }
+    }
 
     // ------------------------------------------------------------------------------------------
     // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.

@@ -7,6 +7,14 @@ namespace mcrt
 {
     void launchAdvance(Counters* c, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(c); }
 
+    void launchSortScan(uint32_t* hist, uint32_t* bin_start, cudaStream_t s) { k_sort_scan<<<1, 1024, 0, s>>>(hist, bin_start); }
+
+    void launchSortScatter(const uint32_t* key, const uint32_t* rank, const uint32_t* bin_start, uint32_t* order,
+                           const uint32_t* n_ptr, int grid, cudaStream_t s)
+    {
+        k_sort_scatter<<<grid, 256, 0, s>>>(key, rank, bin_start, order, n_ptr);
+    }
+
     void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s)
     {
         k_resolve_film<<<grid, 256, 0, s>>>(film, out, n_values, weight);

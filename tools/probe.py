@@ -21,6 +21,7 @@ for mode in a.modes.split(","):
     pt = m.PathTracer(scene, precision=prec)
     if a.pool: pt.set_option("pool_paths", a.pool)
     if a.bps: pt.set_option("blocks_per_sm", a.bps)
+    pt.set_option("stage_timing", 1)
     for r in range(a.reps):
         t = time.time(); img = pt.render_rows(cam); wall = time.time() - t
         st = pt.last_stats
@@ -28,7 +29,8 @@ for mode in a.modes.split(","):
         print(f"{mode} rep{r}: {cam.width}x{cam.height}x{cam.sqrtspp**2}spp gpu_ms={st['gpu_ms_total']:.1f} wall={wall*1e3:.1f} "
               f"Mray/s={rays/st['gpu_ms_total']/1e3:.1f} paths={st['paths']} ext={st['extension_rays']} sh={st['shadow_rays']} "
               f"box/ray={st['box_tests']/rays:.1f} prim/ray={st['prim_tests']/rays:.1f} iters={st['wavefront_iterations']} "
-              f"launches={st['kernel_launches']} maxdepth={st['max_depth']} mean={img.mean():.6f}", flush=True)
+              f"launches={st['kernel_launches']} maxdepth={st['max_depth']} mean={img.mean():.6f} "
+              f"stages ext={st['gpu_ms_extend']:.1f} shade={st['gpu_ms_shade']:.1f} shadow={st['gpu_ms_shadow']:.1f} gen={st['gpu_ms_generate']:.1f}", flush=True)
     imgs[mode] = img
     pt.close()
 if a.compare and len(imgs) == 2:
