@@ -88,6 +88,7 @@ struct mcrt_ctx
 
     // options
     int sort_rays = 1;
+    int sort_shade = 1;
     uint32_t pool_paths = 1u << 22;
     int blocks_per_sm = 8;
     double ray_eps_scale = 1e-5;
@@ -384,6 +385,9 @@ namespace
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_path, (size_t)SORT_BINS))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_shadow, (size_t)SORT_BINS))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.bin_start, (size_t)SORT_BINS))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.block_offset, (size_t)2 * SORT_SCAN_BLOCKS))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.done_counter, (size_t)1))) return rc;
+        CK(cudaMemset(r.done_counter, 0, sizeof(uint32_t)));
         ctx->sort_capacity = ctx->pool_paths;
         return MCRT_OK;
     }
@@ -492,6 +496,7 @@ namespace
         {
             if ((rc = ensureSort(ctx))) return rc;
             p.sort = ctx->sort;
+            p.sort.shade_sorted = ctx->sort_shade ? 1u : 0u;
             for (int k = 0; k < 3; k++)
             {
                 const double ext = ctx->scene_bmax[k] - ctx->scene_bmin[k];
@@ -523,8 +528,8 @@ namespace
         }
         auto sortPaths = [&](int buffer)
         {
-            launchSortScan(p.sort.hist_path, p.sort.bin_start, s);
-            launchSortScatter(p.sort.path_key[buffer], p.sort.path_rank[buffer], p.sort.bin_start, p.sort.path_order,
+            launchSortScan(p.sort.hist_path, p.sort, s);
+            launchSortScatter(p.sort.path_key[buffer], p.sort.path_rank[buffer], p.sort, p.sort.path_order,
                               &ctx->d_counters->n_cur, grid, s);
         };
 
@@ -573,8 +578,8 @@ namespace
                 if (ev) cudaEventRecord(ev[2], s);
                 if (sorting)
                 {
-                    launchSortScan(p.sort.hist_shadow, p.sort.bin_start, s);
-                    launchSortScatter(p.sort.shadow_key, p.sort.shadow_rank, p.sort.bin_start, p.sort.shadow_order,
+                    launchSortScan(p.sort.hist_shadow, p.sort, s);
+                    launchSortScatter(p.sort.shadow_key, p.sort.shadow_rank, p.sort, p.sort.shadow_order,
                                       &ctx->d_counters->n_shadow, grid, s);
                     launches += 2;
                 }
@@ -728,6 +733,7 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "poll_interval") { if (value < 1 || value > 1024) return MCRT_ERR_INVALID; ctx->poll_interval = (int)value; }
     else if (k == "stage_timing") { ctx->stage_timing = value != 0.0; }
     else if (k == "sort_rays") { ctx->sort_rays = value != 0.0; }
+    else if (k == "sort_shade") { ctx->sort_shade = value != 0.0; }
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }

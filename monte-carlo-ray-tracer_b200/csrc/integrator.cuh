@@ -86,7 +86,11 @@ namespace mcrt
         uint32_t* shadow_order;
         uint32_t* hist_path;     // [SORT_BINS]
         uint32_t* hist_shadow;   // [SORT_BINS]
-        uint32_t* bin_start;     // [SORT_BINS] scratch
+        uint32_t* bin_start;     // [SORT_BINS] scratch: exclusive scan within each 1024-bin CTA segment
+        uint32_t* block_offset;  // [2 * SORT_BINS / 1024]: segment offsets, then segment totals
+        uint32_t* done_counter;  // last-CTA-done counter of k_sort_scan
+        uint32_t shade_sorted;   // 1: k_shade also walks the queue in sorted order
+        uint32_t _pad;
         float key_min[3], key_scale[3]; // origin -> cell: (o - key_min) * key_scale in [0, 16)
     };
 
@@ -376,7 +380,8 @@ namespace mcrt
         uint32_t stack_overflows = 0;
 
         const uint32_t n_rounded = (n + 31u) & ~31u; // keep warps converged for the ballots
-        const uint32_t* order = p.sort.path_order;
+        const uint32_t* order = p.sort.shade_sorted ? p.sort.path_order : nullptr;
+        const bool sorting = p.sort.path_order != nullptr;
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n_rounded; ii += gridDim.x * blockDim.x)
         {
             bool alive = ii < n;
@@ -619,7 +624,7 @@ namespace mcrt
                                             (uint32_t)nray.refraction_level);
                 out.meta2[slot] = make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
                                              sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
-                if (order)
+                if (sorting)
                 {
                     const uint32_t key = rayKey(p.sort, nray.start, nray.direction);
                     p.sort.path_key[cur ^ 1][slot] = key;
@@ -693,57 +698,63 @@ namespace mcrt
     // Counting-sort helpers. k_sort_scan: exclusive prefix sum of the SORT_BINS-entry histogram into
     // bin_start, zeroing the histogram for the next bounce (one 1024-thread CTA: 128 bins per thread,
     // 512 KB read once). k_sort_scatter: order[bin_start[key] + rank] = entry.
-    static __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* hist, uint32_t* bin_start)
+    constexpr uint32_t SORT_SCAN_BLOCKS = SORT_BINS / 1024;   // 1024 bins per CTA
+
+    static __global__ void __launch_bounds__(256) k_sort_scan(uint32_t* hist, uint32_t* bin_start, uint32_t* block_offset,
+                                                              uint32_t* done_counter)
     {
-        __shared__ uint32_t warp_sums[32];
-        constexpr uint32_t PER_THREAD = SORT_BINS / 1024;
-        const uint32_t t = threadIdx.x, base = t * PER_THREAD;
-        uint32_t local[PER_THREAD];
-        uint32_t sum = 0;
-#pragma unroll 8
-        for (uint32_t k = 0; k < PER_THREAD; k += 4)
-        {
-            const uint4 v = *reinterpret_cast<const uint4*>(hist + base + k);
-            local[k] = v.x; local[k + 1] = v.y; local[k + 2] = v.z; local[k + 3] = v.w;
-            sum += v.x + v.y + v.z + v.w;
-            *reinterpret_cast<uint4*>(hist + base + k) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        // block exclusive scan of `sum`
+        __shared__ uint32_t warp_sums[8];
+        __shared__ uint32_t is_last;
+        const uint32_t t = threadIdx.x, base = blockIdx.x * 1024u + t * 4u;
+        const uint4 v = *reinterpret_cast<const uint4*>(hist + base);
+        *reinterpret_cast<uint4*>(hist + base) = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t sum = v.x + v.y + v.z + v.w;
         uint32_t incl = sum;
         for (int off = 1; off < 32; off <<= 1)
         {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if ((t & 31u) >= (uint32_t)off) incl += v;
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if ((t & 31u) >= (uint32_t)off) incl += u;
         }
         if ((t & 31u) == 31u) warp_sums[t >> 5] = incl;
         __syncthreads();
-        if (t < 32)
+        uint32_t warp_base = 0;
+        for (uint32_t w = 0; w < (t >> 5); w++) warp_base += warp_sums[w];
+        const uint32_t excl = warp_base + incl - sum;
+        *reinterpret_cast<uint4*>(bin_start + base) = make_uint4(excl, excl + v.x, excl + v.x + v.y, excl + v.x + v.y + v.z);
+        if (t == 255u)
         {
-            uint32_t w = warp_sums[t], wi = w;
-            for (int off = 1; off < 32; off <<= 1)
-            {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
-                if (t >= (uint32_t)off) wi += v;
-            }
-            warp_sums[t] = wi - w;
+            block_offset[SORT_SCAN_BLOCKS + blockIdx.x] = excl + sum;   // this CTA's total
+            __threadfence();
+            is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1u;
         }
         __syncthreads();
-        uint32_t run = warp_sums[t >> 5] + incl - sum;
-#pragma unroll 8
-        for (uint32_t k = 0; k < PER_THREAD; k++)
+        if (is_last && t < 32u)
         {
-            bin_start[base + k] = run;
-            run += local[k];
+            // exclusive scan of the CTA totals by one warp (SORT_SCAN_BLOCKS = 128 -> 4 per lane)
+            __threadfence();
+            constexpr uint32_t PER_LANE = SORT_SCAN_BLOCKS / 32;
+            uint32_t tot[PER_LANE], lane_sum = 0;
+            for (uint32_t k = 0; k < PER_LANE; k++) { tot[k] = block_offset[SORT_SCAN_BLOCKS + t * PER_LANE + k]; lane_sum += tot[k]; }
+            uint32_t inc = lane_sum;
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+                if (t >= (uint32_t)off) inc += u;
+            }
+            uint32_t run = inc - lane_sum;
+            for (uint32_t k = 0; k < PER_LANE; k++) { block_offset[t * PER_LANE + k] = run; run += tot[k]; }
+            if (t == 0) *done_counter = 0u;
         }
     }
 
     static __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* key, const uint32_t* rank, const uint32_t* bin_start,
-                                                                 uint32_t* order, const uint32_t* n_ptr)
+                                                                 const uint32_t* block_offset, uint32_t* order, const uint32_t* n_ptr)
     {
         const uint32_t n = *n_ptr;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         {
-            order[bin_start[key[i]] + rank[i]] = i;
+            const uint32_t k = key[i];
+            order[block_offset[k >> 10] + bin_start[k] + rank[i]] = i;
         }
     }
 

@@ -7,12 +7,15 @@ namespace mcrt
 {
     void launchAdvance(Counters* c, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(c); }
 
-    void launchSortScan(uint32_t* hist, uint32_t* bin_start, cudaStream_t s) { k_sort_scan<<<1, 1024, 0, s>>>(hist, bin_start); }
+    void launchSortScan(uint32_t* hist, const RaySort& rs, cudaStream_t s)
+    {
+        k_sort_scan<<<SORT_SCAN_BLOCKS, 256, 0, s>>>(hist, rs.bin_start, rs.block_offset, rs.done_counter);
+    }
 
-    void launchSortScatter(const uint32_t* key, const uint32_t* rank, const uint32_t* bin_start, uint32_t* order,
+    void launchSortScatter(const uint32_t* key, const uint32_t* rank, const RaySort& rs, uint32_t* order,
                            const uint32_t* n_ptr, int grid, cudaStream_t s)
     {
-        k_sort_scatter<<<grid, 256, 0, s>>>(key, rank, bin_start, order, n_ptr);
+        k_sort_scatter<<<grid, 256, 0, s>>>(key, rank, rs.bin_start, rs.block_offset, order, n_ptr);
     }
 
     void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s)

@@ -19,8 +19,8 @@ namespace mcrt
     };
 
     void launchAdvance(Counters* c, cudaStream_t s);
-    void launchSortScan(uint32_t* hist, uint32_t* bin_start, cudaStream_t s);
-    void launchSortScatter(const uint32_t* key, const uint32_t* rank, const uint32_t* bin_start, uint32_t* order,
+    void launchSortScan(uint32_t* hist, const RaySort& rs, cudaStream_t s);
+    void launchSortScatter(const uint32_t* key, const uint32_t* rank, const RaySort& rs, uint32_t* order,
                            const uint32_t* n_ptr, int grid, cudaStream_t s);
     void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s);
     void launchKnnUser(const DevicePhotonMap& map, uint32_t k, const double* points, size_t n, uint32_t* out_index,

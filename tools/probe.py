@@ -11,6 +11,7 @@ ap.add_argument("pack"); ap.add_argument("--width", type=int); ap.add_argument("
 ap.add_argument("--sqrtspp", type=int); ap.add_argument("--modes", default="f64,f32")
 ap.add_argument("--pool", type=float); ap.add_argument("--bps", type=float); ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--compare", action="store_true")
+ap.add_argument("--opt", action="append", default=[], help="key=value option")
 a = ap.parse_args()
 scene = m.Scene.from_pack(a.pack)
 cam = scene.cameras()[0]
@@ -22,6 +23,8 @@ for mode in a.modes.split(","):
     if a.pool: pt.set_option("pool_paths", a.pool)
     if a.bps: pt.set_option("blocks_per_sm", a.bps)
     pt.set_option("stage_timing", 1)
+    for kv in a.opt:
+        k, v = kv.split("="); pt.set_option(k, float(v))
     for r in range(a.reps):
         t = time.time(); img = pt.render_rows(cam); wall = time.time() - t
         st = pt.last_stats
