@@ -63,6 +63,7 @@ struct mcrt_ctx
     WaveBuffers<float> wave32;
     std::vector<void*> wave_allocs64, wave_allocs32;
 
+    uint32_t* d_sobol_bytes = nullptr;
     Counters* d_counters = nullptr;
     Counters* h_counters = nullptr; // pinned, 2 slots
     double* d_film = nullptr;
@@ -88,7 +89,7 @@ struct mcrt_ctx
 
     // options
     int sort_rays = 1;
-    int sort_shade = 1;
+    int sort_shade = 0;
     uint32_t pool_paths = 1u << 22;
     int blocks_per_sm = 8;
     double ray_eps_scale = 1e-5;
@@ -481,6 +482,7 @@ namespace
         p.shadow = wb.shadow;
         p.hits = wb.hits;
         p.counters = ctx->d_counters;
+        p.sobol_bytes = ctx->d_sobol_bytes;
         p.film = ctx->d_film;
         p.user_rays = d_user_rays; p.user_pixel = d_user_pixel; p.user_sample = d_user_sample;
         p.capacity = wb.capacity;
@@ -501,7 +503,7 @@ namespace
             {
                 const double ext = ctx->scene_bmax[k] - ctx->scene_bmin[k];
                 p.sort.key_min[k] = (float)ctx->scene_bmin[k];
-                p.sort.key_scale[k] = ext > 0.0 ? (float)(16.0 / ext) : 0.0f;
+                p.sort.key_scale[k] = ext > 0.0 ? (float)((double)(1u << SORT_ORIGIN_BITS) / ext) : 0.0f;
             }
         }
 
@@ -688,6 +690,12 @@ int mcrt_init(int device, mcrt_ctx** out_ctx)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(MCRT_ERR_CUDA);
     if (cudaMalloc((void**)&ctx->d_counters, sizeof(Counters)) != cudaSuccess) return fail(MCRT_ERR_CUDA);
     if (cudaMallocHost((void**)&ctx->h_counters, 2 * sizeof(Counters)) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    {
+        std::vector<uint32_t> tab(6 * 4 * 256);
+        makeSobolByteTable(tab.data());
+        if (cudaMalloc((void**)&ctx->d_sobol_bytes, tab.size() * 4) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+        if (cudaMemcpy(ctx->d_sobol_bytes, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail(MCRT_ERR_CUDA);
+    }
     if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) return fail(MCRT_ERR_CUDA);
     for (int i = 0; i < 2; i++)
         if (cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming) != cudaSuccess) return fail(MCRT_ERR_CUDA);
@@ -709,6 +717,7 @@ void mcrt_destroy(mcrt_ctx* ctx)
     if (ctx->knn_queue32) cudaFree(ctx->knn_queue32);
     if (ctx->d_film) cudaFree(ctx->d_film);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);

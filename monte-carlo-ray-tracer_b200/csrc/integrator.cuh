@@ -30,6 +30,12 @@
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 2
 #endif
+#ifndef MCRT_SORT_ORIGIN_BITS
+#define MCRT_SORT_ORIGIN_BITS 4
+#endif
+#ifndef MCRT_SORT_DIR_Q
+#define MCRT_SORT_DIR_Q 1
+#endif
 
 namespace mcrt
 {
@@ -52,10 +58,10 @@ namespace mcrt
         V4<R>* ray_o;    // start.xyz, medium_ior
         V4<R>* ray_d;    // direction.xyz, refraction_scale
         V4<R>* thr;      // throughput.xyz, ls.bsdf_pdf
-        V4<R>* iors_a;   // ls.select_probability, iors[1..3]
-        V4<R>* iors_b;   // iors[4..7]
+        V4<R>* iors_a;   // iors[1..4]  (touched only while the path is inside nested media)
+        V4<R>* iors_b;   // iors[5..7]
         uint4* meta;     // pixel, sample, depth | diffuse_depth<<16, refraction_level
-        uint4* meta2;    // ls.light prim, ior_count | dirac<<8, film_index, source prim (fast mode)
+        uint4* meta2;    // ls.light as light index, ior_count | dirac<<8, film_index, source prim (fast mode)
     };
 
     template <class R> struct ShadowQueue
@@ -73,7 +79,10 @@ namespace mcrt
     // rank = atomicAdd(&hist[key], 1) when it appends an entry, k_sort_scan turns the histogram into
     // bin starts (and zeroes it), k_sort_scatter writes order[bin_start[key] + rank] = entry. The
     // consumers index their queue through `order`; state stays where it was written.
-    constexpr uint32_t SORT_KEY_BITS = 17;
+    constexpr uint32_t SORT_ORIGIN_BITS = MCRT_SORT_ORIGIN_BITS;          // per axis
+    constexpr uint32_t SORT_DIR_Q = MCRT_SORT_DIR_Q;                      // bits per in-face coordinate
+    constexpr uint32_t SORT_DIR_BITS = 3 + 2 * SORT_DIR_Q;
+    constexpr uint32_t SORT_KEY_BITS = 3 * SORT_ORIGIN_BITS + SORT_DIR_BITS;
     constexpr uint32_t SORT_BINS = 1u << SORT_KEY_BITS;
 
     struct RaySort
@@ -91,32 +100,62 @@ namespace mcrt
         uint32_t* done_counter;  // last-CTA-done counter of k_sort_scan
         uint32_t shade_sorted;   // 1: k_shade also walks the queue in sorted order
         uint32_t _pad;
-        float key_min[3], key_scale[3]; // origin -> cell: (o - key_min) * key_scale in [0, 16)
+        float key_min[3], key_scale[3]; // origin -> cell: (o - key_min) * key_scale in [0, 2^SORT_ORIGIN_BITS)
     };
 
-    MCRT_D uint32_t spreadBits4(uint32_t v) // 4 bits -> every third bit
+    MCRT_D uint32_t spreadBits3(uint32_t v) // bit k -> bit 3k (up to 10 bits)
     {
-        return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
     }
 
     template <class R>
     MCRT_D uint32_t rayKey(const RaySort& rs, const V3<R>& o, const V3<R>& d)
     {
+        constexpr float CELLS = (float)(1u << SORT_ORIGIN_BITS);
         float cx = ((float)o.x - rs.key_min[0]) * rs.key_scale[0];
         float cy = ((float)o.y - rs.key_min[1]) * rs.key_scale[1];
         float cz = ((float)o.z - rs.key_min[2]) * rs.key_scale[2];
-        uint32_t ix = (uint32_t)fminf(fmaxf(cx, 0.0f), 15.0f);
-        uint32_t iy = (uint32_t)fminf(fmaxf(cy, 0.0f), 15.0f);
-        uint32_t iz = (uint32_t)fminf(fmaxf(cz, 0.0f), 15.0f);
-        uint32_t cell = spreadBits4(ix) | (spreadBits4(iy) << 1) | (spreadBits4(iz) << 2);
+        uint32_t ix = (uint32_t)fminf(fmaxf(cx, 0.0f), CELLS - 1.0f);
+        uint32_t iy = (uint32_t)fminf(fmaxf(cy, 0.0f), CELLS - 1.0f);
+        uint32_t iz = (uint32_t)fminf(fmaxf(cz, 0.0f), CELLS - 1.0f);
+        uint32_t cell = spreadBits3(ix) | (spreadBits3(iy) << 1) | (spreadBits3(iz) << 2);
         float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
         float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-        uint32_t face, s0, s1;
-        if (ax >= ay && ax >= az) { face = dx < 0.0f ? 1u : 0u; s0 = dy < 0.0f; s1 = dz < 0.0f; }
-        else if (ay >= az)        { face = dy < 0.0f ? 3u : 2u; s0 = dx < 0.0f; s1 = dz < 0.0f; }
-        else                      { face = dz < 0.0f ? 5u : 4u; s0 = dx < 0.0f; s1 = dy < 0.0f; }
-        uint32_t dir = (face << 2) | (s0 << 1) | s1;   // 24 classes in 5 bits
-        return (dir << 12) | cell;
+        uint32_t face; float u, v, m;
+        if (ax >= ay && ax >= az) { face = dx < 0.0f ? 1u : 0u; u = dy; v = dz; m = ax; }
+        else if (ay >= az)        { face = dy < 0.0f ? 3u : 2u; u = dx; v = dz; m = ay; }
+        else                      { face = dz < 0.0f ? 5u : 4u; u = dx; v = dy; m = az; }
+        // in-face coordinates in [-1,1] -> SORT_DIR_Q bits each
+        constexpr float Q = (float)(1u << SORT_DIR_Q);
+        float inv = m > 0.0f ? 0.5f * Q / m : 0.0f;
+        uint32_t qu = (uint32_t)fminf(fmaxf(u * inv + 0.5f * Q, 0.0f), Q - 1.0f);
+        uint32_t qv = (uint32_t)fminf(fmaxf(v * inv + 0.5f * Q, 0.0f), Q - 1.0f);
+        uint32_t dir = (face << (2 * SORT_DIR_Q)) | (qu << SORT_DIR_Q) | qv;
+        return (dir << (3 * SORT_ORIGIN_BITS)) | cell;
+    }
+
+    // rank = atomicAdd(&hist[key], 1) with the lanes of a warp that share a key aggregated into one
+    // atomic (camera rays all fall into a handful of bins: un-aggregated that is ~0.5 M same-address
+    // atomics per launch). Call with the warp converged; lanes with pred == false do not take part.
+    MCRT_D uint32_t sortRank(uint32_t* hist, uint32_t key, bool pred)
+    {
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, pred);
+        uint32_t rank = 0;
+        if (pred)
+        {
+            const unsigned peers = __match_any_sync(active, key);
+            const unsigned lane = threadIdx.x & 31u;
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            rank = base + __popc(peers & ((1u << lane) - 1u));
+        }
+        return rank;
     }
 
     template <class R> struct WaveParams
@@ -142,6 +181,7 @@ namespace mcrt
         R ray_eps;              // C::EPSILON in parity mode; scale-aware in fast mode
         PhotonParams<R> pm;     // photon maps + k-NN query queue (photon-mapped renders only)
         RaySort sort;           // coherence sort of the path / shadow queues (null order = disabled)
+        const uint32_t* sobol_bytes; // byte-sliced Sobol matrices [6][4][256] (makeSobolByteTable)
     };
 
     // ------------------------------------------------------------------------------------------
@@ -256,8 +296,14 @@ namespace mcrt
         const unsigned long long base_work = c->next_work;
         const PathBuffer<R>& out = p.buf[next];
 
-        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x)
+        const uint32_t count_rounded = (count + 31u) & ~31u;
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count_rounded; j += gridDim.x * blockDim.x)
         {
+            const bool valid = j < count;
+            uint32_t key = 0;
+            const uint32_t slot = n_next + j;
+            if (valid)
+            {
             const unsigned long long w = base_work + j;
             uint32_t pixel, sample, film_index;
             V3<R> start, direction;
@@ -281,18 +327,17 @@ namespace mcrt
                 SamplerState smp = SamplerState::make(p.global_seed, pixel, sample, 0u);
                 cameraRay(p.camera, p.scene.scene_ior, pixel, smp, start, direction);
             }
-            const uint32_t slot = n_next + j;
             out.ray_o[slot] = V4<R>(start, p.scene.scene_ior);
             out.ray_d[slot] = V4<R>(direction, R(1));
             out.thr[slot] = V4<R>(R(1), R(1), R(1), R(0));
-            out.iors_a[slot] = V4<R>(R(0), R(0), R(0), R(0));
             out.meta[slot] = make_uint4(pixel, sample, 0u, 0u);
             out.meta2[slot] = make_uint4(NO_PRIM, 1u, film_index, NO_PRIM);
+            if (p.sort.path_order) key = rayKey(p.sort, start, direction);
+            }
             if (p.sort.path_order)
             {
-                const uint32_t key = rayKey(p.sort, start, direction);
-                p.sort.path_key[next][slot] = key;
-                p.sort.path_rank[next][slot] = atomicAdd(&p.sort.hist_path[key], 1u);
+                const uint32_t rank = sortRank(p.sort.hist_path, key, valid);
+                if (valid) { p.sort.path_key[next][slot] = key; p.sort.path_rank[next][slot] = rank; }
             }
         }
     }
@@ -371,6 +416,9 @@ namespace mcrt
     template <class R, int KIND>
     __global__ void __launch_bounds__(128, MCRT_SHADE_MINBLOCKS) k_shade(WaveParams<R> p, int cur)
     {
+        __shared__ SobolByteTables sobol_tab;
+        sobol_tab.fill(p.sobol_bytes);
+        __syncthreads();
         Counters* c = p.counters;
         const uint32_t n = c->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
@@ -416,17 +464,23 @@ namespace mcrt
                 ray.refraction = false;
                 const uint32_t film_index = meta2.z;
 
-                const V4<R> ia_ = in.iors_a[i];
-                ls_select = ia_.x;
                 iors[0] = sc.scene_ior;
                 if (ior_count > 1)
                 {
-                    iors[1] = ia_.y; iors[2] = ia_.z; iors[3] = ia_.w;
-                    if (ior_count > 4)
+                    const V4<R> ia_ = in.iors_a[i];
+                    iors[1] = ia_.x; iors[2] = ia_.y; iors[3] = ia_.z; iors[4] = ia_.w;
+                    if (ior_count > 5)
                     {
                         const V4<R> ib_ = in.iors_b[i];
-                        iors[4] = ib_.x; iors[5] = ib_.y; iors[6] = ib_.z; iors[7] = ib_.w;
+                        iors[5] = ib_.x; iors[6] = ib_.y; iors[7] = ib_.z;
                     }
+                }
+                // LightSample::select_probability of the light picked at the previous bounce,
+                // recomputed from the CDF exactly as Scene::selectLight does (scene.cpp:229-233)
+                if (ls_light != NO_PRIM)
+                {
+                    ls_select = sc.lights[ls_light].cdf;
+                    if (ls_light > 0) ls_select -= sc.lights[ls_light - 1].cdf;
                 }
 
                 if (ray.depth > local_max_depth) local_max_depth = ray.depth;
@@ -445,7 +499,8 @@ namespace mcrt
                 else
                 {
                     // Sampler::shuffle() was called depth+1 times (path-tracer.cpp:23)
-                    const SamplerState smp = SamplerState::make(p.global_seed, meta.x, meta.y, ray.depth + 1u);
+                    SamplerState smp = SamplerState::make(p.global_seed, meta.x, meta.y, ray.depth + 1u);
+                    smp.tab = &sobol_tab;
 
                     // RefractionHistory::externalIOR, ray.cpp:95-98
                     int ext_idx = ray.refraction_level - 1;
@@ -464,7 +519,7 @@ namespace mcrt
                         {
                             filmAddV(p.film, film_index, m.emittance * throughput);
                         }
-                        else if (ls_light == hit.prim)
+                        else if (ls_light != NO_PRIM && sc.lights[ls_light].prim == hit.prim)
                         {
                             R cos_light_theta = dot(ia.out, ia.normal);
                             R light_pdf = pow2(ia.t) / (ps.area * cos_light_theta);
@@ -527,7 +582,7 @@ namespace mcrt
                         const Light<R>& L = sc.lights[left];
                         ls_select = L.cdf;
                         if (left > 0) ls_select -= sc.lights[left - 1].cdf;
-                        ls_light = L.prim;
+                        ls_light = left;
 
                         V3<R> light_pos, light_normal;
                         sampleLightPoint(L, u[0], u[1], light_pos, light_normal);
@@ -611,27 +666,39 @@ namespace mcrt
                 }
             }
 
-            // ---- compaction: survivors → next path buffer, NEE candidates → shadow queue
+            // ---- compaction: survivors → next path buffer, NEE candidates → shadow queue.
+            // All four atomics (two queue appends, two sort ranks) are issued back to back so their
+            // round trips overlap; the stores follow.
             const uint32_t slot = warpAppend(&c->n_next, alive);
+            const uint32_t sslot = warpAppend(&c->n_shadow, want_shadow);
+            uint32_t pkey = 0, prank = 0, skey = 0, srank = 0;
+            if (sorting && alive)
+            {
+                // un-aggregated: lanes of an (unsorted) shade warp rarely share a bin
+                pkey = rayKey(p.sort, nray.start, nray.direction);
+                prank = atomicAdd(&p.sort.hist_path[pkey], 1u);
+            }
+            if (sorting && want_shadow)
+            {
+                skey = rayKey(p.sort, sh_o, sh_d);
+                srank = atomicAdd(&p.sort.hist_shadow[skey], 1u);
+            }
             if (alive)
             {
                 out.ray_o[slot] = V4<R>(nray.start, nray.medium_ior);
                 out.ray_d[slot] = V4<R>(nray.direction, nray.refraction_scale);
                 out.thr[slot] = V4<R>(throughput, ls_bsdf_pdf);
-                out.iors_a[slot] = V4<R>(ls_select, iors[1], iors[2], iors[3]);
-                if (ior_count > 4) out.iors_b[slot] = V4<R>(iors[4], iors[5], iors[6], iors[7]);
+                if (ior_count > 1)
+                {
+                    out.iors_a[slot] = V4<R>(iors[1], iors[2], iors[3], iors[4]);
+                    if (ior_count > 5) out.iors_b[slot] = V4<R>(iors[5], iors[6], iors[7], R(0));
+                }
                 out.meta[slot] = make_uint4(meta.x, meta.y, (nray.depth & 0xFFFFu) | (nray.diffuse_depth << 16),
                                             (uint32_t)nray.refraction_level);
                 out.meta2[slot] = make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
                                              sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
-                if (sorting)
-                {
-                    const uint32_t key = rayKey(p.sort, nray.start, nray.direction);
-                    p.sort.path_key[cur ^ 1][slot] = key;
-                    p.sort.path_rank[cur ^ 1][slot] = atomicAdd(&p.sort.hist_path[key], 1u);
-                }
+                if (sorting) { p.sort.path_key[cur ^ 1][slot] = pkey; p.sort.path_rank[cur ^ 1][slot] = prank; }
             }
-            const uint32_t sslot = warpAppend(&c->n_shadow, want_shadow);
             if (want_shadow)
             {
                 p.shadow.o[sslot] = V4<R>(sh_o, sh_bsdf_pdf);
@@ -639,12 +706,7 @@ namespace mcrt
                 p.shadow.k[sslot] = V4<R>(sh_k, sh_select);
                 p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
                                                   sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, 0u);
-                if (p.sort.shadow_order)
-                {
-                    const uint32_t key = rayKey(p.sort, sh_o, sh_d);
-                    p.sort.shadow_key[sslot] = key;
-                    p.sort.shadow_rank[sslot] = atomicAdd(&p.sort.hist_shadow[key], 1u);
-                }
+                if (sorting) { p.sort.shadow_key[sslot] = skey; p.sort.shadow_rank[sslot] = srank; }
             }
 
             if constexpr (KIND == 1)
@@ -730,11 +792,11 @@ namespace mcrt
         __syncthreads();
         if (is_last && t < 32u)
         {
-            // exclusive scan of the CTA totals by one warp (SORT_SCAN_BLOCKS = 128 -> 4 per lane)
+            // exclusive scan of the CTA totals by one warp (SORT_SCAN_BLOCKS / 32 consecutive per lane)
             __threadfence();
             constexpr uint32_t PER_LANE = SORT_SCAN_BLOCKS / 32;
-            uint32_t tot[PER_LANE], lane_sum = 0;
-            for (uint32_t k = 0; k < PER_LANE; k++) { tot[k] = block_offset[SORT_SCAN_BLOCKS + t * PER_LANE + k]; lane_sum += tot[k]; }
+            uint32_t lane_sum = 0;
+            for (uint32_t k = 0; k < PER_LANE; k++) lane_sum += block_offset[SORT_SCAN_BLOCKS + t * PER_LANE + k];
             uint32_t inc = lane_sum;
             for (int off = 1; off < 32; off <<= 1)
             {
@@ -742,7 +804,12 @@ namespace mcrt
                 if (t >= (uint32_t)off) inc += u;
             }
             uint32_t run = inc - lane_sum;
-            for (uint32_t k = 0; k < PER_LANE; k++) { block_offset[t * PER_LANE + k] = run; run += tot[k]; }
+            for (uint32_t k = 0; k < PER_LANE; k++)
+            {
+                const uint32_t tot = block_offset[SORT_SCAN_BLOCKS + t * PER_LANE + k];
+                block_offset[t * PER_LANE + k] = run;
+                run += tot;
+            }
             if (t == 0) *done_counter = 0u;
         }
     }

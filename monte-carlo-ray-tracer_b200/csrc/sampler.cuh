@@ -97,15 +97,19 @@ namespace mcrt
         DIM_PM_LIGHT = 0, DIM_PM_REJECT = 2
     };
 
+    struct SobolByteTables;
+
     struct SamplerState
     {
         uint32_t seed;
         uint32_t shuffled_index;
+        const SobolByteTables* tab;   // shared-memory byte tables (null: bit loop)
 
         // state after initiate(pixel), setIndex(sample) and `sequence` shuffle() calls
         MCRT_HD static SamplerState make(uint32_t global_seed, uint32_t pixel, uint32_t sample, uint32_t sequence)
         {
             SamplerState s;
+            s.tab = nullptr;
             uint32_t base_seed = samplerHashCombine(global_seed, samplerHash(pixel));
             if (sequence == 0)
             {
@@ -157,9 +161,61 @@ namespace mcrt
         return f < 1.0f ? f : 0x1.fffffep-1f;
     }
 
+    // Byte-sliced Sobol matrices for kernels that draw many dimensions per thread: entry [d][j][v] is
+    // the XOR of the direction numbers of dimension d+1 selected by byte j = v of the index, so one
+    // dimension costs 4 shared-memory lookups + 3 XOR instead of a 32-step bit loop. 6 x 4 x 256 x 4 B
+    // = 24 KB, filled per CTA from the compile-time direction numbers.
+    struct SobolByteTables
+    {
+        uint32_t t[6][4][256];
+
+        // cooperative copy of the host-built tables (makeSobolByteTable) into shared memory
+        MCRT_D void fill(const uint32_t* global_tables)
+        {
+            uint32_t* flat = &t[0][0][0];
+            for (uint32_t e = threadIdx.x; e < 6u * 4u * 256u; e += blockDim.x) flat[e] = __ldg(&global_tables[e]);
+        }
+
+        // raw 32-bit value of dimension `dim` (0..6) for the sampler state
+        MCRT_D uint32_t raw(const SamplerState& s, uint32_t dim) const
+        {
+            uint32_t acc = s.shuffled_index;
+            if (dim > 0)
+            {
+                const uint32_t i = s.shuffled_index;
+                acc = t[dim - 1][0][i & 255u] ^ t[dim - 1][1][(i >> 8) & 255u] ^ t[dim - 1][2][(i >> 16) & 255u] ^ t[dim - 1][3][i >> 24];
+            }
+            return samplerScramble(acc, samplerHashCombine(s.seed, samplerHash(dim)));
+        }
+
+        template <class R, int START, int N>
+        MCRT_D void get(const SamplerState& s, R* u) const
+        {
+#pragma unroll
+            for (int k = 0; k < N; k++) u[k] = unitFromBits(raw(s, (uint32_t)(START + k)), R(0));
+        }
+    };
+
+    // host-side builder of the byte tables (uploaded once per context)
+    inline void makeSobolByteTable(uint32_t* out /* [6*4*256] */)
+    {
+        const SobolTable T = makeSobolTable();
+        for (uint32_t d = 0; d < 6; d++)
+            for (uint32_t j = 0; j < 4; j++)
+                for (uint32_t v = 0; v < 256; v++)
+                {
+                    uint32_t x = 0;
+                    for (uint32_t b = 0; b < 8; b++) if ((v >> b) & 1u) x ^= T.v[d][j * 8 + b];
+                    out[(d * 4 + j) * 256 + v] = x;
+                }
+    }
+
     template <class R, int START, int N>
     MCRT_HD void samplerGet(const SamplerState& s, R* u)
     {
+#ifdef __CUDA_ARCH__
+        if (s.tab) { s.tab->template get<R, START, N>(s, u); return; }
+#endif
         uint32_t raw[7];
         s.raw<(((1u << N) - 1u) << START)>(raw);
 #pragma unroll
