@@ -1,0 +1,760 @@
+// ORACLE / TEST INFRASTRUCTURE — never linked into or imported by the product (libmcrt_b200.so).
+//
+// Scalar float64 CPU restatement of the reference's path-tracing hot path, operating on the
+// flattened scene description of include/mcrt_abi.h. One path at a time, the way the reference
+// runs it; no SIMD, no threads. Build: g++ -O2 -ffp-contract=off (oracle/build_oracle.py).
+// Pinned against the unmodified reference through tests/golden/*.npz (tests/test_oracle_cpu.py):
+// sampler streams bit-exact, Scene::intersect same primitive and t, per-sample radiance and images
+// to 1e-9. Each function cites the reference lines it restates (paths relative to /root/reference).
+//
+// Not restated here: the photon mapper (checked directly against golden outputs on the GPU).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "mcrt_abi.h"
+
+namespace
+{
+    struct D3
+    {
+        double x, y, z;
+        D3() : x(0), y(0), z(0) {}
+        D3(double a, double b, double c) : x(a), y(b), z(c) {}
+        explicit D3(const double* p) : x(p[0]), y(p[1]), z(p[2]) {}
+    };
+    inline D3 operator+(D3 a, D3 b) { return D3(a.x + b.x, a.y + b.y, a.z + b.z); }
+    inline D3 operator-(D3 a, D3 b) { return D3(a.x - b.x, a.y - b.y, a.z - b.z); }
+    inline D3 operator*(D3 a, D3 b) { return D3(a.x * b.x, a.y * b.y, a.z * b.z); }
+    inline D3 operator/(D3 a, D3 b) { return D3(a.x / b.x, a.y / b.y, a.z / b.z); }
+    inline D3 operator*(D3 a, double s) { return D3(a.x * s, a.y * s, a.z * s); }
+    inline D3 operator*(double s, D3 a) { return D3(s * a.x, s * a.y, s * a.z); }
+    inline D3 operator/(D3 a, double s) { return D3(a.x / s, a.y / s, a.z / s); }
+    inline D3 operator-(D3 a) { return D3(-a.x, -a.y, -a.z); }
+    // GLM evaluation orders: lib/glm/glm/detail/func_geometric.inl:48-55,66-78,88,104-108
+    inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+    inline D3 cross(D3 a, D3 b) { return D3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+    inline D3 normalize(D3 v) { return v * (1.0 / std::sqrt(dot(v, v))); }
+    inline double gmin(double x, double y) { return (y < x) ? y : x; }   // func_common.inl:17-30
+    inline double gmax(double x, double y) { return (x < y) ? y : x; }
+    inline double sq(double x) { return x * x; }
+    inline double mixd(double x, double y, double a) { return x * (1.0 - a) + y * a; }
+    inline D3 mix3(D3 x, D3 y, double a) { return x * (1.0 - a) + y * a; }
+    inline double compMax(D3 v) { return gmax(gmax(v.x, v.y), v.z); }
+    inline double compMin(D3 v) { return gmin(gmin(v.x, v.y), v.z); }
+
+    const double PI = 3.14159265358979323846, INV_PI = 0.31830988618379067154, TWO_PI = 6.283185307179586476925;
+    const double EPS = 1e-9; // source/common/constants.hpp:5-9
+
+    // ---------------------------------------------------------------- sampler (sampler.hpp, sobol.hpp)
+    uint32_t reverseBits(uint32_t x) // sobol.hpp:9-16
+    {
+        x = ((x & 0xaaaaaaaau) >> 1) | ((x & 0x55555555u) << 1);
+        x = ((x & 0xccccccccu) >> 2) | ((x & 0x33333333u) << 2);
+        x = ((x & 0xf0f0f0f0u) >> 4) | ((x & 0x0f0f0f0fu) << 4);
+        x = ((x & 0xff00ff00u) >> 8) | ((x & 0x00ff00ffu) << 8);
+        return (x >> 16) | (x << 16);
+    }
+
+    struct Directions
+    {
+        uint32_t v[6][32];
+        Directions() // sobol.hpp:18-56 with the Joe-Kuo (s, a, m) rows for dimensions 2..7
+        {
+            const uint32_t s[6] = { 1, 2, 3, 3, 4, 4 }, a[6] = { 0, 1, 1, 2, 1, 4 };
+            const uint32_t m[6][4] = { { 1, 0, 0, 0 }, { 1, 3, 0, 0 }, { 1, 3, 1, 0 }, { 1, 1, 1, 0 }, { 1, 1, 3, 3 }, { 1, 3, 5, 13 } };
+            for (int d = 0; d < 6; d++)
+            {
+                uint32_t V[32];
+                for (uint32_t b = 0; b < 32; b++)
+                {
+                    if (b < s[d]) V[b] = m[d][b] << (31 - b);
+                    else
+                    {
+                        V[b] = V[b - s[d]] ^ (V[b - s[d]] >> s[d]);
+                        for (uint32_t k = 1; k < s[d]; k++) V[b] ^= (((a[d] >> (s[d] - 1 - k)) & 1u) * V[b - k]);
+                    }
+                }
+                for (int b = 0; b < 32; b++) v[d][b] = reverseBits(V[b]);
+            }
+        }
+    };
+    const Directions DIRS;
+
+    uint32_t hash32(uint32_t x) { x ^= x >> 15; x *= 0xd168aaadu; x ^= x >> 15; x *= 0xaf723597u; x ^= x >> 15; return x; } // sampler.hpp:78-86
+    uint32_t combine(uint32_t seed, uint32_t v) { return seed ^ (v + 0x9e3779b9u + (seed << 6) + (seed >> 2)); }            // :89-92
+    uint32_t scramble(uint32_t x, uint32_t seed)                                                                           // :61-73
+    {
+        x ^= x * 0x3d20adeau; x += seed; x *= (seed >> 16) | 1u; x ^= x * 0x05526c56u; x ^= x * 0x53a22864u;
+        return reverseBits(x);
+    }
+
+    struct Sampler // the thread_local registers of sampler.hpp:55-56
+    {
+        uint32_t global_seed, base_seed = 0, seed = 0, sequence = 0, bit_reversed_index = 0, shuffled_index = 0;
+        explicit Sampler(uint32_t g) : global_seed(g) {}
+        void initiate(uint32_t start) { base_seed = combine(global_seed, hash32(start)); }
+        void setIndex(uint32_t i) { sequence = 0; seed = base_seed; bit_reversed_index = reverseBits(i); shuffled_index = i; }
+        void shuffle() { seed = combine(base_seed, hash32(++sequence)); shuffled_index = scramble(bit_reversed_index, seed); }
+        uint32_t raw(int dim) const
+        {
+            uint32_t x = shuffled_index;
+            if (dim > 0)
+            {
+                x = 0;
+                uint32_t index = shuffled_index;
+                for (int bit = 0; index; index >>= 1, bit++) x ^= (index & 1u) * DIRS.v[dim - 1][bit];
+            }
+            return scramble(x, combine(seed, hash32((uint32_t)dim)));
+        }
+        double get(int dim) const { return raw(dim) * 0x1p-32; }
+    };
+    enum { PIXEL = 0, LENS = 2, LIGHT = 0, BSDF = 3, INTERACTION = 5, ABSORB = 6 }; // sampling.hpp:59-76
+
+    // ---------------------------------------------------------------- scene
+    struct Scene
+    {
+        mcrt_scene_desc d;
+        std::vector<double> node_bounds, prim_area, tri_v0, tri_v1, tri_v2, tri_e1, tri_e2, tri_n, vn, sph, qQ, qG, qB, light_cdf;
+        std::vector<uint32_t> node_first, node_count, node_next, prim_index, prim_material, light_prim;
+        std::vector<uint8_t> prim_type;
+        std::vector<int32_t> tri_vn;
+        std::vector<mcrt_material> materials;
+    };
+
+    template <class T> void copyv(std::vector<T>& dst, const T* src, size_t n) { dst.assign(src, src + (src ? n : 0)); }
+
+    struct Ray
+    {
+        D3 start, direction, inv_direction;
+        double medium_ior = 1.0, refraction_scale = 1.0;
+        bool dirac_delta = false, refraction = false;
+        uint32_t depth = 0, diffuse_depth = 0;
+        int refraction_level = 0;
+        D3 at(double t) const { return start + direction * t; }
+    };
+    Ray makeRay(D3 start, D3 dir, double ior) // ray.cpp:13-14
+    {
+        Ray r; r.start = start; r.direction = dir; r.inv_direction = D3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z); r.medium_ior = ior;
+        return r;
+    }
+    Ray rayTo(D3 start, D3 end) { return makeRay(start, normalize(end - start), 1.0); } // ray.cpp:10-11
+
+    struct Isect { double t = std::numeric_limits<double>::max(); double u = 0, v = 0; uint32_t prim = 0xFFFFFFFFu; bool interpolate = false; };
+
+    bool slab(const double* b, const Ray& r, double& t) // bounding-box.cpp:9-17
+    {
+        D3 t0 = (D3(b) - r.start) * r.inv_direction, t1 = (D3(b + 3) - r.start) * r.inv_direction;
+        D3 lo(gmin(t0.x, t1.x), gmin(t0.y, t1.y), gmin(t0.z, t1.z)), hi(gmax(t0.x, t1.x), gmax(t0.y, t1.y), gmax(t0.z, t1.z));
+        t = gmax(compMax(lo), 0.0);
+        return compMin(hi) >= t;
+    }
+
+    bool solveQuadratic(double a, double b, double c, double& t_min, double& t_max) // util.hpp:60-83
+    {
+        if (a != 0.0)
+        {
+            double d = b * b - 4.0 * a * c;
+            if (d < 0.0) return false;
+            double t = -0.5 * (b + (b < 0.0 ? -std::sqrt(d) : std::sqrt(d)));
+            t_min = t / a; t_max = c / t;
+            if (t_min > t_max) std::swap(t_min, t_max);
+            return true;
+        }
+        if (b != 0.0) { t_min = t_max = -c / b; return true; }
+        return false;
+    }
+
+    bool hitPrim(const Scene& s, uint32_t prim, const Ray& r, Isect& out)
+    {
+        const uint32_t idx = s.prim_index[prim];
+        if (s.prim_type[prim] == MCRT_PRIM_TRIANGLE) // triangle.cpp:23-63
+        {
+            D3 v0(&s.tri_v0[3 * idx]), E1(&s.tri_e1[3 * idx]), E2(&s.tri_e2[3 * idx]);
+            D3 P = cross(r.direction, E2);
+            double det = dot(P, E1);
+            if (det < EPS && det > -EPS) return false;
+            double inv = 1.0 / det;
+            D3 T = r.start - v0;
+            double u = dot(P, T) * inv;
+            if (u > 1.0 || u < 0.0) return false;
+            D3 Q = cross(T, E1);
+            double v = dot(Q, r.direction) * inv;
+            if (v > 1.0 || v < 0.0 || u + v > 1.0) return false;
+            double t = dot(Q, E2) * inv;
+            if (t <= 0.0) return false;
+            out = Isect(); out.t = t;
+            if (s.tri_vn[idx] >= 0) { out.u = u; out.v = v; out.interpolate = true; }
+            return true;
+        }
+        if (s.prim_type[prim] == MCRT_PRIM_SPHERE) // sphere.cpp:13-26
+        {
+            const double* sp = &s.sph[4 * idx];
+            D3 so = r.start - D3(sp);
+            double b = 2.0 * dot(r.direction, so), c = dot(so, so) - sq(sp[3]);
+            double t_min, t_max;
+            if (solveQuadratic(1.0, b, c, t_min, t_max) && t_max >= 0.0) { out = Isect(); out.t = t_min < 0.0 ? t_max : t_min; return true; }
+            return false;
+        }
+        // quadric.cpp:69-100
+        const double* Q = &s.qQ[16 * idx]; const double* B = &s.qB[6 * idx];
+        double t_bb = 0.0;
+        if (!slab(B, r, t_bb)) return false;
+        D3 p = r.at(t_bb);
+        double o[4] = { p.x, p.y, p.z, 1.0 }, d[4] = { r.direction.x, r.direction.y, r.direction.z, 0.0 }, Qo[4], Qd[4];
+        for (int k = 0; k < 4; k++) // glm mat4*vec4: (m0 v0 + m1 v1) + (m2 v2 + m3 v3)
+        {
+            Qo[k] = (Q[k] * o[0] + Q[4 + k] * o[1]) + (Q[8 + k] * o[2] + Q[12 + k] * o[3]);
+            Qd[k] = (Q[k] * d[0] + Q[4 + k] * d[1]) + (Q[8 + k] * d[2] + Q[12 + k] * d[3]);
+        }
+        auto dot4 = [](const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]); };
+        double a = dot4(d, Qd), b = dot4(d, Qo) * 2.0, c = dot4(o, Qo), t_min, t_max;
+        if (solveQuadratic(a, b, c, t_min, t_max) && t_max >= 0.0)
+        {
+            double t = t_bb + (t_min < 0.0 ? t_max : t_min);
+            D3 q = r.at(t);
+            if (!(q.x >= B[0] && q.y >= B[1] && q.z >= B[2] && q.x <= B[3] && q.y <= B[4] && q.z <= B[5])) return false;
+            out = Isect(); out.t = t;
+            return true;
+        }
+        return false;
+    }
+
+    // Scene::intersect + BVH::intersect (scene.cpp:151-176, bvh.cpp:80-129) with the reference's
+    // PriorityQueue push/pop (priority-queue.hpp:19-46,107-126)
+    struct NodeHit { double t; uint32_t node; };
+    struct Heap
+    {
+        std::vector<NodeHit> H;
+        static bool less(const NodeHit& a, const NodeHit& b) { return b.t < a.t; } // bvh.hpp:78
+        void push(NodeHit v)
+        {
+            H.push_back(v);
+            size_t i = H.size() - 1;
+            while (i > 0) { size_t p = (i - 1) / 2; if (!less(H[p], v)) break; H[i] = H[p]; i = p; }
+            H[i] = v;
+        }
+        void shiftDown(NodeHit v, size_t i)
+        {
+            while (true)
+            {
+                size_t l = 2 * i + 1, r = l + 1, m;
+                if (r < H.size()) m = l + (less(H[l], H[r]) ? 1 : 0);
+                else if (l < H.size()) m = l;
+                else break;
+                if (!less(v, H[m])) break;
+                H[i] = H[m]; i = m;
+            }
+            H[i] = v;
+        }
+        void pop() { if (H.size() > 1) { NodeHit v = H.back(); H.pop_back(); shiftDown(v, 0); } else H.pop_back(); }
+    };
+
+    Isect intersect(const Scene& s, const Ray& r, uint64_t* counter)
+    {
+        if (counter) (*counter)++;
+        Isect best;
+        const uint32_t n_prims = (uint32_t)s.prim_type.size();
+        if (s.node_first.empty())
+        {
+            for (uint32_t i = 0; i < n_prims; i++) { Isect c; if (hitPrim(s, i, r, c) && c.t < best.t) { best = c; best.prim = i; } }
+            return best;
+        }
+        Heap heap;
+        double t;
+        if (!slab(&s.node_bounds[0], r, t)) return best;
+        uint32_t node = 0;
+        while (true)
+        {
+            if (s.node_count[node])
+            {
+                for (uint32_t i = s.node_first[node]; i < s.node_first[node] + s.node_count[node]; i++)
+                {
+                    Isect c;
+                    if (hitPrim(s, i, r, c) && c.t < best.t) { best = c; best.prim = i; }
+                }
+            }
+            else
+            {
+                uint32_t child = node + 1;
+                while (child != 0)
+                {
+                    if (slab(&s.node_bounds[6 * child], r, t) && t < best.t) heap.push({ t, child });
+                    child = s.node_next[child];
+                }
+            }
+            if (heap.H.empty() || heap.H.front().t >= best.t) break;
+            node = heap.H.front().node;
+            heap.pop();
+        }
+        return best;
+    }
+
+    // ---------------------------------------------------------------- materials (fresnel.cpp, ggx.cpp, material.cpp)
+    double fresnelDielectric(double n1, double n2, double c) // fresnel.cpp:16-27
+    {
+        double g2 = sq(n2 / n1) + sq(c) - 1.0;
+        if (g2 < 0.0) return 1.0;
+        double g = std::sqrt(g2), gp = g + c, gm = g - c;
+        return 0.5 * sq(gm / gp) * (1.0 + sq((gp * c - 1.0) / (gm * c + 1.0)));
+    }
+    D3 vsqrt(D3 v) { return D3(std::sqrt(v.x), std::sqrt(v.y), std::sqrt(v.z)); }
+    D3 adds(D3 v, double s) { return D3(v.x + s, v.y + s, v.z + s); }
+    D3 fresnelConductor(double n1, D3 re, D3 im, double c) // fresnel.cpp:30-49
+    {
+        double c2 = sq(c), s2 = 1.0 - c2;
+        D3 er = re / n1, ei = im / n1, eta2 = er * er, etak2 = ei * ei;
+        D3 t0 = adds(eta2 - etak2, -s2);
+        D3 a2b2 = vsqrt(t0 * t0 + 4.0 * eta2 * etak2);
+        D3 t1 = adds(a2b2, c2);
+        D3 t2 = (2.0 * c) * vsqrt(0.5 * (a2b2 + t0));
+        D3 rs = (t1 - t2) / (t1 + t2);
+        D3 t3 = adds(c2 * a2b2, sq(s2)), t4 = t2 * s2;
+        D3 rp = rs * (t3 - t4) / (t3 + t4);
+        return (rp + rs) * 0.5;
+    }
+    double ggxD(D3 m, double ax, double ay) { return 1.0 / (PI * ax * ay * sq(sq(m.x / ax) + sq(m.y / ay) + sq(m.z))); }          // ggx.cpp:21-24
+    double ggxLambda(D3 w, double ax, double ay) { return (-1.0 + std::sqrt(1.0 + (sq(ax * w.x) + sq(ay * w.y)) / (sq(w.z)))) / 2.0; } // :31-34
+    double ggxG1(D3 w, double ax, double ay) { return 1.0 / (1.0 + ggxLambda(w, ax, ay)); }
+    double ggxG2(D3 wi, D3 wo, double ax, double ay) { return 1.0 / (1.0 + ggxLambda(wo, ax, ay) + ggxLambda(wi, ax, ay)); }
+    double ggxDV(D3 m, D3 wo, double ax, double ay) { return ggxG1(wo, ax, ay) * dot(wo, m) * ggxD(m, ax, ay) / wo.z; }
+    double ggxReflection(D3 wi, D3 wo, double ax, double ay, double& pdf) // :46-52
+    {
+        D3 m = normalize(wo + wi);
+        pdf = ggxDV(m, wo, ax, ay) / (4.0 * dot(m, wo));
+        return ggxD(m, ax, ay) * ggxG2(wi, wo, ax, ay) / (4.0 * wo.z * wi.z);
+    }
+    double ggxTransmission(D3 wi, D3 wo, double n1, double n2, double ax, double ay, double& pdf) // :54-65
+    {
+        D3 m = wo * n1 + wi * n2;
+        double l2 = dot(m, m);
+        m = m / std::sqrt(l2);
+        if (n1 < n2) m = -m;
+        double dm = sq(n2) * std::abs(dot(wi, m)) / l2;
+        pdf = ggxDV(m, wo, ax, ay) * dm;
+        return std::abs(ggxG2(wi, wo, ax, ay) * ggxD(m, ax, ay) * dot(wo, m) * dm / (wo.z * wi.z));
+    }
+    D3 ggxVisibleMicrofacet(double u, double v, D3 wo, double ax, double ay) // :67-89
+    {
+        D3 Vh = normalize(D3(ax * wo.x, ay * wo.y, wo.z));
+        double len2 = sq(Vh.x) + sq(Vh.y);
+        D3 T1 = len2 > 0.0 ? D3(-Vh.y, Vh.x, 0.0) * (1.0 / std::sqrt(len2)) : D3(1.0, 0.0, 0.0);
+        D3 T2 = cross(Vh, T1);
+        double r = std::sqrt(u), phi = v * TWO_PI;
+        double t1 = r * std::cos(phi), t2 = r * std::sin(phi);
+        double s = 0.5 * (1.0 + Vh.z);
+        t2 = (1.0 - s) * std::sqrt(1.0 - sq(t1)) + s * t2;
+        D3 Nh = t1 * T1 + t2 * T2 + std::sqrt(std::max(0.0, 1.0 - sq(t1) - sq(t2))) * Vh;
+        return normalize(D3(ax * Nh.x, ay * Nh.y, std::max(0.0, Nh.z)));
+    }
+
+    D3 diffuseReflection(const mcrt_material& m, D3 wi, D3 wo, double& pdf) // material.cpp:17-27,76-95
+    {
+        if (wi.z < 0.0) { pdf = 0.0; return D3(); }
+        pdf = wi.z * INV_PI;
+        D3 lambert = D3(m.reflectance) * INV_PI;
+        if (!m.rough) return lambert;
+        double cdp = gmin(gmax((wi.x * wo.x + wi.y * wo.y) / std::sqrt((sq(wi.x) + sq(wi.y)) * (sq(wo.x) + sq(wo.y))), 0.0), 1.0);
+        double Dd = std::sqrt((1.0 - sq(wi.z)) * (1.0 - sq(wo.z))) / std::max(wi.z, wo.z);
+        return lambert * (m.A + m.B * cdp * Dd);
+    }
+    D3 specularReflection(const mcrt_material& m, D3 wi, D3 wo, double& pdf) // material.cpp:29-45
+    {
+        if (wi.z < 0.0) { pdf = 0.0; return D3(); }
+        if (m.rough_specular) return D3(m.specular_reflectance) * ggxReflection(wi, wo, m.a[0], m.a[1], pdf);
+        pdf = 1.0;
+        return D3(m.specular_reflectance) / std::abs(wi.z);
+    }
+    D3 specularTransmission(const mcrt_material& m, D3 wi, D3 wo, double n1, double n2, double& pdf, bool inside, bool flux) // :47-69
+    {
+        if (wi.z > 0.0) { pdf = 0.0; return D3(); }
+        D3 btdf = !inside ? D3(m.transmittance) : D3(1, 1, 1);
+        if (m.rough_specular)
+        {
+            btdf = btdf * ggxTransmission(wi, wo, n1, n2, m.a[0], m.a[1], pdf);
+            if (flux) btdf = btdf * sq(n2 / n1);
+        }
+        else
+        {
+            pdf = 1.0;
+            btdf = btdf * (D3(m.transmittance) / std::abs(wi.z));
+            if (!flux) btdf = btdf * sq(n1 / n2);
+        }
+        return btdf;
+    }
+
+    // ---------------------------------------------------------------- coordinate system (coordinate-system.cpp:7-40)
+    struct Frame
+    {
+        D3 c0, c1, c2;
+        Frame() {}
+        explicit Frame(D3 N)
+        {
+            double sign = std::copysign(1.0, N.z), a = -1.0 / (sign + N.z), b = N.x * N.y * a;
+            c0 = D3(1.0 + sign * N.x * N.x * a, sign * b, -sign * N.x);
+            c1 = D3(b, sign + N.y * N.y * a, -N.y);
+            c2 = N;
+        }
+        D3 from(D3 v) const { return D3(c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z, c0.z * v.x + c1.z * v.y + c2.z * v.z); }
+        D3 to(D3 v) const { return D3(c0.x * v.x + c0.y * v.y + c0.z * v.z, c1.x * v.x + c1.y * v.y + c1.z * v.z, c2.x * v.x + c2.y * v.y + c2.z * v.z); }
+    };
+
+    // ---------------------------------------------------------------- Interaction (interaction.cpp)
+    enum { REFLECT, REFRACT, DIFFUSE };
+    struct Interaction
+    {
+        int type; double t, n1, n2, T, R;
+        const mcrt_material* material; uint32_t prim;
+        D3 position, normal, out; Frame cs; bool inside, dirac_delta; Ray ray;
+
+        D3 bsdfLocal(D3 wo, D3 wi, double& pdf, bool flux, bool wi_dirac) const // interaction.cpp:84-153
+        {
+            const mcrt_material& m = *material;
+            double cos_theta = wo.z;
+            if (m.rough_specular)
+            {
+                if (wi.z > 0.0) cos_theta = dot(wo, normalize(wo + wi));
+                else { D3 h = normalize(wo * n1 + wi * n2); cos_theta = dot(wo, h); if (n1 < n2) cos_theta = -cos_theta; }
+            }
+            if (m.perfect_mirror || m.has_complex_ior)
+            {
+                D3 brdf = specularReflection(m, wi, wo, pdf);
+                if (m.has_complex_ior) brdf = brdf * fresnelConductor(n1, D3(m.complex_ior_real), D3(m.complex_ior_imag), cos_theta);
+                return brdf;
+            }
+            if (n2 < 1.0) return diffuseReflection(m, wi, wo, pdf);
+            double F = fresnelDielectric(n1, n2, cos_theta), pdf_s, pdf_d;
+            D3 brdf_s = specularReflection(m, wi, wo, pdf_s), brdf_d = diffuseReflection(m, wi, wo, pdf_d);
+            double pdf_t = pdf_s; D3 btdf = brdf_s;
+            if (F < 1.0) btdf = specularTransmission(m, wi, wo, n1, n2, pdf_t, inside, flux);
+            if (wi_dirac)
+            {
+                if (type == REFLECT) { pdf = R; return brdf_s * F; }
+                pdf = T * (1.0 - R); return btdf * T * (1.0 - F);
+            }
+            else if (!m.rough_specular) { pdf = pdf_d * (1.0 - R) * (1.0 - T); return brdf_d * (1.0 - F) * (1.0 - T); }
+            pdf = mixd(mixd(pdf_d, pdf_t, T), pdf_s, R);
+            return mix3(mix3(brdf_d, btdf, T), brdf_s, F);
+        }
+        bool bsdfWorld(D3& f, D3 world_wi, double& pdf) const // interaction.cpp:74-82
+        {
+            D3 wi = cs.to(world_wi), wo = cs.to(out);
+            f = bsdfLocal(wo, wi, pdf, false, false) * std::abs(wi.z);
+            return pdf > 0.0;
+        }
+    };
+
+    D3 primNormal(const Scene& s, uint32_t prim, D3 pos)
+    {
+        const uint32_t idx = s.prim_index[prim];
+        if (s.prim_type[prim] == MCRT_PRIM_TRIANGLE) return D3(&s.tri_n[3 * idx]);
+        if (s.prim_type[prim] == MCRT_PRIM_SPHERE) return (pos - D3(&s.sph[4 * idx])) / s.sph[4 * idx + 3];
+        const double* G = &s.qG[12 * idx]; // quadric.cpp:129-132, type_mat4x3.inl:474-477
+        return normalize(D3(G[0] * pos.x + G[3] * pos.y + G[6] * pos.z + G[9] * 1.0, G[1] * pos.x + G[4] * pos.y + G[7] * pos.z + G[10] * 1.0,
+                            G[2] * pos.x + G[5] * pos.y + G[8] * pos.z + G[11] * 1.0));
+    }
+
+    Interaction makeInteraction(const Scene& s, const Isect& is, const Ray& ray, double external_ior, const Sampler& smp) // interaction.cpp:12-54,156-183
+    {
+        Interaction ia;
+        ia.t = is.t; ia.ray = ray; ia.out = -ray.direction; ia.n1 = ray.medium_ior; ia.prim = is.prim;
+        ia.material = &s.materials[s.prim_material[is.prim]];
+        const mcrt_material& m = *ia.material;
+        ia.position = ray.at(is.t);
+        D3 normal = primNormal(s, is.prim, ia.position);
+        double cos_theta = dot(ray.direction, normal);
+        ia.inside = cos_theta > 0.0;
+        ia.n2 = (ia.inside && !m.opaque) ? external_ior : m.ior;
+        D3 sn = normal;
+        if (is.interpolate)
+        {
+            const double* N = &s.vn[9 * s.tri_vn[s.prim_index[is.prim]]];
+            sn = normalize((1.0 - is.u - is.v) * D3(N) + is.u * D3(N + 3) + is.v * D3(N + 6)); // triangle.cpp:109-113
+            if ((cos_theta < 0.0) != (dot(ray.direction, sn) < 0.0)) sn = normal;
+        }
+        if (cos_theta > 0.0) { normal = -normal; sn = -sn; }
+        ia.normal = normal;
+        ia.cs = Frame(sn);
+        ia.R = fresnelDielectric(ia.n1, ia.n2, dot(sn, ia.out));
+        ia.T = m.transparency;
+        if (m.rough_specular) ia.R = gmin(gmax(ia.R, 0.1), 0.9);
+        if (m.perfect_mirror || m.has_complex_ior) ia.type = REFLECT;
+        else if (ia.n2 < 1.0) ia.type = DIFFUSE;
+        else
+        {
+            double p = smp.get(INTERACTION);
+            if (ia.R > p) ia.type = REFLECT;
+            else if (ia.R + (1.0 - ia.R) * ia.T > p) ia.type = REFRACT;
+            else ia.type = DIFFUSE;
+        }
+        ia.dirac_delta = ia.type != DIFFUSE && !m.rough_specular;
+        return ia;
+    }
+
+    Ray spawn(const Interaction& ia, const Sampler& smp) // ray.cpp:16-67
+    {
+        const mcrt_material& m = *ia.material;
+        Ray r;
+        r.depth = ia.ray.depth + 1; r.diffuse_depth = ia.ray.diffuse_depth; r.refraction_scale = ia.ray.refraction_scale;
+        r.start = ia.position; r.refraction_level = ia.ray.refraction_level; r.dirac_delta = ia.dirac_delta;
+        auto specularNormal = [&]() // interaction.cpp:185-193
+        {
+            if (m.rough_specular) return ia.cs.from(ggxVisibleMicrofacet(smp.get(BSDF), smp.get(BSDF + 1), ia.cs.to(ia.out), m.a[0], m.a[1]));
+            return ia.cs.c2;
+        };
+        if (ia.type == REFLECT)
+        {
+            D3 n = specularNormal();
+            r.direction = ia.ray.direction - n * dot(n, ia.ray.direction) * 2.0; // glm::reflect
+            r.medium_ior = ia.n1; r.start = r.start + ia.normal * EPS;
+        }
+        else if (ia.type == REFRACT)
+        {
+            D3 n = specularNormal();
+            double inv_eta = ia.n1 / ia.n2, c = dot(n, ia.ray.direction), k = 1.0 - sq(inv_eta) * (1.0 - sq(c));
+            if (k >= 0.0)
+            {
+                r.direction = inv_eta * ia.ray.direction - (inv_eta * c + std::sqrt(k)) * n;
+                r.medium_ior = ia.n2; r.start = r.start - ia.normal * EPS;
+                if (ia.inside) r.refraction_level--; else r.refraction_level++;
+                r.refraction_scale *= sq(1.0 / inv_eta);
+                r.refraction = true;
+            }
+            else
+            {
+                r.direction = ia.ray.direction - n * c * 2.0;
+                r.medium_ior = ia.n1; r.start = r.start + ia.normal * EPS;
+            }
+        }
+        else
+        {
+            r.diffuse_depth++;
+            double u = smp.get(BSDF), v = smp.get(BSDF + 1); // Sampling::cosWeightedHemi, sampling.hpp:36-44
+            double rr = std::sqrt(u), az = v * TWO_PI;
+            r.direction = ia.cs.from(D3(rr * std::cos(az), rr * std::sin(az), std::sqrt(1 - u)));
+            r.medium_ior = ia.n1; r.start = r.start + ia.normal * EPS;
+        }
+        r.inv_direction = D3(1.0 / r.direction.x, 1.0 / r.direction.y, 1.0 / r.direction.z);
+        return r;
+    }
+
+    bool sampleBSDF(const Interaction& ia, const Sampler& smp, D3& f, double& pdf, Ray& nr) // interaction.cpp:56-72
+    {
+        nr = spawn(ia, smp);
+        D3 wi = ia.cs.to(nr.direction);
+        if ((nr.refraction && wi.z >= 0.0) || (!nr.refraction && wi.z <= 0.0)) return false;
+        D3 wo = ia.cs.to(ia.out);
+        f = ia.bsdfLocal(wo, wi, pdf, false, nr.dirac_delta) * std::abs(wi.z);
+        return pdf > 0.0;
+    }
+
+    // ---------------------------------------------------------------- integrator (integrator.cpp, path-tracer.cpp)
+    struct LightSample { double bsdf_pdf = 0.0, select_probability = 0.0; uint32_t light = 0xFFFFFFFFu; };
+
+    D3 lightPoint(const Scene& s, uint32_t prim, double u, double v)
+    {
+        const uint32_t idx = s.prim_index[prim];
+        if (s.prim_type[prim] == MCRT_PRIM_TRIANGLE) // triangle.cpp:93-97
+        {
+            double su = std::sqrt(u);
+            return (1 - su) * D3(&s.tri_v0[3 * idx]) + (1 - v) * su * D3(&s.tri_v1[3 * idx]) + v * su * D3(&s.tri_v2[3 * idx]);
+        }
+        const double* sp = &s.sph[4 * idx]; // sphere.cpp:37-44
+        double z = 1.0 - 2.0 * u, r = std::sqrt(1.0 - sq(z)), phi = TWO_PI * v;
+        return D3(sp) + sp[3] * D3(r * std::cos(phi), r * std::sin(phi), z);
+    }
+
+    double powerHeuristic(double a, double b) { double a2 = a * a; return a2 / (a2 + b * b); } // util.hpp:85-89
+
+    D3 sampleDirect(const Scene& s, const Interaction& ia, LightSample& ls, const Sampler& smp, uint64_t* rays) // integrator.cpp:31-87
+    {
+        if (s.light_prim.empty() || ia.material->dirac_delta) { ls.light = 0xFFFFFFFFu; return D3(); }
+        double u0 = smp.get(LIGHT), u1 = smp.get(LIGHT + 1), u2 = smp.get(LIGHT + 2);
+        size_t left = 0, right = s.light_cdf.size() - 1; // sampling.hpp:13-28
+        while (left < right) { size_t mid = (left + right) / 2; if (s.light_cdf[mid] < u2) left = mid + 1; else right = mid; }
+        ls.select_probability = s.light_cdf[left];
+        if (left > 0) ls.select_probability -= s.light_cdf[left - 1];
+        ls.light = s.light_prim[left];
+        D3 light_pos = lightPoint(s, ls.light, u0, u1);
+        Ray shadow = rayTo(ia.position + ia.normal * EPS, light_pos);
+        double cos_light = dot(-shadow.direction, primNormal(s, ls.light, light_pos));
+        if (cos_light <= 0.0) return D3();
+        double cos_theta = dot(shadow.direction, ia.normal);
+        if (cos_theta <= 0.0)
+        {
+            if (ia.material->opaque || cos_theta == 0.0) return D3();
+            shadow = rayTo(ia.position - ia.normal * EPS, light_pos);
+        }
+        Isect si = intersect(s, shadow, rays);
+        if (si.prim == 0xFFFFFFFFu || si.prim != ls.light) return D3();
+        double light_pdf = sq(si.t) / (s.prim_area[ls.light] * cos_light);
+        double bsdf_pdf; D3 f;
+        if (!ia.bsdfWorld(f, shadow.direction, bsdf_pdf)) return D3();
+        double w = powerHeuristic(light_pdf, bsdf_pdf);
+        return w * f * D3(s.materials[s.prim_material[ls.light]].emittance) / (light_pdf * ls.select_probability);
+    }
+
+    D3 sampleEmissive(const Scene& s, const Interaction& ia, const LightSample& ls) // integrator.cpp:93-110
+    {
+        if (ia.material->emissive && !ia.inside)
+        {
+            if (ia.ray.depth == 0 || ia.ray.dirac_delta) return D3(ia.material->emittance);
+            if (ls.light == ia.prim)
+            {
+                double cos_light = dot(ia.out, ia.normal);
+                double light_pdf = sq(ia.t) / (s.prim_area[ia.prim] * cos_light);
+                double w = powerHeuristic(ls.bsdf_pdf, light_pdf);
+                return w * D3(ia.material->emittance) / ls.select_probability;
+            }
+        }
+        return D3();
+    }
+
+    D3 skyColor(const Ray& r) // scene.cpp:219-223
+    {
+        double fy = (1.0 + std::asin(0.0 * r.direction.x + 1.0 * r.direction.y + 0.0 * r.direction.z) / PI) / 2.0;
+        return mix3(D3(1.0, 0.5, 0.0), D3(0.0, 0.5, 1.0), fy);
+    }
+
+    D3 sampleRay(const Scene& s, Ray ray, Sampler& smp, uint64_t* rays) // path-tracer.cpp:14-51
+    {
+        D3 radiance, throughput(1, 1, 1);
+        std::vector<double> iors(1, ray.medium_ior); // RefractionHistory, ray.cpp:74-98
+        LightSample ls;
+        while (true)
+        {
+            smp.shuffle();
+            Isect is = intersect(s, ray, rays);
+            if (is.prim == 0xFFFFFFFFu) return radiance + skyColor(ray) * throughput;
+            int ext = std::min(std::max(ray.refraction_level - 1, 0), (int)iors.size() - 1);
+            Interaction ia = makeInteraction(s, is, ray, iors[ext], smp);
+            radiance = radiance + sampleEmissive(s, ia, ls) * throughput;
+            radiance = radiance + sampleDirect(s, ia, ls, smp, rays) * throughput;
+            D3 f;
+            if (!sampleBSDF(ia, smp, f, ls.bsdf_pdf, ray)) return radiance;
+            throughput = throughput * (f / ls.bsdf_pdf);
+            // Integrator::absorb, integrator.cpp:112-129
+            double survive = compMax(throughput) * ray.refraction_scale;
+            if (survive == 0.0) return radiance;
+            if (ray.diffuse_depth > 3 || ray.depth > 16)
+            {
+                survive = std::min(0.95, survive);
+                if (survive <= smp.get(ABSORB)) return radiance;
+                throughput = throughput / survive;
+            }
+            if (ray.refraction_level > 0) // RefractionHistory::update
+            {
+                if (ray.refraction_level == (int)iors.size()) iors.push_back(ray.medium_ior);
+                else if (ray.refraction_level < (int)iors.size() - 1) iors.pop_back();
+            }
+        }
+    }
+
+    Ray cameraRay(const mcrt_camera& c, double scene_ior, uint32_t pixel, const Sampler& smp) // camera.cpp:66-95
+    {
+        const size_t x = pixel % c.width, y = pixel / c.width;
+        double pixel_size = c.sensor_width / c.width;
+        double px = x + smp.get(PIXEL), py = y + smp.get(PIXEL + 1);
+        double lx = pixel_size * (c.width * 0.5 - px), ly = pixel_size * (c.height * 0.5 - py);
+        D3 dir = normalize(D3(c.forward) * c.focal_length + D3(c.left) * lx + D3(c.up) * ly);
+        Ray ray = makeRay(D3(c.eye), dir, scene_ior);
+        if (c.thin_lens)
+        {
+            double u = smp.get(LENS), v = smp.get(LENS + 1), az = v * TWO_PI;
+            double ax = (std::cos(az) * std::sqrt(u)) * c.aperture_radius, ay = (std::sin(az) * std::sqrt(u)) * c.aperture_radius;
+            D3 focus = ray.at(c.focus_distance / dot(ray.direction, D3(c.forward)));
+            D3 start = D3(c.eye) + D3(c.left) * ax + D3(c.up) * ay;
+            ray = makeRay(start, normalize(focus - start), scene_ior);
+        }
+        return ray;
+    }
+}
+
+extern "C"
+{
+
+void* oracle_scene_create(const mcrt_scene_desc* d)
+{
+    Scene* s = new Scene();
+    s->d = *d;
+    copyv(s->node_bounds, d->node_bounds, 6 * (size_t)d->n_nodes);
+    copyv(s->node_first, d->node_first_prim, d->n_nodes); copyv(s->node_count, d->node_prim_count, d->n_nodes);
+    copyv(s->node_next, d->node_next_sibling, d->n_nodes);
+    copyv(s->prim_type, d->prim_type, d->n_prims); copyv(s->prim_index, d->prim_index, d->n_prims);
+    copyv(s->prim_material, d->prim_material, d->n_prims); copyv(s->prim_area, d->prim_area, d->n_prims);
+    copyv(s->tri_v0, d->tri_v0, 3 * (size_t)d->n_tris); copyv(s->tri_v1, d->tri_v1, 3 * (size_t)d->n_tris);
+    copyv(s->tri_v2, d->tri_v2, 3 * (size_t)d->n_tris); copyv(s->tri_e1, d->tri_e1, 3 * (size_t)d->n_tris);
+    copyv(s->tri_e2, d->tri_e2, 3 * (size_t)d->n_tris); copyv(s->tri_n, d->tri_normal, 3 * (size_t)d->n_tris);
+    copyv(s->tri_vn, d->tri_vn_index, d->n_tris); copyv(s->vn, d->vertex_normals, 9 * (size_t)d->n_vertex_normals);
+    copyv(s->sph, d->sphere_origin_radius, 4 * (size_t)d->n_spheres);
+    copyv(s->qQ, d->quadric_Q, 16 * (size_t)d->n_quadrics); copyv(s->qG, d->quadric_G, 12 * (size_t)d->n_quadrics);
+    copyv(s->qB, d->quadric_bounds, 6 * (size_t)d->n_quadrics);
+    copyv(s->materials, d->materials, d->n_materials);
+    copyv(s->light_prim, d->light_prim, d->n_lights); copyv(s->light_cdf, d->light_cdf, d->n_lights);
+    return s;
+}
+
+void oracle_scene_destroy(void* h) { delete static_cast<Scene*>(h); }
+
+void oracle_sampler_stream(const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles, uint32_t seed, uint32_t* out)
+{
+    Sampler smp(seed);
+    for (size_t i = 0; i < n; i++)
+    {
+        smp.initiate(pixel[i]); smp.setIndex(sample[i]);
+        for (uint32_t k = 0; k < n_shuffles; k++) smp.shuffle();
+        for (int d = 0; d < 7; d++) out[7 * i + d] = smp.raw(d);
+    }
+}
+
+void oracle_trace(void* h, const mcrt_ray* rays, size_t n, mcrt_hit* hits)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    for (size_t i = 0; i < n; i++)
+    {
+        Isect is = intersect(s, makeRay(D3(rays[i].origin), D3(rays[i].direction), s.d.scene_ior), nullptr);
+        hits[i].t = is.t; hits[i].u = is.u; hits[i].v = is.v; hits[i].prim = is.prim; hits[i].interpolate = is.interpolate;
+    }
+}
+
+void oracle_sample_rays(void* h, const mcrt_ray* rays, const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t seed, double* out)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    Sampler smp(seed);
+    for (size_t i = 0; i < n; i++)
+    {
+        smp.initiate(pixel[i]); smp.setIndex(sample[i]);
+        D3 r = sampleRay(s, makeRay(D3(rays[i].origin), D3(rays[i].direction), s.d.scene_ior), smp, nullptr);
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+}
+
+// Camera::samplePixel over rows [y0,y1) with the default box film (film.cpp:106-113)
+void oracle_render_rows(void* h, const mcrt_camera* cam, uint32_t y0, uint32_t y1, uint32_t sqrtspp, uint32_t seed, double* out, uint64_t* rays)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    Sampler smp(seed);
+    uint64_t count = 0;
+    const uint32_t spp = sqrtspp * sqrtspp;
+    for (uint32_t y = y0; y < y1; y++)
+        for (uint32_t x = 0; x < cam->width; x++)
+        {
+            const uint32_t pixel = y * cam->width + x;
+            smp.initiate(pixel);
+            double sum[3] = { 0, 0, 0 };
+            for (uint32_t i = 0; i < spp; i++)
+            {
+                smp.setIndex(i);
+                D3 r = sampleRay(s, cameraRay(*cam, s.d.scene_ior, pixel, smp), smp, &count);
+                sum[0] += r.x * 1.0; sum[1] += r.y * 1.0; sum[2] += r.z * 1.0; // Film::Splat::update, weight 1
+            }
+            double* o = out + ((size_t)(y - y0) * cam->width + x) * 3;
+            for (int k = 0; k < 3; k++) { double v = sum[k] / (double)spp; o[k] = (v < 0.0) ? 0.0 : v; }
+        }
+    if (rays) *rays = count;
+}
+
+} // extern "C"

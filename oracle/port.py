@@ -1,0 +1,82 @@
+"""ORACLE / TEST INFRASTRUCTURE - ctypes binding of the CPU restatement (oracle/mcrt_oracle.cpp).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libmcrt_oracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("build_oracle", os.path.join(HERE, "build_oracle.py"))
+            mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+            mod.build()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.c_void_p]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_sampler_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+        L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def sampler_stream(pixel, sample, n_shuffles, seed):
+    pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
+    out = np.zeros((len(pixel), 7), dtype=np.uint32)
+    lib().oracle_sampler_stream(_p(pixel), _p(sample), len(pixel), n_shuffles, seed, _p(out))
+    return out
+
+
+class PortScene:
+    """The restatement's view of a flattened scene (takes the product package's Scene only as a
+    container of the float64 arrays and the ctypes struct layout)."""
+
+    def __init__(self, scene):
+        self.scene = scene
+        self._desc = scene.desc()
+        self.h = lib().oracle_scene_create(C.addressof(self._desc))
+        self.pkg = importlib.import_module("monte-carlo-ray-tracer_b200")
+
+    def close(self):
+        if self.h:
+            lib().oracle_scene_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def trace(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        hits = np.zeros(len(rays), dtype=self.pkg.HIT_DTYPE)
+        lib().oracle_trace(self.h, _p(rays), len(rays), _p(hits))
+        return hits
+
+    def sample_rays(self, rays, pixel, sample, seed):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(rays), 3))
+        lib().oracle_sample_rays(self.h, _p(rays), _p(pixel), _p(sample), len(rays), seed, _p(out))
+        return out
+
+    def render_rows(self, camera, y0, y1, sqrtspp, seed):
+        out = np.zeros((y1 - y0, camera.width, 3))
+        rays = C.c_uint64()
+        lib().oracle_render_rows(self.h, C.addressof(camera.rec), y0, y1, sqrtspp, seed, _p(out), C.byref(rays))
+        return out, rays.value
