@@ -2,6 +2,7 @@
 // the float64 parity layout and the float32 wide-node layout from the flattened reference scene),
 // the wavefront render loop and the batched sampleRay / Scene::intersect / sampler entry points.
 // There is deliberately no CPU fallback: without a CUDA device every entry point fails.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -26,8 +27,7 @@ namespace
 {
     template <class R> struct SceneArrays
     {
-        std::vector<Node<R>> nodes;
-        std::vector<WideChild> wide;
+        std::vector<WideChild<R>> wide;
         std::vector<V4<R>> geom;
         std::vector<PrimShade<R>> shade;
         std::vector<V4<R>> vnormals;
@@ -138,18 +138,6 @@ namespace
     template <class R>
     int buildArrays(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<R>& a)
     {
-        // ---- reference-order nodes
-        a.nodes.resize(s.n_nodes);
-        for (uint32_t i = 0; i < s.n_nodes; i++)
-        {
-            Node<R>& n = a.nodes[i];
-            for (int k = 0; k < 3; k++) { n.bmin[k] = (R)s.node_bounds[6 * i + k]; n.bmax[k] = (R)s.node_bounds[6 * i + 3 + k]; }
-            n.first_prim = s.node_first_prim[i];
-            n.prim_count = s.node_prim_count[i];
-            n.next_sibling = s.node_next_sibling[i];
-            n._pad = 0;
-        }
-
         // ---- geometry slots + shading records
         a.geom.resize(3 * (size_t)s.n_prims);
         a.shade.resize(s.n_prims);
@@ -261,14 +249,19 @@ namespace
         return MCRT_OK;
     }
 
-    // float32 wide layout: the children of every inner node as consecutive 32-byte records.
-    int buildWide(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<float>& a)
+    // Children-contiguous layout of the BVH (see scene.cuh). Child order inside a block = the
+    // reference's next_sibling chain, which the parity traversal depends on.
+    template <class R>
+    int buildWide(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<R>& a)
     {
-        DeviceScene<float>& d = a.dev;
+        DeviceScene<R>& d = a.dev;
         d.root_is_leaf = 0; d.root_first_prim = 0; d.root_prim_count = 0; d.n_wide_root = 0;
-        for (int k = 0; k < 3; k++) { d.root_bmin[k] = 0.f; d.root_bmax[k] = 0.f; }
+        for (int k = 0; k < 3; k++) { d.root_bmin[k] = R(0); d.root_bmax[k] = R(0); }
         if (s.n_nodes == 0) return MCRT_OK;
-        for (int k = 0; k < 3; k++) { d.root_bmin[k] = (float)s.node_bounds[k]; d.root_bmax[k] = (float)s.node_bounds[3 + k]; }
+        auto lower = [&](double v) { R r = (R)v; if ((double)r > v) r = std::nextafter(r, (R)-INFINITY); return r; };
+        auto upper = [&](double v) { R r = (R)v; if ((double)r < v) r = std::nextafter(r, (R)INFINITY); return r; };
+        // float bounds are rounded outwards so that no double-precision hit is lost; exact in double
+        for (int k = 0; k < 3; k++) { d.root_bmin[k] = lower(s.node_bounds[k]); d.root_bmax[k] = upper(s.node_bounds[3 + k]); }
         if (s.node_prim_count[0])
         {
             d.root_is_leaf = 1; d.root_first_prim = s.node_first_prim[0]; d.root_prim_count = s.node_prim_count[0];
@@ -291,15 +284,9 @@ namespace
             if (ks.size() > 8) { ctx->error = "BVH arity > 8 unsupported"; return MCRT_ERR_UNSUPPORTED; }
             for (uint32_t c : ks)
             {
-                WideChild w;
-                // conservative float bounds: round outwards so no double-precision hit is lost
-                for (int k = 0; k < 3; k++)
-                {
-                    float lo = (float)s.node_bounds[6 * c + k], hi = (float)s.node_bounds[6 * c + 3 + k];
-                    if ((double)lo > s.node_bounds[6 * c + k]) lo = nextafterf(lo, -INFINITY);
-                    if ((double)hi < s.node_bounds[6 * c + 3 + k]) hi = nextafterf(hi, INFINITY);
-                    w.bmin[k] = lo; w.bmax[k] = hi;
-                }
+                WideChild<R> w;
+                std::memset(&w, 0, sizeof(w));
+                for (int k = 0; k < 3; k++) { w.bmin[k] = lower(s.node_bounds[6 * c + k]); w.bmax[k] = upper(s.node_bounds[6 * c + 3 + k]); }
                 if (s.node_prim_count[c]) { w.a = s.node_first_prim[c]; w.b = s.node_prim_count[c] | WIDE_LEAF; }
                 else { w.a = 0; w.b = 0; queue.push_back({ c, (uint32_t)a.wide.size() }); }
                 a.wide.push_back(w);
@@ -325,7 +312,6 @@ namespace
     {
         DeviceScene<R>& d = a.dev;
         int rc;
-        if ((rc = devUpload(ctx, ctx->scene_allocs, &d.nodes, a.nodes, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.wide, a.wide, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.geom, a.geom, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.shade, a.shade, bytes))) return rc;
@@ -815,6 +801,7 @@ int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d
         SceneArrays<double> a;
         if ((rc = buildArrays(ctx, s, a))) return rc;
         std::memset(&a.dev, 0, sizeof(a.dev));
+        if ((rc = buildWide(ctx, s, a))) return rc;
         if ((rc = uploadArrays(ctx, s, a, bytes))) return rc;
         CK(cudaStreamSynchronize(ctx->stream)); // host vectors die at scope exit
         ctx->scene64 = a.dev;

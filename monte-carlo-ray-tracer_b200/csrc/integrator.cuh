@@ -24,11 +24,16 @@
 #include "photon.cuh"
 
 // launch-bound knobs (overridable at build time for tuning experiments)
-#ifndef MCRT_TRACE_MINBLOCKS
-#define MCRT_TRACE_MINBLOCKS 2
+// (measured on B200, r1: float traversal gains 25-30 % from 64 registers / 32 warps per SM, double
+// traversal loses to the spills; shade gains a little from 3 CTAs of 128 threads)
+#ifndef MCRT_TRACE_MINBLOCKS_F64
+#define MCRT_TRACE_MINBLOCKS_F64 2
+#endif
+#ifndef MCRT_TRACE_MINBLOCKS_F32
+#define MCRT_TRACE_MINBLOCKS_F32 4
 #endif
 #ifndef MCRT_SHADE_MINBLOCKS
-#define MCRT_SHADE_MINBLOCKS 2
+#define MCRT_SHADE_MINBLOCKS 3
 #endif
 #ifndef MCRT_SORT_ORIGIN_BITS
 #define MCRT_SORT_ORIGIN_BITS 4
@@ -186,8 +191,8 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     template <class R> struct Mode;
-    template <> struct Mode<double> { static constexpr bool parity = true; };
-    template <> struct Mode<float> { static constexpr bool parity = false; };
+    template <> struct Mode<double> { static constexpr bool parity = true; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F64; };
+    template <> struct Mode<float> { static constexpr bool parity = false; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F32; };
 
     template <class R>
     MCRT_D Hit<R> traceClosest(const DeviceScene<R>& sc, const V3<R>& o, const V3<R>& d, uint32_t skip_prim,
@@ -354,7 +359,7 @@ namespace mcrt
     }
 
     template <class R>
-    __global__ void __launch_bounds__(256, MCRT_TRACE_MINBLOCKS) k_extend(WaveParams<R> p, int cur)
+    __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
@@ -728,7 +733,7 @@ namespace mcrt
     }
 
     template <class R>
-    __global__ void __launch_bounds__(256, MCRT_TRACE_MINBLOCKS) k_shadow(WaveParams<R> p)
+    __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
         TraceCounters cnt = { 0u, 0u };

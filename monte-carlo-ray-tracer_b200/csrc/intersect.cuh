@@ -185,11 +185,11 @@ namespace mcrt
     struct RefHeap
     {
         R t[REF_HEAP_CAPACITY];
-        uint32_t node[REF_HEAP_CAPACITY];
+        uint2 node[REF_HEAP_CAPACITY];   // (a, b) of the child record: no dependent load after a pop
         int size;
 
         // NodeIntersection::operator< is inverted (bvh.hpp:78): a < b  <=>  b.t < a.t
-        MCRT_D void push(R vt, uint32_t vn)
+        MCRT_D void push(R vt, uint2 vn)
         {
             int index = size++;
             while (index > 0)
@@ -206,7 +206,7 @@ namespace mcrt
         {
             if (size > 1)
             {
-                R vt = t[size - 1]; uint32_t vn = node[size - 1];
+                R vt = t[size - 1]; uint2 vn = node[size - 1];
                 size--;
                 int index = 0;
                 while (true)
@@ -246,35 +246,37 @@ namespace mcrt
         heap.size = 0;
         R t;
         cnt.box_tests++;
-        if (!slabTest(sc.nodes[0].bmin, sc.nodes[0].bmax, ray, t)) return best;
+        if (!slabTest(sc.root_bmin, sc.root_bmax, ray, t)) return best;
 
-        uint32_t node_idx = 0;
+        // (a, b) of the node being visited; the heap holds child-record indices
+        uint32_t cur_a, cur_b;
+        if (sc.root_is_leaf) { cur_a = sc.root_first_prim; cur_b = sc.root_prim_count | WIDE_LEAF; }
+        else { cur_a = 0; cur_b = sc.n_wide_root; }
+
         while (true)
         {
-            const uint32_t first = sc.nodes[node_idx].first_prim;
-            const uint32_t count = sc.nodes[node_idx].prim_count;
-            if (count)
+            if (cur_b & WIDE_LEAF)
             {
-                for (uint32_t i = first; i < first + count; i++) testPrim(sc, i, ray, best);
+                const uint32_t count = cur_b & ~WIDE_LEAF;
+                for (uint32_t i = cur_a; i < cur_a + count; i++) testPrim(sc, i, ray, best);
                 cnt.prim_tests += count;
             }
             else
             {
-                uint32_t child = node_idx + 1;
-                while (child != 0)
+                // children in next_sibling order; the loads are independent of each other
+                for (uint32_t c = cur_a; c < cur_a + cur_b; c++)
                 {
-                    const Node<R>& cn = sc.nodes[child];
-                    cnt.box_tests++;
+                    const WideChild<R>& cn = sc.wide[c];
                     if (slabTest(cn.bmin, cn.bmax, ray, t) && t < best.t)
                     {
-                        if (heap.size < REF_HEAP_CAPACITY) heap.push(t, child);
+                        if (heap.size < REF_HEAP_CAPACITY) heap.push(t, make_uint2(cn.a, cn.b));
                         else overflow = 1;
                     }
-                    child = cn.next_sibling;
                 }
+                cnt.box_tests += cur_b;
             }
             if (heap.size == 0 || heap.t[0] >= best.t) break;
-            node_idx = heap.node[0];
+            cur_a = heap.node[0].x; cur_b = heap.node[0].y;
             heap.pop();
         }
         return best;
@@ -318,8 +320,9 @@ namespace mcrt
         cnt.box_tests++;
         if (!slabTest(sc.root_bmin, sc.root_bmax, ray, t)) return best;
 
-        // stack entries: (a, b) of a child record
+        // stack entries: (a, b) of a child record + its entry distance (culled against best.t on pop)
         uint32_t stack_a[WIDE_STACK], stack_b[WIDE_STACK];
+        float stack_t[WIDE_STACK];
         int sp = 0;
         uint32_t cur_a, cur_b;
         if (sc.root_is_leaf) { cur_a = sc.root_first_prim; cur_b = sc.root_prim_count | WIDE_LEAF; }
@@ -359,7 +362,7 @@ namespace mcrt
                 // ct is sorted descending: push all but the last (nearest)
                 for (int j = 0; j < n - 1; j++)
                 {
-                    if (sp < WIDE_STACK) { stack_a[sp] = ca[j]; stack_b[sp] = cb[j]; sp++; }
+                    if (sp < WIDE_STACK) { stack_a[sp] = ca[j]; stack_b[sp] = cb[j]; stack_t[sp] = ct[j]; sp++; }
                     else overflow = 1;
                 }
                 if (n > 0)
@@ -368,9 +371,14 @@ namespace mcrt
                     continue;
                 }
             }
-            if (sp == 0) break;
-            sp--;
-            cur_a = stack_a[sp]; cur_b = stack_b[sp];
+            // pop, skipping subtrees that start beyond the closest hit found so far
+            bool found = false;
+            while (sp > 0)
+            {
+                sp--;
+                if (stack_t[sp] < best.t) { cur_a = stack_a[sp]; cur_b = stack_b[sp]; found = true; break; }
+            }
+            if (!found) break;
         }
         return best;
     }

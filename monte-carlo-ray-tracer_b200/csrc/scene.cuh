@@ -1,14 +1,13 @@
 // Device-side scene layout, templated on the arithmetic type R.
 //
 // HBM layout (all arrays are built once in mcrt_scene_upload from the float64 description):
-//   nodes     BVH::LinearNode order (source/bvh/bvh.hpp:68-82): bounds + first/count/next_sibling.
-//             64 B in double (same as the reference), 32 B in float. Used by the reference-order
-//             best-first traversal (parity mode) and by nothing else.
-//   wide      float only: one 32-byte record per *child* {min.xyz, max.xyz, a, b}, the children of
-//             an inner node stored contiguously so that one inner visit is n coalesced 2×float4
-//             loads. (a,b) = (first child record, child count) for inner children and
-//             (first prim, count | LEAF) for leaves. This is the "32 B per box" of the roofline
-//             formula.
+//   wide      the BVH (source/bvh/bvh.hpp:68-82) re-laid as one record per *child* {min.xyz,
+//             max.xyz, a, b}: the children of an inner node are contiguous, in next_sibling order,
+//             so one inner visit is n independent loads (2×float4 each in float = the "32 B per
+//             box" of the roofline formula; 64 B in double). (a,b) = (first child
+//             record, child count) for inner children and (first prim, count | LEAF) for leaves.
+//             Both traversals use it: the reference-order best-first one (parity) keeps the
+//             reference's child order, the depth-first one (fast mode) sorts children by distance.
 //   geom      3 × V4<R> per ordered primitive = the 48 B (float) / 96 B (double) intersection
 //             record: triangle {v0,type | E1 | E2}, sphere {origin,type | radius | -},
 //             quadric {index,type | - | -}. Indexed by ordered-primitive id: no indirection.
@@ -29,18 +28,23 @@ namespace mcrt
 
     enum PrimType : uint32_t { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_QUADRIC = 2 };
 
-    template <class R> struct alignas(16) Node
-    {
-        R bmin[3];
-        R bmax[3];
-        uint32_t first_prim, prim_count, next_sibling, _pad;
-    };
-
-    struct alignas(16) WideChild
+    // One record per *child*: the children of an inner node are stored contiguously in the order of
+    // the reference's next_sibling chain (bvh.cpp:109-118), so one inner-node visit is n independent
+    // loads instead of n dependent pointer hops. (a, b) = (first child record, child count) for an
+    // inner child, (first primitive, count | WIDE_LEAF) for a leaf. 32 B in float, 64 B in double.
+    template <class R> struct WideChild;
+    template <> struct alignas(16) WideChild<float>
     {
         float bmin[3];
         float bmax[3];
         uint32_t a, b;
+    };
+    template <> struct alignas(16) WideChild<double>
+    {
+        double bmin[3];
+        double bmax[3];
+        uint32_t a, b;
+        uint32_t _pad[2];
     };
 
     template <class R> struct alignas(16) PrimShade
@@ -88,8 +92,7 @@ namespace mcrt
 
     template <class R> struct DeviceScene
     {
-        const Node<R>* nodes;
-        const WideChild* wide;      // float mode only
+        const WideChild<R>* wide;
         const V4<R>* geom;
         const PrimShade<R>* shade;
         const V4<R>* vnormals;
