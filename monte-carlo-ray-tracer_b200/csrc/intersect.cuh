@@ -248,20 +248,18 @@ namespace mcrt
         cnt.box_tests++;
         if (!slabTest(sc.root_bmin, sc.root_bmax, ray, t)) return best;
 
-        // (a, b) of the node being visited; the heap holds child-record indices
+        // (a, b) of the node being visited; the heap holds the (a, b) of pending children.
+        // "while-while" control flow: every lane first walks down through inner nodes (all lanes of
+        // the warp do box tests together), then all lanes test leaf primitives together. The order
+        // of operations per ray is exactly the reference's; only the SIMT schedule changes.
         uint32_t cur_a, cur_b;
         if (sc.root_is_leaf) { cur_a = sc.root_first_prim; cur_b = sc.root_prim_count | WIDE_LEAF; }
         else { cur_a = 0; cur_b = sc.n_wide_root; }
 
-        while (true)
+        bool done = false;
+        while (!done)
         {
-            if (cur_b & WIDE_LEAF)
-            {
-                const uint32_t count = cur_b & ~WIDE_LEAF;
-                for (uint32_t i = cur_a; i < cur_a + count; i++) testPrim(sc, i, ray, best);
-                cnt.prim_tests += count;
-            }
-            else
+            while (!(cur_b & WIDE_LEAF))
             {
                 // children in next_sibling order; the loads are independent of each other
                 for (uint32_t c = cur_a; c < cur_a + cur_b; c++)
@@ -274,6 +272,15 @@ namespace mcrt
                     }
                 }
                 cnt.box_tests += cur_b;
+                if (heap.size == 0 || heap.t[0] >= best.t) { done = true; break; }
+                cur_a = heap.node[0].x; cur_b = heap.node[0].y;
+                heap.pop();
+            }
+            if (done) break;
+            {
+                const uint32_t count = cur_b & ~WIDE_LEAF;
+                for (uint32_t i = cur_a; i < cur_a + count; i++) testPrim(sc, i, ray, best);
+                cnt.prim_tests += count;
             }
             if (heap.size == 0 || heap.t[0] >= best.t) break;
             cur_a = heap.node[0].x; cur_b = heap.node[0].y;
@@ -329,9 +336,45 @@ namespace mcrt
         else { cur_a = 0; cur_b = sc.n_wide_root; }
 
         const float4* wide = reinterpret_cast<const float4*>(sc.wide);
-        while (true)
+        bool done = false;
+        while (!done)
         {
-            if (cur_b & WIDE_LEAF)
+            // "while-while": inner nodes first (all lanes doing box tests), then leaf primitives
+            while (!(cur_b & WIDE_LEAF))
+            {
+                // the nearest hit child is visited next, the others are pushed; the stack is not kept
+                // sorted: entries carry their entry distance and are culled against best.t on pop
+                float near_t = Consts<float>::MAXV; uint32_t near_a = 0, near_b = 0; bool have = false;
+                for (uint32_t c = 0; c < cur_b; c++)
+                {
+                    const float4 lo = __ldg(&wide[2 * (cur_a + c)]);
+                    const float4 hi = __ldg(&wide[2 * (cur_a + c) + 1]);
+                    float tc;
+                    if (slabTestWide(lo, hi, ray, best.t, tc))
+                    {
+                        uint32_t a = __float_as_uint(hi.z), b = __float_as_uint(hi.w);
+                        if (!have) { near_t = tc; near_a = a; near_b = b; have = true; continue; }
+                        if (tc < near_t)
+                        {
+                            const float tt = near_t; const uint32_t ta = near_a, tb = near_b;
+                            near_t = tc; near_a = a; near_b = b;
+                            tc = tt; a = ta; b = tb;
+                        }
+                        if (sp < WIDE_STACK) { stack_a[sp] = a; stack_b[sp] = b; stack_t[sp] = tc; sp++; }
+                        else overflow = 1;
+                    }
+                }
+                cnt.box_tests += cur_b;
+                if (have) { cur_a = near_a; cur_b = near_b; continue; }
+                bool found = false;
+                while (sp > 0)
+                {
+                    sp--;
+                    if (stack_t[sp] < best.t) { cur_a = stack_a[sp]; cur_b = stack_b[sp]; found = true; break; }
+                }
+                if (!found) { done = true; break; }
+            }
+            if (done) break;
             {
                 const uint32_t count = cur_b & ~WIDE_LEAF;
                 for (uint32_t i = cur_a; i < cur_a + count; i++)
@@ -340,38 +383,6 @@ namespace mcrt
                 }
                 cnt.prim_tests += count;
             }
-            else
-            {
-                // test all children; keep the nearest as `cur`, push the rest far-to-near.
-                // Children are few (<= 8): insertion into a small sorted run held in registers.
-                float ct[8]; uint32_t ca[8], cb[8];
-                int n = 0;
-                for (uint32_t c = 0; c < cur_b; c++)
-                {
-                    const float4 lo = __ldg(&wide[2 * (cur_a + c)]);
-                    const float4 hi = __ldg(&wide[2 * (cur_a + c) + 1]);
-                    float tc;
-                    if (slabTestWide(lo, hi, ray, best.t, tc))
-                    {
-                        int j = n++;
-                        while (j > 0 && ct[j - 1] < tc) { ct[j] = ct[j - 1]; ca[j] = ca[j - 1]; cb[j] = cb[j - 1]; j--; }
-                        ct[j] = tc; ca[j] = __float_as_uint(hi.z); cb[j] = __float_as_uint(hi.w);
-                    }
-                }
-                cnt.box_tests += cur_b;
-                // ct is sorted descending: push all but the last (nearest)
-                for (int j = 0; j < n - 1; j++)
-                {
-                    if (sp < WIDE_STACK) { stack_a[sp] = ca[j]; stack_b[sp] = cb[j]; stack_t[sp] = ct[j]; sp++; }
-                    else overflow = 1;
-                }
-                if (n > 0)
-                {
-                    cur_a = ca[n - 1]; cur_b = cb[n - 1];
-                    continue;
-                }
-            }
-            // pop, skipping subtrees that start beyond the closest hit found so far
             bool found = false;
             while (sp > 0)
             {
