@@ -90,6 +90,7 @@ struct mcrt_ctx
     // options
     int sort_rays = 1;
     int sort_shade = 0;
+    int sort_prim_key = -1;   // -1 auto (>= 4096 primitives), 0 origin-cell keys, 1 source-primitive keys
     uint32_t pool_paths = 1u << 22;
     int blocks_per_sm = 8;
     double ray_eps_scale = 1e-5;
@@ -485,6 +486,13 @@ namespace
             if ((rc = ensureSort(ctx))) return rc;
             p.sort = ctx->sort;
             p.sort.shade_sorted = ctx->sort_shade ? 1u : 0u;
+            {
+                // source-primitive keys for scenes with enough primitives to index space finely
+                const uint32_t n_prims = sceneOf<R>(ctx).n_prims;
+                const bool use_prim = ctx->sort_prim_key < 0 ? n_prims >= 4096u : ctx->sort_prim_key != 0;
+                const double cells = (double)(1u << (3 * SORT_ORIGIN_BITS));
+                p.sort.prim_scale = use_prim ? (uint32_t)(cells * 4294967296.0 / (double)n_prims * 0.999999) : 0u;
+            }
             for (int k = 0; k < 3; k++)
             {
                 const double ext = ctx->scene_bmax[k] - ctx->scene_bmin[k];
@@ -729,6 +737,7 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "stage_timing") { ctx->stage_timing = value != 0.0; }
     else if (k == "sort_rays") { ctx->sort_rays = value != 0.0; }
     else if (k == "sort_shade") { ctx->sort_shade = value != 0.0; }
+    else if (k == "sort_prim_key") { ctx->sort_prim_key = (int)value; }
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }

@@ -164,7 +164,9 @@ namespace mcrt
         Frame<R> shading_cs;
         bool inside, dirac_delta;
 
-        // Interaction::BSDF (private overload), interaction.cpp:84-153
+        // Interaction::BSDF (private overload), interaction.cpp:84-153. Kept inline: a __noinline__
+        // version shrinks k_shade<double> from 9176 to 6864 SASS instructions but measured 17 % slower
+        // (call ABI spills the Interaction).
         MCRT_D V3<R> bsdfLocal(const V3<R>& wo, const V3<R>& wi, R& pdf, bool flux, bool wi_dirac_delta) const
         {
             const Material<R>& m = *material;

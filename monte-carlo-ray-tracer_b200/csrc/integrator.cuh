@@ -104,7 +104,9 @@ namespace mcrt
         uint32_t* block_offset;  // [2 * SORT_BINS / 1024]: segment offsets, then segment totals
         uint32_t* done_counter;  // last-CTA-done counter of k_sort_scan
         uint32_t shade_sorted;   // 1: k_shade also walks the queue in sorted order
-        uint32_t _pad;
+        uint32_t prim_scale;     // != 0: the cell field of the key is the source primitive's position in
+                                 // BVH order, (prim * prim_scale) >> 32 (large scenes: the BVH order is a
+                                 // far finer spatial index than a 16^3 grid where the geometry is dense)
         float key_min[3], key_scale[3]; // origin -> cell: (o - key_min) * key_scale in [0, 2^SORT_ORIGIN_BITS)
     };
 
@@ -117,17 +119,26 @@ namespace mcrt
         return v;
     }
 
+    // src_prim: ordered primitive the ray leaves from (NO_PRIM for camera rays)
     template <class R>
-    MCRT_D uint32_t rayKey(const RaySort& rs, const V3<R>& o, const V3<R>& d)
+    MCRT_D uint32_t rayKey(const RaySort& rs, const V3<R>& o, const V3<R>& d, uint32_t src_prim)
     {
-        constexpr float CELLS = (float)(1u << SORT_ORIGIN_BITS);
-        float cx = ((float)o.x - rs.key_min[0]) * rs.key_scale[0];
-        float cy = ((float)o.y - rs.key_min[1]) * rs.key_scale[1];
-        float cz = ((float)o.z - rs.key_min[2]) * rs.key_scale[2];
-        uint32_t ix = (uint32_t)fminf(fmaxf(cx, 0.0f), CELLS - 1.0f);
-        uint32_t iy = (uint32_t)fminf(fmaxf(cy, 0.0f), CELLS - 1.0f);
-        uint32_t iz = (uint32_t)fminf(fmaxf(cz, 0.0f), CELLS - 1.0f);
-        uint32_t cell = spreadBits3(ix) | (spreadBits3(iy) << 1) | (spreadBits3(iz) << 2);
+        uint32_t cell;
+        if (rs.prim_scale && src_prim != NO_PRIM)
+        {
+            cell = (uint32_t)(((unsigned long long)src_prim * rs.prim_scale) >> 32);
+        }
+        else
+        {
+            constexpr float CELLS = (float)(1u << SORT_ORIGIN_BITS);
+            float cx = ((float)o.x - rs.key_min[0]) * rs.key_scale[0];
+            float cy = ((float)o.y - rs.key_min[1]) * rs.key_scale[1];
+            float cz = ((float)o.z - rs.key_min[2]) * rs.key_scale[2];
+            uint32_t ix = (uint32_t)fminf(fmaxf(cx, 0.0f), CELLS - 1.0f);
+            uint32_t iy = (uint32_t)fminf(fmaxf(cy, 0.0f), CELLS - 1.0f);
+            uint32_t iz = (uint32_t)fminf(fmaxf(cz, 0.0f), CELLS - 1.0f);
+            cell = spreadBits3(ix) | (spreadBits3(iy) << 1) | (spreadBits3(iz) << 2);
+        }
         float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
         float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
         uint32_t face; float u, v, m;
@@ -337,7 +348,7 @@ namespace mcrt
             out.thr[slot] = V4<R>(R(1), R(1), R(1), R(0));
             out.meta[slot] = make_uint4(pixel, sample, 0u, 0u);
             out.meta2[slot] = make_uint4(NO_PRIM, 1u, film_index, NO_PRIM);
-            if (p.sort.path_order) key = rayKey(p.sort, start, direction);
+            if (p.sort.path_order) key = rayKey(p.sort, start, direction, NO_PRIM);
             }
             if (p.sort.path_order)
             {
@@ -680,12 +691,12 @@ namespace mcrt
             if (sorting && alive)
             {
                 // un-aggregated: lanes of an (unsorted) shade warp rarely share a bin
-                pkey = rayKey(p.sort, nray.start, nray.direction);
+                pkey = rayKey(p.sort, nray.start, nray.direction, hit_prim);
                 prank = atomicAdd(&p.sort.hist_path[pkey], 1u);
             }
             if (sorting && want_shadow)
             {
-                skey = rayKey(p.sort, sh_o, sh_d);
+                skey = rayKey(p.sort, sh_o, sh_d, hit_prim);
                 srank = atomicAdd(&p.sort.hist_shadow[skey], 1u);
             }
             if (alive)
