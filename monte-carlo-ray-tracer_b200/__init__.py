@@ -160,8 +160,13 @@ _PACK_DTYPES = {0: np.uint8, 1: np.uint32, 2: np.int32, 3: np.uint64, 4: np.floa
 
 def read_pack(path):
     """Reads a scene pack written by host/exporter.cpp (PackWriter) → dict of numpy arrays."""
-    with open(path, "rb") as f:
-        blob = f.read()
+    if path.endswith(".xz"):   # large OBJ-scene packs are shipped xz-compressed (float64 arrays: ~5x)
+        import lzma
+        with lzma.open(path, "rb") as f:
+            blob = f.read()
+    else:
+        with open(path, "rb") as f:
+            blob = f.read()
     if blob[:8] != b"MCRTPK01":
         raise McrtError(f"{path}: not a scene pack")
     n, = struct.unpack_from("<I", blob, 8)

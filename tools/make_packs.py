@@ -30,5 +30,8 @@ if __name__ == "__main__":
         t = time.time()
         s = ref.RefScene(scene, ov, photon_map=pm)
         path = s.export_pack(os.path.join(OUT, cid + ".mcrtpack"))
+        if os.path.getsize(path) > (8 << 20):   # OBJ scenes: ship compressed (gpurun snapshots are capped at 512 MiB)
+            os.system(f"xz -1 -T8 -f {path}")
+            path += ".xz"
         print(cid, "prims", s.n_prims, "nodes", s.n_nodes, "lights", s.n_lights, os.path.getsize(path), "bytes", round(time.time() - t, 1), "s")
         s.close()
