@@ -165,6 +165,9 @@ typedef struct mcrt_stats {
     double gpu_ms_generate, gpu_ms_extend, gpu_ms_shade, gpu_ms_shadow, gpu_ms_knn;
     uint64_t extend_launches, shadow_launches;
     uint64_t shadow_box_tests, shadow_prim_tests; /* k_shadow's share of box_tests / prim_tests */
+    /* k_extend warp-tail diagnostic: sum over rays of (box+prim tests) / sum over warps of
+     * 32*max over the warp's rays = the lane utilisation lost to uneven ray lengths alone */
+    uint64_t extend_work_sum, extend_work_warpmax;
 } mcrt_stats;
 
 typedef struct mcrt_ctx mcrt_ctx;

@@ -417,6 +417,8 @@ namespace
         st->gpu_ms_total = ms;
         st->shadow_box_tests = c.shadow_box_tests;
         st->shadow_prim_tests = c.shadow_prim_tests;
+        st->extend_work_sum = c.work_sum;
+        st->extend_work_warpmax = c.work_warpmax;
     }
 
     // The wavefront loop shared by mcrt_render_rows(_dev) and mcrt_sample_rays.

@@ -56,6 +56,8 @@ namespace mcrt
         unsigned long long ior_stack_overflows;
         uint32_t traversal_overflow, max_depth;
         uint32_t n_knn, _pad;
+        // diagnostics of k_extend: sum over rays of (box+prim tests) and sum over warps of 32*max
+        unsigned long long work_sum, work_warpmax;
     };
 
     template <class R> struct PathBuffer
@@ -376,7 +378,7 @@ namespace mcrt
         const PathBuffer<R>& in = p.buf[cur];
         TraceCounters cnt = { 0u, 0u };
         uint32_t overflow = 0;
-        unsigned long long rays = 0;
+        unsigned long long rays = 0, work_sum = 0, work_max = 0;
         const uint32_t* order = p.sort.path_order;
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
@@ -385,9 +387,21 @@ namespace mcrt
             const V4<R> rd = in.ray_d[i];
             uint32_t skip = NO_PRIM;
             if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
+            const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
             Hit<R> h = traceClosest(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
             p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
             rays++;
+            // tail diagnostic: how much of the warp's time (~ its slowest ray) the average ray uses
+            const uint32_t w = cnt.box_tests + cnt.prim_tests - w0;
+            const unsigned am = __activemask();
+            work_sum += w;
+            if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) work_max += 32ull * __reduce_max_sync(am, w);
+            else __reduce_max_sync(am, w);
+        }
+        {
+            unsigned long long ws = work_sum, wm = work_max;
+            for (int off = 16; off > 0; off >>= 1) { ws += __shfl_down_sync(0xFFFFFFFFu, ws, off); wm += __shfl_down_sync(0xFFFFFFFFu, wm, off); }
+            if ((threadIdx.x & 31u) == 0) { atomicAdd(&p.counters->work_sum, ws); atomicAdd(&p.counters->work_warpmax, wm); }
         }
         flushStats(p.counters, cnt, rays, false, overflow);
     }

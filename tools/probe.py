@@ -33,7 +33,7 @@ for mode in a.modes.split(","):
               f"Mray/s={rays/st['gpu_ms_total']/1e3:.1f} paths={st['paths']} ext={st['extension_rays']} sh={st['shadow_rays']} "
               f"box/ray={st['box_tests']/rays:.1f} prim/ray={st['prim_tests']/rays:.1f} iters={st['wavefront_iterations']} "
               f"launches={st['kernel_launches']} maxdepth={st['max_depth']} mean={img.mean():.6f} "
-              f"stages ext={st['gpu_ms_extend']:.1f} shade={st['gpu_ms_shade']:.1f} shadow={st['gpu_ms_shadow']:.1f} gen={st['gpu_ms_generate']:.1f}", flush=True)
+              f"tail_util={st['extend_work_sum']/max(1,st['extend_work_warpmax']):.3f} stages ext={st['gpu_ms_extend']:.1f} shade={st['gpu_ms_shade']:.1f} shadow={st['gpu_ms_shadow']:.1f} gen={st['gpu_ms_generate']:.1f}", flush=True)
     imgs[mode] = img
     pt.close()
 if a.compare and len(imgs) == 2:
