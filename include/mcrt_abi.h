@@ -188,6 +188,39 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map,
                        const mcrt_photon_map_desc* global_map, uint32_t k_nearest,
                        uint32_t direct_visualization, uint64_t* h2d_bytes);
 
+/* Parameters of the photon pass, the "photon_map" object of the scene JSON
+ * (source/integrator/photon-mapper/photon-mapper.cpp:28-38). */
+typedef struct mcrt_photon_emit_params {
+    uint64_t emissions;                    /* "emissions" (before the caustic_factor scaling)  */
+    double caustic_factor;
+    uint32_t max_photons_per_octree_leaf;
+    uint32_t k_nearest_photons;
+    uint32_t direct_visualization;
+    uint32_t global_seed;
+    double scene_bounds[6];                /* Scene::BB() = root box of both octrees            */
+} mcrt_photon_emit_params;
+
+/* SURVEY.md §8f-1 ("next"): replaces the first pass of PhotonMapper::PhotonMapper
+ * (photon-mapper.cpp:24-223) — photon emission + tracing (emitPhoton, :225-277) on the GPU, then
+ * Octree<Photon> construction + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244)
+ * — and installs the two maps in the context exactly as mcrt_photon_upload would. The photon
+ * multiset and the octree structure equal the reference's (photons inside one leaf may be stored
+ * in a different order: the reference's order depends on its thread schedule). */
+int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision,
+                     uint64_t* n_caustic, uint64_t* n_global, mcrt_stats* stats);
+
+/* Host view of the maps built by mcrt_photon_emit (which: 0 caustic, 1 global). The pointers stay
+ * valid until the next mcrt_photon_emit / mcrt_destroy. */
+int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out);
+
+/* The octree construction step of mcrt_photon_emit alone, on caller photons (host only, no GPU
+ * needed): Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81,
+ * linear-octree.cpp:201-244). photons: [n][8] floats {flux.xyz, pos.xyz, phi, theta}. *out points
+ * into memory owned by *handle; release with mcrt_octree_free_host. */
+int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf,
+                           const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out);
+void mcrt_octree_free_host(void* handle);
+
 /* Replaces Camera::sampleImage (camera.cpp:101-145) for rows [y0, y1) with the default box
  * film (film.cpp:13-17): out_rgb[(y-y0)*W+x][3] = mean over sqrtspp² samples of
  * Integrator::sampleRay, clamped at 0 (film.cpp:112). Sample s of pixel p uses

@@ -25,7 +25,8 @@ NO_PRIM = 0xFFFFFFFF
 
 ABI_SYMBOLS = [
     "mcrt_abi_version", "mcrt_init", "mcrt_destroy", "mcrt_last_error", "mcrt_scene_upload",
-    "mcrt_photon_upload", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
+    "mcrt_photon_upload", "mcrt_photon_emit", "mcrt_photon_download", "mcrt_octree_build_host",
+    "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option",
 ]
@@ -98,6 +99,12 @@ class PhotonMapDesc(C.Structure):
                 ("n_photons", C.c_uint64), ("photons", C.c_void_p)]
 
 
+class PhotonEmitParams(C.Structure):
+    _fields_ = [("emissions", C.c_uint64), ("caustic_factor", C.c_double), ("max_photons_per_octree_leaf", C.c_uint32),
+                ("k_nearest_photons", C.c_uint32), ("direct_visualization", C.c_uint32), ("global_seed", C.c_uint32),
+                ("scene_bounds", C.c_double * 6)]
+
+
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("prim_tests", C.c_uint64), ("knn_queries", C.c_uint64),
@@ -132,6 +139,12 @@ def lib():
         L.mcrt_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_uint64)]
         L.mcrt_photon_upload.argtypes = [C.c_void_p, C.POINTER(PhotonMapDesc), C.POINTER(PhotonMapDesc),
                                          C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.mcrt_photon_emit.argtypes = [C.c_void_p, C.POINTER(PhotonEmitParams), C.c_int, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.POINTER(Stats)]
+        L.mcrt_photon_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(PhotonMapDesc)]
+        L.mcrt_octree_build_host.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PhotonMapDesc)]
+        L.mcrt_octree_free_host.argtypes = [C.c_void_p]
+        L.mcrt_octree_free_host.restype = None
         render_args = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_render_rows.argtypes = render_args
@@ -406,13 +419,42 @@ class PhotonMapper(Integrator):
     the CPU); maps come from the scene pack or from explicit arrays."""
     kind = INTEGRATOR_PHOTON
 
-    def __init__(self, scene, device=0, precision=PRECISION_F64, global_seed=0x12345678, photon_maps=None):
+    def __init__(self, scene, device=0, precision=PRECISION_F64, global_seed=0x12345678, photon_maps=None, emit=None):
+        """photon_maps: (caustic, global, k, direct_visualization) built by the reference's CPU pass (default: the
+        ones in the scene pack); emit: dict(emissions, caustic_factor, max_photons_per_octree_leaf, k_nearest_photons,
+        direct_visualization, scene_bounds) to run the photon pass on the GPU instead (mcrt_photon_emit)."""
         super().__init__(scene, device, precision, global_seed)
+        if emit is not None:
+            self.emit(**emit)
+            return
         maps = photon_maps or scene.photon_maps()
         if maps is None:
-            raise McrtError("PhotonMapper needs photon maps (scene pack exported with photon_map=True)")
+            raise McrtError("PhotonMapper needs photon maps (scene pack exported with photon_map=True) or emit=...")
         self._maps = maps
         self.upload_photons()
+
+    def emit(self, emissions, caustic_factor, max_photons_per_octree_leaf=200, k_nearest_photons=50,
+             direct_visualization=False, scene_bounds=None, precision=None):
+        """PhotonMapper::PhotonMapper's first pass on the GPU; replaces the uploaded maps."""
+        p = PhotonEmitParams()
+        p.emissions = int(emissions); p.caustic_factor = float(caustic_factor)
+        p.max_photons_per_octree_leaf = int(max_photons_per_octree_leaf); p.k_nearest_photons = int(k_nearest_photons)
+        p.direct_visualization = int(bool(direct_visualization)); p.global_seed = self.global_seed
+        b = scene_bounds if scene_bounds is not None else self.scene.a["node_bounds"][:6]
+        for i in range(6):
+            p.scene_bounds[i] = float(b[i])
+        nc, ng, st = C.c_uint64(), C.c_uint64(), Stats()
+        self._check(lib().mcrt_photon_emit(self.ctx, C.byref(p), self.precision if precision is None else precision,
+                                           C.byref(nc), C.byref(ng), C.byref(st)))
+        self.last_stats = st.as_dict()
+        self.k_nearest = int(k_nearest_photons)
+        maps = []
+        for which in (0, 1):
+            d = PhotonMapDesc()
+            self._check(lib().mcrt_photon_download(self.ctx, which, C.byref(d)))
+            maps.append(_map_arrays(d))
+        self._maps = (maps[0], maps[1], int(k_nearest_photons), int(bool(direct_visualization)))
+        return nc.value, ng.value
 
     @staticmethod
     def _map_desc(m):
@@ -440,6 +482,35 @@ class PhotonMapper(Integrator):
         st = Stats()
         self._check(lib().mcrt_knn_search(self.ctx, which, _ptr(points), n, _ptr(idx), _ptr(d2), _ptr(cnt), C.byref(st)))
         return idx, d2, cnt
+
+
+def _map_arrays(d):
+    """PhotonMapDesc (host pointers) -> dict of numpy copies."""
+    n, npn = d.n_octants, d.n_photons
+
+    def arr(ptr, ctype, count, dtype):
+        if not ptr or count == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).astype(dtype, copy=True)
+    return {"octant_bounds": arr(d.octant_bounds, C.c_double, 6 * n, np.float64),
+            "octant_start": arr(d.octant_start, C.c_uint64, n, np.uint64),
+            "octant_count": arr(d.octant_count, C.c_uint64, n, np.uint64),
+            "octant_next": arr(d.octant_next_sibling, C.c_uint32, n, np.uint32),
+            "octant_leaf": arr(d.octant_leaf, C.c_uint8, n, np.uint8),
+            "photons": arr(d.photons, C.c_float, 8 * npn, np.float32)}
+
+
+def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds):
+    """Host-only octree construction of mcrt_photon_emit (Octree<Photon> + LinearOctree::compact)."""
+    photons = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 8)
+    bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64)
+    h, d = C.c_void_p(), PhotonMapDesc()
+    rc = lib().mcrt_octree_build_host(_ptr(photons), len(photons), int(max_photons_per_octree_leaf), _ptr(bounds), C.byref(h), C.byref(d))
+    if rc:
+        raise McrtError(f"mcrt_octree_build_host failed: {rc}")
+    out = _map_arrays(d)
+    lib().mcrt_octree_free_host(h)
+    return out
 
 
 def shard_rows(height, rank, world_size):

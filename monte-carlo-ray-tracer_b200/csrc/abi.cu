@@ -13,6 +13,9 @@
 
 using namespace mcrt;
 
+// internal "integrator" of runWavefront: the photon emission pass (not an ABI value)
+static const int MCRT_INTERNAL_EMIT = 100;
+
 #define CK(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
@@ -75,6 +78,22 @@ struct mcrt_ctx
     std::vector<void*> photon_allocs;
     DevicePhotonMap photon_map[2];
     uint32_t k_nearest = 0, direct_visualization = 0;
+    // maps built by mcrt_photon_emit (host copies, also what mcrt_photon_download returns)
+    struct HostPhotonMap
+    {
+        std::vector<double> octant_bounds;
+        std::vector<uint64_t> octant_start, octant_count;
+        std::vector<uint32_t> octant_next;
+        std::vector<uint8_t> octant_leaf;
+        std::vector<float> photons;
+    } built_map[2];
+    bool built_valid = false;
+    // emission pass inputs (device), set by mcrt_photon_emit around runWavefront
+    const unsigned long long* d_emit_offsets = nullptr;
+    const void* d_emit_flux = nullptr;
+    float4* d_emit_photons[2] = { nullptr, nullptr };
+    unsigned long long emit_capacity[2] = { 0, 0 };
+    double emit_non_caustic_reject = 1.0;
     void* knn_queue64 = nullptr; void* knn_queue32 = nullptr;
     uint32_t knn_capacity64 = 0, knn_capacity32 = 0;
 
@@ -503,6 +522,15 @@ namespace
             }
         }
 
+        const bool emitting = integrator == MCRT_INTERNAL_EMIT;
+        if (emitting)
+        {
+            p.emit.emit_offsets = ctx->d_emit_offsets;
+            p.emit.photon_flux = static_cast<const V4<R>*>(ctx->d_emit_flux);
+            p.emit.photons[0] = ctx->d_emit_photons[0]; p.emit.photons[1] = ctx->d_emit_photons[1];
+            p.emit.capacity[0] = ctx->emit_capacity[0]; p.emit.capacity[1] = ctx->emit_capacity[1];
+            p.emit.non_caustic_reject = (R)ctx->emit_non_caustic_reject;
+        }
         if (integrator == MCRT_INTEGRATOR_PHOTON)
         {
             p.pm.map[0] = ctx->photon_map[0]; p.pm.map[1] = ctx->photon_map[1];
@@ -534,7 +562,8 @@ namespace
         CK(cudaEventRecord(ctx->ev_start, s));
         uint64_t launches = 0, iterations = 0;
 
-        Launch<R>::generate(p, 0, grid, s);
+        if (emitting) Launch<R>::emitGenerate(p, 0, grid, s);
+        else Launch<R>::generate(p, 0, grid, s);
         launchAdvance(ctx->d_counters, s);
         launches += 2;
         if (sorting) { sortPaths(0); launches += 2; }
@@ -563,7 +592,11 @@ namespace
                 }
                 Launch<R>::extend(p, cur, grid, s);
                 if (ev) cudaEventRecord(ev[1], s);
-                if (integrator == MCRT_INTEGRATOR_PHOTON)
+                if (emitting)
+                {
+                    Launch<R>::emitShade(p, cur, grid, s);
+                }
+                else if (integrator == MCRT_INTEGRATOR_PHOTON)
                 {
                     Launch<R>::shadePhoton(p, cur, grid, s);
                     Launch<R>::knn(p, grid, s);
@@ -574,16 +607,20 @@ namespace
                     Launch<R>::shade(p, cur, grid, s);
                 }
                 if (ev) cudaEventRecord(ev[2], s);
-                if (sorting)
+                if (!emitting)
                 {
-                    launchSortScan(p.sort.hist_shadow, p.sort, s);
-                    launchSortScatter(p.sort.shadow_key, p.sort.shadow_rank, p.sort, p.sort.shadow_order,
-                                      &ctx->d_counters->n_shadow, grid, s);
-                    launches += 2;
+                    if (sorting)
+                    {
+                        launchSortScan(p.sort.hist_shadow, p.sort, s);
+                        launchSortScatter(p.sort.shadow_key, p.sort.shadow_rank, p.sort, p.sort.shadow_order,
+                                          &ctx->d_counters->n_shadow, grid, s);
+                        launches += 2;
+                    }
+                    Launch<R>::shadow(p, grid, s);
                 }
-                Launch<R>::shadow(p, grid, s);
                 if (ev) cudaEventRecord(ev[3], s);
-                Launch<R>::generate(p, cur ^ 1, grid, s);
+                if (emitting) Launch<R>::emitGenerate(p, cur ^ 1, grid, s);
+                else Launch<R>::generate(p, cur ^ 1, grid, s);
                 launchAdvance(ctx->d_counters, s);
                 if (sorting) { sortPaths(cur ^ 1); launches += 2; }
                 if (ev) cudaEventRecord(ev[4], s);
@@ -604,8 +641,11 @@ namespace
             slot = other;
         }
 
-        launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
-        launches += 1;
+        if (!emitting)
+        {
+            launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
+            launches += 1;
+        }
         CK(cudaEventRecord(ctx->ev_stop, s));
         CK(cudaMemcpyAsync(&ctx->h_counters[0], ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -636,7 +676,102 @@ namespace
             ctx->error = "traversal stack/heap overflow: result would differ from the reference";
             return MCRT_ERR_UNSUPPORTED;
         }
+        if (emitting && c.photon_overflow)
+        {
+            ctx->error = "photon arrays overflowed";
+            return MCRT_ERR_UNSUPPORTED;
+        }
         return MCRT_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // Octree<Photon> + LinearOctree::compact on the host (octree.cpp:34-81, linear-octree.cpp:201-244).
+    // The reference inserts photons one by one; a node ends up internal exactly when more than
+    // max_node_data photons fall into its box, and child boxes are derived from the parent's box by
+    // fixed arithmetic, so the finished tree is a function of the photon set alone. This builder
+    // produces that tree top-down: partition the node's photons into octants (stable counting sort),
+    // recurse in octant order = the DFS order compact() emits.
+    struct OctreeBuilder
+    {
+        const float* in;            // photons, 8 floats each
+        uint32_t max_node_data;
+        mcrt_ctx::HostPhotonMap* out;
+        std::vector<float> scratch;
+
+        // photons [begin, end) of `data` belong to this node; returns the node's tight bounds
+        void build(std::vector<float>& data, uint64_t begin, uint64_t end, const double* bmin, const double* bmax, bool last, int depth = 0)
+        {
+            const uint64_t count = end - begin;
+            const uint32_t idx = (uint32_t)out->octant_leaf.size();
+            // (the reference recurses without bound when > max_node_data photons coincide; stop at 64 levels)
+            const bool split = count > max_node_data && depth < 64;
+            out->octant_leaf.push_back(split ? 0 : 1);
+            out->octant_start.push_back(begin);
+            out->octant_count.push_back(count);
+            out->octant_next.push_back(0xFFFFFFFFu);
+            out->octant_bounds.resize(out->octant_bounds.size() + 6);
+            double lo[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
+            double hi[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
+            for (uint64_t i = begin; i < end; i++)
+                for (int c = 0; c < 3; c++)
+                {
+                    const double v = (double)data[8 * i + 3 + c];
+                    if (lo[c] > v) lo[c] = v;
+                    if (hi[c] < v) hi[c] = v;
+                }
+            if (split)
+            {
+                // BoundingBox::centroid / dimensions (bounding-box.cpp:25-33), child boxes octree.cpp:51-60
+                double centroid[3], half[3];
+                for (int c = 0; c < 3; c++) { centroid[c] = (bmax[c] + bmin[c]) / 2.0; half[c] = (bmax[c] - bmin[c]) / 2.0; }
+                uint64_t counts[8] = { 0 }, starts[9];
+                auto octantOf = [&](const float* ph)
+                {
+                    int o = 0;
+                    for (int c = 0; c < 3; c++) if ((double)ph[3 + c] >= centroid[c]) o |= (4 >> c);   // octree.cpp:73-79
+                    return o;
+                };
+                for (uint64_t i = begin; i < end; i++) counts[octantOf(&data[8 * i])]++;
+                starts[0] = begin;
+                for (int o = 0; o < 8; o++) starts[o + 1] = starts[o] + counts[o];
+                scratch.resize(8 * count);
+                uint64_t cursor[8];
+                for (int o = 0; o < 8; o++) cursor[o] = starts[o] - begin;
+                for (uint64_t i = begin; i < end; i++)
+                {
+                    const int o = octantOf(&data[8 * i]);
+                    std::memcpy(&scratch[8 * cursor[o]++], &data[8 * i], 32);
+                }
+                std::memcpy(&data[8 * begin], scratch.data(), 32 * count);
+                int last_used = -1;
+                for (int o = 0; o < 8; o++) if (counts[o]) last_used = o;
+                for (int o = 0; o < 8; o++)
+                {
+                    if (!counts[o]) continue;   // empty leaves are dropped (linear-octree.cpp:222-229)
+                    double cmin[3], cmax[3];
+                    for (int c = 0; c < 3; c++)
+                    {
+                        const double new_origin = centroid[c] + half[c] * ((o & (4 >> c)) ? 0.5 : -0.5);
+                        const double h = half[c] * 0.5;
+                        cmin[c] = new_origin - h; cmax[c] = new_origin + h;
+                    }
+                    build(data, starts[o], starts[o + 1], cmin, cmax, o == last_used, depth + 1);
+                }
+            }
+            for (int c = 0; c < 3; c++) { out->octant_bounds[6 * idx + c] = lo[c]; out->octant_bounds[6 * idx + 3 + c] = hi[c]; }
+            out->octant_next[idx] = last ? 0xFFFFFFFFu : (uint32_t)out->octant_leaf.size();
+        }
+    };
+
+    void buildHostOctree(std::vector<float>& photons, uint32_t max_node_data, const double* bounds, mcrt_ctx::HostPhotonMap& out)
+    {
+        out = mcrt_ctx::HostPhotonMap();
+        const uint64_t n = photons.size() / 8;
+        if (n == 0) return;
+        OctreeBuilder b;
+        b.in = photons.data(); b.max_node_data = max_node_data; b.out = &out;
+        b.build(photons, 0, n, bounds, bounds + 3, true);
+        out.photons = std::move(photons);
     }
 
     int renderDispatch(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step, uint32_t n_rows,
@@ -664,6 +799,9 @@ namespace
         return MCRT_ERR_INVALID;
     }
 }
+
+extern "C" int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, const mcrt_photon_map_desc* global_map,
+                                  uint32_t k_nearest, uint32_t direct_visualization, uint64_t* h2d_bytes);
 
 extern "C"
 {
@@ -891,6 +1029,130 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, c
     ctx->direct_visualization = direct_visualization;
     ctx->has_photons = true;
     if (h2d_bytes) *h2d_bytes = bytes;
+    return MCRT_OK;
+}
+
+
+int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision, uint64_t* n_caustic,
+                     uint64_t* n_global, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!params || params->emissions == 0 || !(params->caustic_factor > 0.0) || params->max_photons_per_octree_leaf == 0 ||
+        params->k_nearest_photons == 0)
+    { ctx->error = "mcrt_photon_emit: invalid parameters"; return MCRT_ERR_INVALID; }
+    if (!ctx->has_scene) { ctx->error = "no scene uploaded"; return MCRT_ERR_NO_SCENE; }
+    CK(cudaSetDevice(ctx->device));
+    const DeviceScene<double>& sc = ctx->scene64;
+    if (sc.n_lights == 0) { ctx->error = "scene has no emissive surfaces"; return MCRT_ERR_INVALID; }
+
+    // photon-mapper.cpp:38-72: emissions per light proportional to its flux
+    std::vector<Light<double>> lights(sc.n_lights);
+    CK(cudaMemcpy(lights.data(), sc.lights, sizeof(Light<double>) * sc.n_lights, cudaMemcpyDeviceToHost));
+    const size_t photon_emissions = (size_t)((double)params->emissions * params->caustic_factor);
+    double total_add_flux = 0.0;
+    for (const auto& l : lights) { V3<double> f = l.emittance * l.area; total_add_flux += (0.0 + f.x + f.y + f.z); }
+    std::vector<unsigned long long> offsets(sc.n_lights + 1, 0);
+    std::vector<V4<double>> flux64(sc.n_lights);
+    std::vector<V4<float>> flux32(sc.n_lights);
+    for (uint32_t i = 0; i < sc.n_lights; i++)
+    {
+        const V3<double> light_flux = lights[i].emittance * lights[i].area;
+        const double share = (0.0 + light_flux.x + light_flux.y + light_flux.z) / total_add_flux;   // glm::compAdd
+        const size_t n_light = (size_t)((double)photon_emissions * share);
+        const V3<double> pf = light_flux / (double)n_light;
+        offsets[i + 1] = offsets[i] + n_light;
+        flux64[i] = V4<double>(pf, 0.0);
+        flux32[i] = V4<float>((float)pf.x, (float)pf.y, (float)pf.z, 0.0f);
+    }
+    const uint64_t total = offsets[sc.n_lights];
+    if (total == 0) { ctx->error = "no emissions"; return MCRT_ERR_INVALID; }
+
+    std::vector<void*> tmp;
+    auto cleanup = [&]() { freeAll(tmp); ctx->d_emit_offsets = nullptr; ctx->d_emit_flux = nullptr; ctx->d_emit_photons[0] = ctx->d_emit_photons[1] = nullptr; };
+    uint64_t bytes = 0;
+    const unsigned long long* d_off = nullptr;
+    int rc = devUpload(ctx, tmp, &d_off, offsets, bytes);
+    if (rc) { cleanup(); return rc; }
+    const void* d_flux = nullptr;
+    if (precision == MCRT_PRECISION_F64) { const V4<double>* q = nullptr; rc = devUpload(ctx, tmp, &q, flux64, bytes); d_flux = q; }
+    else if (precision == MCRT_PRECISION_F32) { const V4<float>* q = nullptr; rc = devUpload(ctx, tmp, &q, flux32, bytes); d_flux = q; }
+    else { cleanup(); ctx->error = "unknown precision"; return MCRT_ERR_INVALID; }
+    if (rc) { cleanup(); return rc; }
+    // capacity: a path stores at most one photon per bounce; 4 photons per emission per map is far
+    // above what any shipped scene produces (1.2 caustic per emission in water_caustics)
+    for (int w = 0; w < 2; w++)
+    {
+        ctx->emit_capacity[w] = 4ull * total + 1024;
+        if ((rc = devAlloc(ctx, tmp, &ctx->d_emit_photons[w], (size_t)ctx->emit_capacity[w] * 2))) { cleanup(); return rc; }
+    }
+    ctx->d_emit_offsets = d_off; ctx->d_emit_flux = d_flux;
+    ctx->emit_non_caustic_reject = 1.0 / params->caustic_factor;
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    if (precision == MCRT_PRECISION_F64)
+        rc = runWavefront<double>(ctx, nullptr, 0, 1, 0, 1, total, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
+    else
+        rc = runWavefront<float>(ctx, nullptr, 0, 1, 0, 1, total, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
+    if (rc) { cleanup(); return rc; }
+
+    const Counters& c = ctx->h_counters[0];
+    std::vector<float> photons[2];
+    for (int w = 0; w < 2; w++)
+    {
+        photons[w].resize((size_t)c.n_photons[w] * 8);
+        if (c.n_photons[w])
+        {
+            cudaError_t e = cudaMemcpy(photons[w].data(), ctx->d_emit_photons[w], (size_t)c.n_photons[w] * 32, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { cleanup(); ctx->error = cudaGetErrorString(e); return MCRT_ERR_CUDA; }
+        }
+    }
+    cleanup();
+    if (n_caustic) *n_caustic = c.n_photons[0];
+    if (n_global) *n_global = c.n_photons[1];
+
+    for (int w = 0; w < 2; w++) buildHostOctree(photons[w], params->max_photons_per_octree_leaf, params->scene_bounds, ctx->built_map[w]);
+    ctx->built_valid = true;
+    mcrt_photon_map_desc d[2];
+    for (int w = 0; w < 2; w++) mcrt_photon_download(ctx, w, &d[w]);
+    return mcrt_photon_upload(ctx, &d[0], &d[1], params->k_nearest_photons, params->direct_visualization, nullptr);
+}
+
+static void describeHostMap(const mcrt_ctx::HostPhotonMap& m, mcrt_photon_map_desc* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->n_octants = (uint32_t)m.octant_leaf.size();
+    out->octant_bounds = m.octant_bounds.data();
+    out->octant_start = m.octant_start.data();
+    out->octant_count = m.octant_count.data();
+    out->octant_next_sibling = m.octant_next.data();
+    out->octant_leaf = m.octant_leaf.data();
+    out->n_photons = m.photons.size() / 8;
+    out->photons = m.photons.data();
+}
+
+int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf, const double* scene_bounds6,
+                           void** handle, mcrt_photon_map_desc* out)
+{
+    if (!handle || !out || !scene_bounds6 || max_photons_per_octree_leaf == 0 || (n && !photons)) return MCRT_ERR_INVALID;
+    auto* m = new mcrt_ctx::HostPhotonMap();
+    std::vector<float> data(photons, photons + 8 * n);
+    buildHostOctree(data, max_photons_per_octree_leaf, scene_bounds6, *m);
+    describeHostMap(*m, out);
+    *handle = m;
+    return MCRT_OK;
+}
+
+void mcrt_octree_free_host(void* handle)
+{
+    delete static_cast<mcrt_ctx::HostPhotonMap*>(handle);
+}
+
+int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!out || (which != 0 && which != 1)) { ctx->error = "mcrt_photon_download: invalid arguments"; return MCRT_ERR_INVALID; }
+    if (!ctx->built_valid) { ctx->error = "no maps built by mcrt_photon_emit"; return MCRT_ERR_NO_PHOTONS; }
+    describeHostMap(ctx->built_map[which], out);
     return MCRT_OK;
 }
 

@@ -58,6 +58,9 @@ namespace mcrt
         uint32_t n_knn, _pad;
         // diagnostics of k_extend: sum over rays of (box+prim tests) and sum over warps of 32*max
         unsigned long long work_sum, work_warpmax;
+        // photon emission pass: photons stored so far in the caustic / global arrays
+        unsigned long long n_photons[2];
+        uint32_t photon_overflow, _pad2;
     };
 
     template <class R> struct PathBuffer
@@ -176,6 +179,17 @@ namespace mcrt
         return rank;
     }
 
+    // Photon emission pass (PhotonMapper::PhotonMapper + emitPhoton, photon-mapper.cpp:24-277).
+    // Work item w = emission j of light l: emit_offsets[l] <= w < emit_offsets[l+1].
+    template <class R> struct EmitParams
+    {
+        const unsigned long long* emit_offsets;  // [n_lights + 1] prefix sums of num_light_emissions
+        const V4<R>* photon_flux;                // [n_lights] light_flux / num_light_emissions
+        float4* photons[2];                      // output: 2 float4 per photon {flux.xyz,pos.x | pos.yz,phi,theta}
+        unsigned long long capacity[2];
+        R non_caustic_reject;                    // 1 / caustic_factor
+    };
+
     template <class R> struct WaveParams
     {
         DeviceScene<R> scene;
@@ -200,6 +214,7 @@ namespace mcrt
         PhotonParams<R> pm;     // photon maps + k-NN query queue (photon-mapped renders only)
         RaySort sort;           // coherence sort of the path / shadow queues (null order = disabled)
         const uint32_t* sobol_bytes; // byte-sliced Sobol matrices [6][4][256] (makeSobolByteTable)
+        EmitParams<R> emit;         // photon emission pass (mcrt_photon_emit) only
     };
 
     // ------------------------------------------------------------------------------------------
@@ -954,6 +969,233 @@ namespace mcrt
             __syncwarp();
         }
         if (overflow && lane == 0) atomicOr(overflow_flag, 1u);
+    }
+
+
+    // ------------------------------------------------------------------------------------------
+    // Photon emission pass on the device. Same wavefront as the camera paths:
+    // k_emit_generate -> [sort] -> k_extend -> k_emit_shade -> ... ; photons are appended to the
+    // caustic / global arrays with one atomic per warp per array.
+    template <class R>
+    __global__ void __launch_bounds__(256) k_emit_generate(WaveParams<R> p, int next)
+    {
+        Counters* c = p.counters;
+        const uint32_t n_next = c->n_next;
+        const unsigned long long remaining = c->total_work - c->next_work;
+        const uint32_t room = p.capacity - n_next;
+        const uint32_t count = remaining < (unsigned long long)room ? (uint32_t)remaining : room;
+        if (blockIdx.x == 0 && threadIdx.x == 0) c->n_gen = count;
+        const unsigned long long base_work = c->next_work;
+        const PathBuffer<R>& out = p.buf[next];
+        const DeviceScene<R>& sc = p.scene;
+
+        const uint32_t count_rounded = (count + 31u) & ~31u;
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count_rounded; j += gridDim.x * blockDim.x)
+        {
+            const bool valid = j < count;
+            uint32_t key = 0;
+            const uint32_t slot = n_next + j;
+            if (valid)
+            {
+                const unsigned long long w = base_work + j;
+                // light of this emission: last l with emit_offsets[l] <= w
+                uint32_t lo = 0, hi = sc.n_lights;
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (p.emit.emit_offsets[mid] <= w) lo = mid; else hi = mid; }
+                const uint32_t light = lo;
+                const uint32_t index = (uint32_t)(w - p.emit.emit_offsets[light]);
+                // photon-mapper.cpp:95-110: initiate(light_index), setIndex(offset + i), get<PM_LIGHT,4>
+                SamplerState smp = SamplerState::make(p.global_seed, light, index, 0u);
+                R u[4];
+                samplerGet<R, DIM_PM_LIGHT, 4>(smp, u);
+                V3<R> pos, normal;
+                sampleLightPoint(sc.lights[light], u[0], u[1], pos, normal);
+                const V3<R> dir = Frame<R>(normal).from(cosWeightedHemi(u[2], u[3]));
+                pos += normal * p.ray_eps;   // photon-mapper.cpp:108 (C::EPSILON in parity mode)
+                const V4<R> flux = p.emit.photon_flux[light];
+                out.ray_o[slot] = V4<R>(pos, sc.scene_ior);
+                out.ray_d[slot] = V4<R>(dir, R(1));
+                out.thr[slot] = V4<R>(flux.x, flux.y, flux.z, R(0));
+                out.meta[slot] = make_uint4(light, index, 0u, 0u);
+                out.meta2[slot] = make_uint4(NO_PRIM, 1u, 0u, sc.lights[light].type == PRIM_TRIANGLE ? sc.lights[light].prim : NO_PRIM);
+                if (p.sort.path_order) key = rayKey(p.sort, pos, dir, sc.lights[light].prim);
+            }
+            if (p.sort.path_order)
+            {
+                const uint32_t rank = sortRank(p.sort.hist_path, key, valid);
+                if (valid) { p.sort.path_key[next][slot] = key; p.sort.path_rank[next][slot] = rank; }
+            }
+        }
+    }
+
+    MCRT_D void storePhoton(float4* arr, unsigned long long idx, const V3<double>& flux, const V3<double>& pos, const V3<double>& dir)
+    {
+        // Photon::Photon, photon.hpp:7-12: float flux/position, polar angles of the direction
+        const float theta = (float)atan2(sqrt(dir.x * dir.x + dir.y * dir.y), dir.z);
+        const float phi = (float)atan2(dir.y, dir.x);
+        arr[2 * idx] = make_float4((float)flux.x, (float)flux.y, (float)flux.z, (float)pos.x);
+        arr[2 * idx + 1] = make_float4((float)pos.y, (float)pos.z, phi, theta);
+    }
+
+    template <class R>
+    __global__ void __launch_bounds__(128, MCRT_SHADE_MINBLOCKS) k_emit_shade(WaveParams<R> p, int cur)
+    {
+        __shared__ SobolByteTables sobol_tab;
+        sobol_tab.fill(p.sobol_bytes);
+        __syncthreads();
+        Counters* c = p.counters;
+        const uint32_t n = c->n_cur;
+        const PathBuffer<R>& in = p.buf[cur];
+        const PathBuffer<R>& out = p.buf[cur ^ 1];
+        const DeviceScene<R>& sc = p.scene;
+        const bool sorting = p.sort.path_order != nullptr;
+        uint32_t local_max_depth = 0, stack_overflows = 0;
+
+        const uint32_t n_rounded = (n + 31u) & ~31u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x)
+        {
+            bool alive = i < n;
+            int store = -1;              // 0 caustic, 1 global
+            V3<R> ph_flux, ph_pos, ph_dir;
+            PathRay<R> ray, nray;
+            V3<R> flux;
+            uint4 meta, meta2;
+            uint32_t ior_count = 1, hit_prim = NO_PRIM;
+            R iors[IOR_STACK_CAPACITY];
+
+            if (alive)
+            {
+                const V4<R> ro = in.ray_o[i], rd = in.ray_d[i], th = in.thr[i], hv = p.hits[i];
+                meta = in.meta[i]; meta2 = in.meta2[i];
+                ray.start = ro.xyz(); ray.medium_ior = ro.w;
+                ray.direction = rd.xyz(); ray.refraction_scale = rd.w;
+                flux = th.xyz();
+                ray.depth = meta.z & 0xFFFFu; ray.diffuse_depth = meta.z >> 16;
+                ray.refraction_level = (int32_t)meta.w;
+                ior_count = meta2.y & 0xFFu;
+                ray.dirac_delta = (meta2.y >> 8) & 1u;
+                ray.refraction = false;
+                iors[0] = sc.scene_ior;
+                if (ior_count > 1)
+                {
+                    const V4<R> ia_ = in.iors_a[i];
+                    iors[1] = ia_.x; iors[2] = ia_.y; iors[3] = ia_.z; iors[4] = ia_.w;
+                    if (ior_count > 5) { const V4<R> ib_ = in.iors_b[i]; iors[5] = ib_.x; iors[6] = ib_.y; iors[7] = ib_.z; }
+                }
+                if (ray.depth > local_max_depth) local_max_depth = ray.depth;
+
+                Hit<R> hit;
+                hit.t = hv.x; hit.u = hv.y; hit.v = hv.z;
+                hit.prim = hv.w < R(0) ? NO_PRIM : (uint32_t)hv.w;
+                hit_prim = hit.prim;
+                if (hit.prim == NO_PRIM)
+                {
+                    alive = false;  // photon-mapper.cpp:238-241
+                }
+                else
+                {
+                    SamplerState smp = SamplerState::make(p.global_seed, meta.x, meta.y, ray.depth + 1u);
+                    smp.tab = &sobol_tab;
+                    int ext_idx = ray.refraction_level - 1;
+                    ext_idx = ext_idx < 0 ? 0 : (ext_idx > (int)ior_count - 1 ? (int)ior_count - 1 : ext_idx);
+                    Interaction<R> ia;
+                    buildInteraction(ia, sc, hit, ray, iors[ext_idx], smp);
+                    const Material<R>& m = *ia.material;
+
+                    // photon-mapper.cpp:245-256: store only where non-delta interactions are possible
+                    if (!(m.flags & MAT_DIRAC_DELTA))
+                    {
+                        if (ray.dirac_delta)
+                        {
+                            store = 0; ph_flux = flux;
+                        }
+                        else
+                        {
+                            R ur;
+                            samplerGet<R, DIM_PM_REJECT, 1>(smp, &ur);
+                            if (p.emit.non_caustic_reject > ur) { store = 1; ph_flux = flux / p.emit.non_caustic_reject; }
+                        }
+                        ph_pos = ia.position; ph_dir = -ray.direction;
+                    }
+
+                    V3<R> bsdf_absIdotN; R bsdf_pdf;
+                    if (!sampleBSDF(ia, ray, smp, p.ray_eps, true, bsdf_absIdotN, bsdf_pdf, nray))
+                    {
+                        alive = false;
+                    }
+                    else
+                    {
+                        bsdf_absIdotN /= bsdf_pdf;
+                        // photon-mapper.cpp:265-272: survival probability instead of flux scaling
+                        R survive = gmin(compMax(bsdf_absIdotN), R(0.95));
+                        R ua;
+                        samplerGet<R, DIM_ABSORB, 1>(smp, &ua);
+                        if (survive == R(0) || survive <= ua) alive = false;
+                        else
+                        {
+                            flux *= bsdf_absIdotN / survive;
+                            if (nray.refraction_level > 0)   // RefractionHistory::update
+                            {
+                                if (nray.refraction_level == (int32_t)ior_count)
+                                {
+                                    if (ior_count < (uint32_t)IOR_STACK_CAPACITY) iors[ior_count++] = nray.medium_ior;
+                                    else stack_overflows++;
+                                }
+                                else if (nray.refraction_level < (int32_t)ior_count - 1) ior_count--;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // photons: warp-aggregated append per array
+            for (int which = 0; which < 2; which++)
+            {
+                const bool mine = store == which;
+                const unsigned mask = __ballot_sync(0xFFFFFFFFu, mine);
+                if (mask)
+                {
+                    const unsigned lane = threadIdx.x & 31u;
+                    const int leader = __ffs(mask) - 1;
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&c->n_photons[which], (unsigned long long)__popc(mask));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (mine)
+                    {
+                        const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1u));
+                        if (idx < p.emit.capacity[which])
+                            storePhoton(p.emit.photons[which], idx, V3<double>((double)ph_flux.x, (double)ph_flux.y, (double)ph_flux.z),
+                                        V3<double>((double)ph_pos.x, (double)ph_pos.y, (double)ph_pos.z),
+                                        V3<double>((double)ph_dir.x, (double)ph_dir.y, (double)ph_dir.z));
+                        else c->photon_overflow = 1u;
+                    }
+                }
+            }
+
+            const uint32_t slot = warpAppend(&c->n_next, alive);
+            uint32_t pkey = 0, prank = 0;
+            if (sorting && alive)
+            {
+                pkey = rayKey(p.sort, nray.start, nray.direction, hit_prim);
+                prank = atomicAdd(&p.sort.hist_path[pkey], 1u);
+            }
+            if (alive)
+            {
+                out.ray_o[slot] = V4<R>(nray.start, nray.medium_ior);
+                out.ray_d[slot] = V4<R>(nray.direction, nray.refraction_scale);
+                out.thr[slot] = V4<R>(flux, R(0));
+                if (ior_count > 1)
+                {
+                    out.iors_a[slot] = V4<R>(iors[1], iors[2], iors[3], iors[4]);
+                    if (ior_count > 5) out.iors_b[slot] = V4<R>(iors[5], iors[6], iors[7], R(0));
+                }
+                out.meta[slot] = make_uint4(meta.x, meta.y, (nray.depth & 0xFFFFu) | (nray.diffuse_depth << 16), (uint32_t)nray.refraction_level);
+                out.meta2[slot] = make_uint4(NO_PRIM, ior_count | (nray.dirac_delta ? 256u : 0u), 0u,
+                                             sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
+                if (sorting) { p.sort.path_key[cur ^ 1][slot] = pkey; p.sort.path_rank[cur ^ 1][slot] = prank; }
+            }
+        }
+        if (local_max_depth) atomicMax(&c->max_depth, local_max_depth);
+        if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
     // ------------------------------------------------------------------------------------------

@@ -27,6 +27,14 @@ namespace mcrt
     {
         k_shadow<MCRT_REAL><<<grid, 256, 0, s>>>(p);
     }
+    template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
+    {
+        k_emit_generate<MCRT_REAL><<<grid, 256, 0, s>>>(p, next);
+    }
+    template <> void Launch<MCRT_REAL>::emitShade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
+    {
+        k_emit_shade<MCRT_REAL><<<grid * 2, 128, 0, s>>>(p, cur);
+    }
     template <> void Launch<MCRT_REAL>::traceUser(const DeviceScene<MCRT_REAL>& sc, const double* rays6, size_t n,
                                                   double* out_tuv, uint32_t* out_prim, Counters* c, int grid, cudaStream_t s)
     {

@@ -13,6 +13,8 @@ namespace mcrt
         static void shade(const WaveParams<R>& p, int cur, int grid, cudaStream_t s);   // PathTracer loop body
         static void shadePhoton(const WaveParams<R>& p, int cur, int grid, cudaStream_t s); // PhotonMapper loop body
         static void knn(const WaveParams<R>& p, int grid, cudaStream_t s);
+        static void emitGenerate(const WaveParams<R>& p, int next, int grid, cudaStream_t s);
+        static void emitShade(const WaveParams<R>& p, int cur, int grid, cudaStream_t s);
         static void shadow(const WaveParams<R>& p, int grid, cudaStream_t s);
         static void traceUser(const DeviceScene<R>& sc, const double* rays6, size_t n, double* out_tuv,
                               uint32_t* out_prim, Counters* c, int grid, cudaStream_t s);

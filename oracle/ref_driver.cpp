@@ -436,6 +436,11 @@ int ref_export_pack(void* handle, const char* path)
         uint32_t k, dv;
         mcrt_host::photonMapParams(*pm, k, dv);
         w.addScalarsU32("photon_params", { k, dv });
+        // parameters of the photon pass (scene JSON "photon_map") + Scene::BB(), for mcrt_photon_emit
+        const auto& pmj = h->scene_json.at("photon_map");
+        const BoundingBox bb = h->camera->integrator->scene.BB();
+        w.addScalars("photon_emit_params", { (double)pmj.at("emissions").get<size_t>(), pmj.at("caustic_factor").get<double>(),
+                                             (double)pm->max_node_data, bb.min.x, bb.min.y, bb.min.z, bb.max.x, bb.max.y, bb.max.z });
     }
     return w.write(path) ? 0 : -1;
 }
