@@ -83,10 +83,15 @@ namespace mcrt
         uint32_t* fr_node;    // [KNN_FRONTIER]
     };
 
+    // warp maximum of non-negative doubles: their bit patterns order like the values, so two
+    // hardware integer reductions (REDUX) replace five 64-bit shuffle steps
     MCRT_D double warpMaxD(double v)
     {
-        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
-        return v;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        const unsigned mlo = __reduce_max_sync(0xFFFFFFFFu, hi == mhi ? lo : 0u);
+        return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
     }
 
     // Warp-cooperative search. Distances are always float64, as in the reference
@@ -130,26 +135,36 @@ namespace mcrt
                         cand = d2 <= max_d2;
                     }
                     unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand);
+                    // fill phase: while the result set has room, the candidates of a batch are appended
+                    // in parallel (the reference's push_unordered, linear-octree.cpp:63-66)
+                    if (ballot && n_found < k)
+                    {
+                        const uint32_t room = k - n_found;
+                        const uint32_t my = (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                        if (cand && my < room) { sh.res_d2[n_found + my] = d2; sh.res_idx[n_found + my] = (uint32_t)(base + lane); }
+                        const uint32_t taken = min(room, (uint32_t)__popc(ballot));
+                        n_found += taken;
+                        // drop the lanes that were stored from the ballot
+                        unsigned rest = ballot;
+                        for (uint32_t t = 0; t < taken; t++) rest &= rest - 1;
+                        ballot = rest;
+                        __syncwarp();
+                        if (n_found == k)
+                        {
+                            double m = 0.0;
+                            for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            cur_max = warpMaxD(m);
+                            if (cur_max < max_d2) max_d2 = cur_max;
+                        }
+                    }
+                    // replace phase: one candidate at a time against the current farthest result
                     while (ballot)
                     {
                         const int src = __ffs(ballot) - 1;
                         ballot &= ballot - 1;
                         const double cd2 = __shfl_sync(0xFFFFFFFFu, d2, src);
                         const uint32_t cidx = (uint32_t)(base + src);
-                        if (n_found < k)
-                        {
-                            if (lane == 0) { sh.res_d2[n_found] = cd2; sh.res_idx[n_found] = cidx; }
-                            n_found++;
-                            __syncwarp();
-                            if (n_found == k)
-                            {
-                                double m = 0.0;
-                                for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
-                                cur_max = warpMaxD(m);
-                                if (cur_max < max_d2) max_d2 = cur_max;
-                            }
-                        }
-                        else if (cd2 <= max_d2)
+                        if (cd2 <= max_d2)
                         {
                             // pop_push: replace the farthest of the k results (linear-octree.cpp:79)
                             uint32_t slot = 0xFFFFFFFFu;
@@ -258,9 +273,18 @@ namespace mcrt
     // Photon::dir(), photon.hpp:19-27: std::sin/std::cos of the *float* angles (float overloads),
     // products in double. The float results are obtained by rounding the double functions, which is
     // what glibc's sinf/cosf return in all but vanishingly rare double-rounding cases.
+    MCRT_D V3<float> photonDirFast(float phi, float theta)
+    {
+        float st, ct, sp, cp;
+        sincosf(theta, &st, &ct);
+        sincosf(phi, &sp, &cp);
+        return V3<float>(st * cp, st * sp, ct);
+    }
+
     template <class R>
     MCRT_D V3<R> photonDir(float phi, float theta)
     {
+        if constexpr (sizeof(R) == 4) return photonDirFast(phi, theta);   // fast mode: float sincosf
         float st = (float)sin((double)theta), ct = (float)cos((double)theta);
         float sp = (float)sin((double)phi), cp = (float)cos((double)phi);
         double sin_theta = (double)st;
