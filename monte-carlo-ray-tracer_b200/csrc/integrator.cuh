@@ -872,8 +872,8 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.
-    template <class R>
-    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK) k_knn(WaveParams<R> p)
+    template <class R, int SLOTS>
+    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK, 4) k_knn(WaveParams<R> p)
     {
         extern __shared__ __align__(16) unsigned char knn_smem[];
         const uint32_t n = min(p.counters->n_knn, p.pm.query_capacity);
@@ -888,8 +888,8 @@ namespace mcrt
             const uint32_t which = (qr.meta.z >> 1) & 1u;
             const DevicePhotonMap& map = p.pm.map[which];
             double res_max;
-            const uint32_t found = knnSearchWarp(map, k, (double)qr.pos_n1.x, (double)qr.pos_n1.y, (double)qr.pos_n1.z,
-                                                 sh, &res_max, &overflow);
+            const uint32_t found = knnSearchWarpT<SLOTS>(map, k, (double)qr.pos_n1.x, (double)qr.pos_n1.y, (double)qr.pos_n1.z,
+                                                         sh, &res_max, &overflow);
             if (found == 0) continue;
 
             // rebuild the Interaction fields Interaction::BSDF reads
@@ -947,7 +947,8 @@ namespace mcrt
     }
 
     // Batched LinearOctree::knnSearch on caller points (mcrt_knn_search): results sorted by the host.
-    static __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK) k_knn_user(DevicePhotonMap map, uint32_t k, const double* points,
+    template <int SLOTS>
+    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK) k_knn_user(DevicePhotonMap map, uint32_t k, const double* points,
                                                                           size_t n, uint32_t* out_index, double* out_d2,
                                                                           uint32_t* out_count, uint32_t* overflow_flag)
     {
@@ -959,7 +960,7 @@ namespace mcrt
         for (size_t q = (size_t)blockIdx.x * KNN_WARPS_PER_BLOCK + (threadIdx.x >> 5); q < n; q += warps_total)
         {
             double res_max;
-            const uint32_t found = knnSearchWarp(map, k, points[3 * q], points[3 * q + 1], points[3 * q + 2], sh, &res_max, &overflow);
+            const uint32_t found = knnSearchWarpT<SLOTS>(map, k, points[3 * q], points[3 * q + 1], points[3 * q + 2], sh, &res_max, &overflow);
             for (uint32_t s = lane; s < k; s += 32)
             {
                 out_index[q * k + s] = s < found ? sh.res_idx[s] : 0xFFFFFFFFu;

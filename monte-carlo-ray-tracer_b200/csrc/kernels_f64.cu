@@ -26,7 +26,16 @@ namespace mcrt
     void launchKnnUser(const DevicePhotonMap& map, uint32_t k, const double* points, size_t n, uint32_t* out_index,
                        double* out_d2, uint32_t* out_count, uint32_t* overflow_flag, int grid, cudaStream_t s)
     {
-        k_knn_user<<<grid, 32 * KNN_WARPS_PER_BLOCK, knnSharedBytes(k), s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag);
+        const dim3 g(grid), b(32 * KNN_WARPS_PER_BLOCK);
+        const size_t smem = knnSharedBytes(k);
+        switch (knnSlotsFor(k))
+        {
+            case 1: k_knn_user<1><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;
+            case 2: k_knn_user<2><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;
+            case 4: k_knn_user<4><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;
+            case 8: k_knn_user<8><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;
+            default: k_knn_user<0><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;
+        }
     }
 
     __global__ void k_sampler_stream(const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t n_shuffles,

@@ -21,7 +21,18 @@ namespace mcrt
     }
     template <> void Launch<MCRT_REAL>::knn(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
-        k_knn<MCRT_REAL><<<grid * 2, 32 * KNN_WARPS_PER_BLOCK, knnSharedBytes(p.pm.k_nearest), s>>>(p);
+        const dim3 g(grid * 2), b(32 * KNN_WARPS_PER_BLOCK);
+        const size_t smem = knnSharedBytes(p.pm.k_nearest);
+        // the photon maps hold at least k photons in every render that matters; if a map is smaller the
+        // search clamps k itself and the register slots are simply not all used
+        switch (knnSlotsFor(p.pm.k_nearest))
+        {
+            case 1: k_knn<MCRT_REAL, 1><<<g, b, smem, s>>>(p); break;
+            case 2: k_knn<MCRT_REAL, 2><<<g, b, smem, s>>>(p); break;
+            case 4: k_knn<MCRT_REAL, 4><<<g, b, smem, s>>>(p); break;
+            case 8: k_knn<MCRT_REAL, 8><<<g, b, smem, s>>>(p); break;
+            default: k_knn<MCRT_REAL, 0><<<g, b, smem, s>>>(p); break;
+        }
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {

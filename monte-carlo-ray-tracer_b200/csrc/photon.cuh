@@ -97,9 +97,17 @@ namespace mcrt
     // Warp-cooperative search. Distances are always float64, as in the reference
     // (glm::distance2(data.pos(), p) on dvec3). Returns the number of results (<= k); the results
     // are left in sh.res_*; *res_max is the largest distance2 among them.
-    MCRT_D uint32_t knnSearchWarp(const DevicePhotonMap& map, uint32_t k, double px, double py, double pz,
-                                  const KnnShared& sh, double* res_max, uint32_t* overflow)
+    // SLOTS = ceil(k / 32) when that is 1, 2, 4 or 8: once the result set is full it moves from
+    // shared memory into SLOTS registers per lane (slot s lives in lane s % 32), so replacing the
+    // farthest result and re-deriving the maximum are register operations + two REDUX (ncu on the
+    // shared-memory version: 37 % of all instructions were those two loops). SLOTS = 0: any k.
+    template <int SLOTS>
+    MCRT_D uint32_t knnSearchWarpT(const DevicePhotonMap& map, uint32_t k, double px, double py, double pz,
+                                   const KnnShared& sh, double* res_max, uint32_t* overflow)
     {
+        constexpr int NS = SLOTS > 0 ? SLOTS : 1;
+        double r_d2[NS]; uint32_t r_idx[NS];
+        bool in_regs = false;
         const unsigned lane = threadIdx.x & 31u;
         *res_max = 0.0;
         if (map.n_octants == 0 || map.n_photons == 0) return 0;
@@ -152,7 +160,22 @@ namespace mcrt
                         if (n_found == k)
                         {
                             double m = 0.0;
-                            for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            if constexpr (SLOTS > 0)
+                            {
+#pragma unroll
+                                for (int j = 0; j < NS; j++)
+                                {
+                                    const uint32_t s = lane + 32u * j;
+                                    r_d2[j] = s < k ? sh.res_d2[s] : -1.0;
+                                    r_idx[j] = s < k ? sh.res_idx[s] : 0xFFFFFFFFu;
+                                    m = fmax(m, r_d2[j]);
+                                }
+                                in_regs = true;
+                            }
+                            else
+                            {
+                                for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            }
                             cur_max = warpMaxD(m);
                             if (cur_max < max_d2) max_d2 = cur_max;
                         }
@@ -167,14 +190,31 @@ namespace mcrt
                         if (cd2 <= max_d2)
                         {
                             // pop_push: replace the farthest of the k results (linear-octree.cpp:79)
-                            uint32_t slot = 0xFFFFFFFFu;
-                            for (uint32_t s = lane; s < k; s += 32) if (sh.res_d2[s] == cur_max) slot = s;
-                            const unsigned has = __ballot_sync(0xFFFFFFFFu, slot != 0xFFFFFFFFu);
-                            const int owner = __ffs(has) - 1;
-                            if ((int)lane == owner) { sh.res_d2[slot] = cd2; sh.res_idx[slot] = cidx; }
-                            __syncwarp();
                             double m = 0.0;
-                            for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            if constexpr (SLOTS > 0)
+                            {
+                                int mine = -1;
+#pragma unroll
+                                for (int j = NS - 1; j >= 0; j--) if (r_d2[j] == cur_max) mine = j;
+                                const unsigned has = __ballot_sync(0xFFFFFFFFu, mine >= 0);
+                                const int owner = __ffs(has) - 1;
+#pragma unroll
+                                for (int j = 0; j < NS; j++)
+                                {
+                                    if ((int)lane == owner && j == mine) { r_d2[j] = cd2; r_idx[j] = cidx; }
+                                    m = fmax(m, r_d2[j]);
+                                }
+                            }
+                            else
+                            {
+                                uint32_t slot = 0xFFFFFFFFu;
+                                for (uint32_t s = lane; s < k; s += 32) if (sh.res_d2[s] == cur_max) slot = s;
+                                const unsigned has = __ballot_sync(0xFFFFFFFFu, slot != 0xFFFFFFFFu);
+                                const int owner = __ffs(has) - 1;
+                                if ((int)lane == owner) { sh.res_d2[slot] = cd2; sh.res_idx[slot] = cidx; }
+                                __syncwarp();
+                                for (uint32_t s = lane; s < k; s += 32) m = fmax(m, sh.res_d2[s]);
+                            }
                             cur_max = warpMaxD(m);
                             if (cur_max < max_d2) max_d2 = cur_max;
                         }
@@ -246,8 +286,28 @@ namespace mcrt
             for (uint32_t s = lane; s < n_found; s += 32) m = fmax(m, sh.res_d2[s]);
             cur_max = warpMaxD(m);
         }
+        if constexpr (SLOTS > 0)
+        {
+            if (in_regs)
+            {
+                // hand the results back through shared memory (what the callers read)
+#pragma unroll
+                for (int j = 0; j < NS; j++)
+                {
+                    const uint32_t s = lane + 32u * j;
+                    if (s < k) { sh.res_d2[s] = r_d2[j]; sh.res_idx[s] = r_idx[j]; }
+                }
+                __syncwarp();
+            }
+        }
         *res_max = cur_max;
         return n_found;
+    }
+
+    // register slots for a given k (0 = shared-memory fallback)
+    inline int knnSlotsFor(uint32_t k)
+    {
+        return k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : k <= 256 ? 8 : 0;
     }
 
     MCRT_D KnnShared knnSharedFor(unsigned char* smem, uint32_t k_pad)
