@@ -52,7 +52,7 @@ def build(force=False, verbose=False, defines=(), suffix=""):
         for o in outs:
             sys.stderr.write(o)
     if jobs or not os.path.exists(lib):
-        _run(["nvcc"] + ARCH + ["-shared", "-o", lib] + objs)
+        _run(["nvcc"] + ARCH + ["-shared", "-o", lib] + objs + ["-Xcompiler", "-pthread"])
     return lib
 
 

@@ -4,8 +4,10 @@
 // There is deliberately no CPU fallback: without a CUDA device every entry point fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mcrt_abi.h"
@@ -763,14 +765,100 @@ namespace
         }
     };
 
+    // Parallel front end: the top two levels are partitioned serially, the (up to 64) subtrees are
+    // built by worker threads into fragments with local node indices, then concatenated in octant
+    // (= depth-first) order with the sibling links rebased. Same tree as the serial builder.
+    struct OctreeFragment
+    {
+        mcrt_ctx::HostPhotonMap map;   // photons unused
+    };
+
+    void appendFragment(mcrt_ctx::HostPhotonMap& dst, const mcrt_ctx::HostPhotonMap& src, bool last)
+    {
+        const uint32_t offset = (uint32_t)dst.octant_leaf.size();
+        dst.octant_bounds.insert(dst.octant_bounds.end(), src.octant_bounds.begin(), src.octant_bounds.end());
+        dst.octant_start.insert(dst.octant_start.end(), src.octant_start.begin(), src.octant_start.end());
+        dst.octant_count.insert(dst.octant_count.end(), src.octant_count.begin(), src.octant_count.end());
+        dst.octant_leaf.insert(dst.octant_leaf.end(), src.octant_leaf.begin(), src.octant_leaf.end());
+        for (uint32_t v : src.octant_next) dst.octant_next.push_back(v == 0xFFFFFFFFu ? v : v + offset);
+        // the fragment's root was built as "last"; give it its real sibling link
+        dst.octant_next[offset] = last ? 0xFFFFFFFFu : (uint32_t)dst.octant_leaf.size();
+    }
+
+    void buildSubtreeParallel(std::vector<float>& data, uint64_t begin, uint64_t end, const double* bmin, const double* bmax,
+                              uint32_t max_node_data, int depth, mcrt_ctx::HostPhotonMap& out)
+    {
+        const uint64_t count = end - begin;
+        // MCRT_OCTREE_PAR_MIN: test hook to push small inputs through the parallel path
+        static const uint64_t par_min = []() { const char* e = std::getenv("MCRT_OCTREE_PAR_MIN"); return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)200000; }();
+        if (depth >= 2 || count <= max_node_data || count < par_min)
+        {
+            OctreeBuilder b;
+            b.in = data.data(); b.max_node_data = max_node_data; b.out = &out;
+            b.build(data, begin, end, bmin, bmax, true, depth);
+            return;
+        }
+        // this node (internal): bounds over its photons, octant partition exactly as OctreeBuilder::build
+        double lo[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
+        double hi[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
+        double centroid[3], half[3];
+        for (int c = 0; c < 3; c++) { centroid[c] = (bmax[c] + bmin[c]) / 2.0; half[c] = (bmax[c] - bmin[c]) / 2.0; }
+        auto octantOf = [&](const float* ph)
+        {
+            int o = 0;
+            for (int c = 0; c < 3; c++) if ((double)ph[3 + c] >= centroid[c]) o |= (4 >> c);
+            return o;
+        };
+        uint64_t counts[8] = { 0 }, starts[9];
+        for (uint64_t i = begin; i < end; i++)
+        {
+            for (int c = 0; c < 3; c++) { const double v = (double)data[8 * i + 3 + c]; if (lo[c] > v) lo[c] = v; if (hi[c] < v) hi[c] = v; }
+            counts[octantOf(&data[8 * i])]++;
+        }
+        starts[0] = begin;
+        for (int o = 0; o < 8; o++) starts[o + 1] = starts[o] + counts[o];
+        {
+            std::vector<float> scratch(8 * count);
+            uint64_t cursor[8];
+            for (int o = 0; o < 8; o++) cursor[o] = starts[o] - begin;
+            for (uint64_t i = begin; i < end; i++) std::memcpy(&scratch[8 * cursor[octantOf(&data[8 * i])]++], &data[8 * i], 32);
+            std::memcpy(&data[8 * begin], scratch.data(), 32 * count);
+        }
+        mcrt_ctx::HostPhotonMap frag[8];
+        std::vector<std::thread> workers;
+        for (int o = 0; o < 8; o++)
+        {
+            if (!counts[o]) continue;
+            workers.emplace_back([&, o]()
+            {
+                double cmin[3], cmax[3];
+                for (int c = 0; c < 3; c++)
+                {
+                    const double new_origin = centroid[c] + half[c] * ((o & (4 >> c)) ? 0.5 : -0.5);
+                    const double h = half[c] * 0.5;
+                    cmin[c] = new_origin - h; cmax[c] = new_origin + h;
+                }
+                buildSubtreeParallel(data, starts[o], starts[o + 1], cmin, cmax, max_node_data, depth + 1, frag[o]);
+            });
+        }
+        for (auto& w : workers) w.join();
+        out.octant_leaf.push_back(0);
+        out.octant_start.push_back(begin);
+        out.octant_count.push_back(count);
+        out.octant_next.push_back(0xFFFFFFFFu);
+        for (int c = 0; c < 3; c++) out.octant_bounds.push_back(lo[c]);
+        for (int c = 0; c < 3; c++) out.octant_bounds.push_back(hi[c]);
+        int last_used = -1;
+        for (int o = 0; o < 8; o++) if (counts[o]) last_used = o;
+        for (int o = 0; o < 8; o++) if (counts[o]) appendFragment(out, frag[o], o == last_used);
+    }
+
     void buildHostOctree(std::vector<float>& photons, uint32_t max_node_data, const double* bounds, mcrt_ctx::HostPhotonMap& out)
     {
         out = mcrt_ctx::HostPhotonMap();
         const uint64_t n = photons.size() / 8;
         if (n == 0) return;
-        OctreeBuilder b;
-        b.in = photons.data(); b.max_node_data = max_node_data; b.out = &out;
-        b.build(photons, 0, n, bounds, bounds + 3, true);
+        buildSubtreeParallel(photons, 0, n, bounds, bounds + 3, max_node_data, 0, out);
         out.photons = std::move(photons);
     }
 

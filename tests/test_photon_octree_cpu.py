@@ -33,6 +33,27 @@ def test_octree_matches_reference(mcrt):
         assert _leaf_sets(built) == _leaf_sets(ref_map)
 
 
+def test_parallel_build_path_matches_reference():
+    """Same check through the multi-threaded front end (subtrees built by worker threads and
+    concatenated): forced on for this small input with MCRT_OCTREE_PAR_MIN in a fresh process."""
+    import subprocess, sys
+    code = (
+        "import importlib, os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "m = importlib.import_module('monte-carlo-ray-tracer_b200')\n"
+        "scene = m.Scene.from_pack(%r)\n"
+        "maps = scene.photon_maps(); p = scene.extra['photon_emit_params']\n"
+        "for ref in maps[:2]:\n"
+        "    ph = ref['photons'].reshape(-1, 8)[::-1]\n"
+        "    b = m.build_photon_octree(ph, int(p[2]), p[3:9])\n"
+        "    for k in ('octant_start', 'octant_count', 'octant_next', 'octant_leaf', 'octant_bounds'):\n"
+        "        assert np.array_equal(b[k], ref[k]), k\n"
+        "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(GOLDEN, "pm_hexagon_room_64.mcrtpack"))
+    env = dict(os.environ, MCRT_OCTREE_PAR_MIN="300")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_octree_edge_cases(mcrt):
     bounds = np.array([0, 0, 0, 1, 1, 1], dtype=np.float64)
     empty = mcrt.build_photon_octree(np.zeros((0, 8), np.float32), 4, bounds)
