@@ -192,8 +192,7 @@ def run_gpu_arm(args):
         cam = cam.resized(cam.width, cam.height, args.sqrtspp)
     precision = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32
     pt = m.PathTracer(scene, device=local_rank, precision=precision, global_seed=0x12345678)
-    if args.pool:
-        pt.set_option("pool_paths", args.pool)
+    pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))   # 16 Mi paths in flight (6.5 GB of HBM)
     pt.set_option("stage_timing", 1)
 
     mdist = importlib.import_module("monte-carlo-ray-tracer_b200.distributed")
@@ -326,7 +325,7 @@ def run_gpu_arm(args):
             "config": {"workload": label, "paths_per_step": W * H * cam.sqrtspp ** 2,
                        "rays_per_step": rays_total / args.steps,
                        "parallelism": f"rows interleaved over {world} GPU(s), scene replicated, 1 NCCL all-gather of the f64 framebuffer/step" if world > 1 else "1 GPU",
-                       "l2": "per-step working set (path pool ~2 GB, film 50 MB) exceeds the 126 MB L2; the 3 KB scene is cache-resident by nature",
+                       "l2": "per-step working set (16 Mi-path pool ~6.5 GB, film 50 MB) exceeds the 126 MB L2; the 3 KB scene is cache-resident by nature",
                        "mode": "parity (float64, reference operation order, --fmad=false)" if args.precision == "f64" else "fast (float32)"},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
             "e2e": {"value": e2e_rays_total / e2e_wall_max / 1e6, "unit": "Mray/s",
