@@ -94,6 +94,16 @@ namespace mcrt
         return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
     }
 
+    // warp minimum of non-negative doubles (same trick, inverted)
+    MCRT_D double warpMinD(double v)
+    {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+        const unsigned mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
+        return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    }
+
     // Warp-cooperative search. Distances are always float64, as in the reference
     // (glm::distance2(data.pos(), p) on dvec3). Returns the number of results (<= k); the results
     // are left in sh.res_*; *res_max is the largest distance2 among them.
@@ -180,14 +190,19 @@ namespace mcrt
                             if (cur_max < max_d2) max_d2 = cur_max;
                         }
                     }
-                    // replace phase: one candidate at a time against the current farthest result
+                    // replace phase: candidates in ascending distance order against the current farthest
+                    // result; as soon as the nearest remaining candidate is beyond the radius all the
+                    // others are too (the outcome - the k smallest - does not depend on the order)
+                    bool pending = (ballot >> lane) & 1u;
                     while (ballot)
                     {
-                        const int src = __ffs(ballot) - 1;
-                        ballot &= ballot - 1;
-                        const double cd2 = __shfl_sync(0xFFFFFFFFu, d2, src);
+                        const double cd2 = warpMinD(pending ? d2 : 1.7976931348623157e308);
+                        if (!(cd2 <= max_d2)) break;
+                        const unsigned who = __ballot_sync(0xFFFFFFFFu, pending && d2 == cd2);
+                        const int src = __ffs(who) - 1;
+                        ballot &= ~(1u << src);
+                        if ((int)lane == src) pending = false;
                         const uint32_t cidx = (uint32_t)(base + src);
-                        if (cd2 <= max_d2)
                         {
                             // pop_push: replace the farthest of the k results (linear-octree.cpp:79)
                             double m = 0.0;
@@ -255,19 +270,16 @@ namespace mcrt
 
             if (n_frontier == 0) break;
             // pop the nearest octant: warp arg-min over the unsorted frontier
-            double best = 1.7976931348623157e308;
-            uint32_t best_slot = 0xFFFFFFFFu;
+            double mine_best = 1.7976931348623157e308;
+            uint32_t mine_slot = 0xFFFFFFFFu;
             for (uint32_t s = lane; s < n_frontier; s += 32)
             {
                 const double v = sh.fr_d2[s];
-                if (v < best || best_slot == 0xFFFFFFFFu) { best = v; best_slot = s; }
+                if (v < mine_best || mine_slot == 0xFFFFFFFFu) { mine_best = v; mine_slot = s; }
             }
-            for (int off = 16; off > 0; off >>= 1)
-            {
-                const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
-                const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, best_slot, off);
-                if (os != 0xFFFFFFFFu && (best_slot == 0xFFFFFFFFu || ob < best || (ob == best && os < best_slot))) { best = ob; best_slot = os; }
-            }
+            const double best = warpMinD(mine_best);
+            const unsigned holders = __ballot_sync(0xFFFFFFFFu, mine_slot != 0xFFFFFFFFu && mine_best == best);
+            const uint32_t best_slot = __shfl_sync(0xFFFFFFFFu, mine_slot, __ffs(holders) - 1);
             if (best > max_d2) break; // linear-octree.cpp:113
             cur = sh.fr_node[best_slot];
             __syncwarp();
