@@ -188,6 +188,22 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map,
                        const mcrt_photon_map_desc* global_map, uint32_t k_nearest,
                        uint32_t direct_visualization, uint64_t* h2d_bytes);
 
+/* Film reconstruction filter, the "film" object of a camera in the scene JSON
+ * (source/camera/film.cpp:19-59). Default (never set): box, radius 0.5, no cache. */
+enum { MCRT_FILM_BOX = 0, MCRT_FILM_MITCHELL_NETRAVALI = 1, MCRT_FILM_CATMULL_ROM = 2, MCRT_FILM_B_SPLINE = 3,
+       MCRT_FILM_HERMITE = 4, MCRT_FILM_GAUSSIAN = 5, MCRT_FILM_LANCZOS = 6 };
+typedef struct mcrt_film {
+    uint32_t filter;        /* MCRT_FILM_* */
+    uint32_t cache_size;    /* 0: evaluate the filter function, else nearest-neighbour lookup table */
+    double radius;          /* <= 0: the filter's default radius (film.cpp:32-43) */
+} mcrt_film;
+
+/* SURVEY.md §8f-4 ("next"): Film::deposit with the reference's reconstruction filters for the
+ * following renders of this context (source/camera/film.cpp:61-113, filter.hpp). With a filter other
+ * than the default box, samples splat into neighbouring pixels, so mcrt_render_rows* must then
+ * cover the whole frame (rows cannot be sharded without halo exchange). NULL restores the default. */
+int mcrt_set_film(mcrt_ctx* ctx, const mcrt_film* film);
+
 /* Parameters of the photon pass, the "photon_map" object of the scene JSON
  * (source/integrator/photon-mapper/photon-mapper.cpp:28-38). */
 typedef struct mcrt_photon_emit_params {

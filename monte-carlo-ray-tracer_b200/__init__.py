@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "mcrt_photon_upload", "mcrt_photon_emit", "mcrt_photon_download", "mcrt_octree_build_host",
     "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
-    "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option",
+    "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
 ]
 
 
@@ -83,6 +83,14 @@ class CameraRec(C.Structure):
                 ("up", C.c_double * 3), ("focal_length", C.c_double), ("sensor_width", C.c_double),
                 ("aperture_radius", C.c_double), ("focus_distance", C.c_double),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("thin_lens", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class FilmRec(C.Structure):
+    _fields_ = [("filter", C.c_uint32), ("cache_size", C.c_uint32), ("radius", C.c_double)]
+
+
+FILM_FILTERS = {"box": 0, "mitchell-netravali": 1, "catmull-rom": 2, "b-spline": 3, "hermite": 4, "gaussian": 5,
+                "lanczos": 6}
 
 
 class HitRec(C.Structure):
@@ -158,6 +166,7 @@ def lib():
         L.mcrt_knn_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.POINTER(Stats)]
         L.mcrt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.mcrt_set_film.argtypes = [C.c_void_p, C.POINTER(FilmRec)]
         if L.mcrt_abi_version() != 1:
             raise McrtError("libmcrt_b200.so ABI version mismatch")
         _lib = L
@@ -248,7 +257,8 @@ class Scene:
         """Cameras stored in the pack (the exporter writes the one the scene was opened with)."""
         cams = []
         if "camera_f64" in self.extra:
-            cams.append(Camera.from_pack_arrays(self.extra["camera_f64"], self.extra["camera_u32"]))
+            cams.append(Camera.from_pack_arrays(self.extra["camera_f64"], self.extra["camera_u32"],
+                                                self.extra.get("camera_film_u32"), self.extra.get("camera_film_f64")))
         return cams
 
     def photon_maps(self):
@@ -266,7 +276,10 @@ class Camera:
     """Camera state after the reference's Camera::Camera (camera.cpp:20-64)."""
 
     def __init__(self, eye, forward, left, up, focal_length, sensor_width, width, height,
-                 aperture_radius=-1.0, focus_distance=-1.0, thin_lens=False, sqrtspp=1):
+                 aperture_radius=-1.0, focus_distance=-1.0, thin_lens=False, sqrtspp=1, film=None):
+        """film: None (default box film) or dict(filter=name|code, radius=None, cache_size=0), the camera's
+        "film" object in the scene JSON (source/camera/film.cpp:19-59)."""
+        self.film = dict(film) if film else None
         self.rec = CameraRec()
         for name, v in (("eye", eye), ("forward", forward), ("left", left), ("up", up)):
             for i in range(3):
@@ -280,9 +293,21 @@ class Camera:
         self.sqrtspp = int(sqrtspp)
 
     @classmethod
-    def from_pack_arrays(cls, f64, u32):
+    def from_pack_arrays(cls, f64, u32, film_u32=None, film_f64=None):
+        film = None
+        if film_u32 is not None and not (int(film_u32[0]) == 0 and float(film_f64[0]) == 0.5):
+            film = dict(filter=int(film_u32[0]), cache_size=int(film_u32[1]), radius=float(film_f64[0]))
         return cls(f64[0:3], f64[3:6], f64[6:9], f64[9:12], f64[12], f64[13], u32[0], u32[1],
-                   f64[14], f64[15], bool(u32[2]), int(u32[3]))
+                   f64[14], f64[15], bool(u32[2]), int(u32[3]), film)
+
+    def film_rec(self):
+        """mcrt_film of this camera, or None for the default box film."""
+        if not self.film:
+            return None
+        f = self.film.get("filter", "box")
+        code = FILM_FILTERS[f.lower()] if isinstance(f, str) else int(f)
+        radius = self.film.get("radius")
+        return FilmRec(code, int(self.film.get("cache_size") or 0), float(radius) if radius else 0.0)
 
     @property
     def width(self):
@@ -295,7 +320,7 @@ class Camera:
     def resized(self, width, height, sqrtspp=None):
         c = Camera(self.rec.eye, self.rec.forward, self.rec.left, self.rec.up, self.rec.focal_length,
                    self.rec.sensor_width, width, height, self.rec.aperture_radius, self.rec.focus_distance,
-                   self.rec.thin_lens, self.sqrtspp if sqrtspp is None else sqrtspp)
+                   self.rec.thin_lens, self.sqrtspp if sqrtspp is None else sqrtspp, self.film)
         return c
 
 
@@ -368,8 +393,14 @@ class Integrator:
         return hits
 
     # -- Camera::sampleImage for a block of rows (box film), host output
+    def set_film(self, camera):
+        """Film of the following renders = the camera's (Camera owns its Film, camera.cpp:34-37)."""
+        rec = camera.film_rec()
+        self._check(lib().mcrt_set_film(self.ctx, C.byref(rec) if rec is not None else None))
+
     def render_rows(self, camera, y0=0, y1=None, sqrtspp=None, precision=None, out=None):
         y1 = camera.height if y1 is None else y1
+        self.set_film(camera)
         if out is None:
             out = np.zeros((y1 - y0, camera.width, 3))
         st = Stats()
@@ -382,6 +413,7 @@ class Integrator:
     # -- same, framebuffer stays in HBM (raw device pointer, float64 [rows*W*3])
     def render_rows_dev(self, camera, out_dev_ptr, y0=0, y1=None, sqrtspp=None, precision=None):
         y1 = camera.height if y1 is None else y1
+        self.set_film(camera)
         st = Stats()
         self._check(lib().mcrt_render_rows_dev(self.ctx, C.byref(camera.rec), y0, y1,
                                                camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed,
@@ -392,6 +424,7 @@ class Integrator:
 
     # -- interleaved rows y_first + k*y_step (multi-GPU sharding), framebuffer in HBM
     def render_rows_strided_dev(self, camera, out_dev_ptr, y_first, y_step, n_rows, sqrtspp=None, precision=None):
+        self.set_film(camera)
         st = Stats()
         self._check(lib().mcrt_render_rows_strided_dev(self.ctx, C.byref(camera.rec), y_first, y_step, n_rows,
                                                        camera.sqrtspp if sqrtspp is None else sqrtspp,

@@ -73,6 +73,12 @@ struct mcrt_ctx
     Counters* h_counters = nullptr; // pinned, 2 slots
     double* d_film = nullptr;
     size_t film_values = 0;
+    // reconstruction filter (mcrt_set_film); the default box film needs none of this
+    bool film_default = true;
+    mcrt_film film = {MCRT_FILM_BOX, 0u, 0.5};
+    double* d_film_wsum = nullptr;
+    size_t film_wsum_values = 0;
+    double* d_film_cache = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_poll[2] = { nullptr, nullptr };
 
     // photon maps (PhotonMapper::caustic_map / global_map) + k-NN query queues
@@ -459,6 +465,14 @@ namespace
         int rc;
         if ((rc = ensureWave(ctx, wb, waveAllocsOf<R>(ctx)))) return rc;
         if ((rc = ensureFilm(ctx, film_pixels * 3))) return rc;
+        const bool filtered = cam && !d_user_rays && !ctx->film_default && integrator != MCRT_INTERNAL_EMIT;
+        if (filtered && ctx->film_wsum_values < film_pixels)
+        {
+            if (ctx->d_film_wsum) cudaFree(ctx->d_film_wsum);
+            ctx->d_film_wsum = nullptr; ctx->film_wsum_values = 0;
+            CK(cudaMalloc((void**)&ctx->d_film_wsum, film_pixels * sizeof(double)));
+            ctx->film_wsum_values = film_pixels;
+        }
         KnnQuery<R>* knn_queue = nullptr;
         const uint32_t knn_capacity = 2u * ctx->pool_paths; // a path emits at most caustic + global per bounce
         if (integrator == MCRT_INTEGRATOR_PHOTON)
@@ -494,6 +508,17 @@ namespace
         p.counters = ctx->d_counters;
         p.sobol_bytes = ctx->d_sobol_bytes;
         p.film = ctx->d_film;
+        p.filmp.is_default_box = filtered ? 0u : 1u;
+        if (filtered)
+        {
+            p.filmp.rgb = ctx->d_film; p.filmp.wsum = ctx->d_film_wsum;
+            p.filmp.cache = ctx->film.cache_size ? ctx->d_film_cache : nullptr;
+            p.filmp.radius = ctx->film.radius;
+            p.filmp.two_inv_radius = 2.0 / ctx->film.radius;
+            p.filmp.inv_dx = ctx->film.cache_size ? (double)(ctx->film.cache_size - 1) / ctx->film.radius : 0.0;
+            p.filmp.filter = ctx->film.filter; p.filmp.cache_size = ctx->film.cache_size;
+            p.filmp.width = cam->width; p.filmp.height = cam->height;
+        }
         p.user_rays = d_user_rays; p.user_pixel = d_user_pixel; p.user_sample = d_user_sample;
         p.capacity = wb.capacity;
         p.global_seed = global_seed;
@@ -548,6 +573,7 @@ namespace
         ctx->h_counters[0] = init;
         CK(cudaMemcpyAsync(ctx->d_counters, &ctx->h_counters[0], sizeof(Counters), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ctx->d_film, 0, film_pixels * 3 * sizeof(double), s));
+        if (filtered) CK(cudaMemsetAsync(ctx->d_film_wsum, 0, film_pixels * sizeof(double), s));
         const bool sorting = ctx->sort_rays != 0;
         if (sorting)
         {
@@ -645,7 +671,8 @@ namespace
 
         if (!emitting)
         {
-            launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
+            if (filtered) launchResolveFilmWeighted(ctx->d_film, ctx->d_film_wsum, out_dev, film_pixels, grid, s);
+            else launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
             launches += 1;
         }
         CK(cudaEventRecord(ctx->ev_stop, s));
@@ -872,6 +899,11 @@ namespace
             ctx->error = "mcrt_render_rows: invalid camera / row range / sqrtspp";
             return MCRT_ERR_INVALID;
         }
+        if (!ctx->film_default && (y_first != 0 || y_step != 1 || n_rows != camera->height))
+        {
+            ctx->error = "a reconstruction filter other than the default box splats across rows: render the whole frame in one call";
+            return MCRT_ERR_UNSUPPORTED;
+        }
         const uint64_t n_pixels64 = (uint64_t)camera->width * n_rows;
         if (n_pixels64 > 0xFFFFFFFFull) { ctx->error = "row block too large"; return MCRT_ERR_INVALID; }
         const uint32_t n_pixels = (uint32_t)n_pixels64;
@@ -938,6 +970,8 @@ void mcrt_destroy(mcrt_ctx* ctx)
     if (ctx->knn_queue64) cudaFree(ctx->knn_queue64);
     if (ctx->knn_queue32) cudaFree(ctx->knn_queue32);
     if (ctx->d_film) cudaFree(ctx->d_film);
+    if (ctx->d_film_wsum) cudaFree(ctx->d_film_wsum);
+    if (ctx->d_film_cache) cudaFree(ctx->d_film_cache);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1252,6 +1286,35 @@ int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, 
     CK(cudaSetDevice(ctx->device));
     if (y1 <= y0) { ctx->error = "empty row range"; return MCRT_ERR_INVALID; }
     return renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_set_film(mcrt_ctx* ctx, const mcrt_film* film)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    mcrt_film f = {MCRT_FILM_BOX, 0u, 0.5};
+    if (film)
+    {
+        if (film->filter > MCRT_FILM_LANCZOS) { ctx->error = "mcrt_set_film: unknown filter"; return MCRT_ERR_INVALID; }
+        if (film->cache_size == 1) { ctx->error = "mcrt_set_film: cache_size must be 0 or >= 2"; return MCRT_ERR_INVALID; }
+        // default radii of Film::Film (film.cpp:32-45)
+        static const double default_radius[7] = {0.5, 2.0, 2.0, 1.39, 1.0, 1.71, 2.0};
+        f = *film;
+        if (!(f.radius > 0.0)) f.radius = default_radius[f.filter];
+    }
+    if (ctx->d_film_cache) { cudaFree(ctx->d_film_cache); ctx->d_film_cache = nullptr; }
+    if (f.cache_size)
+    {
+        // Film::filter_cache (film.cpp:50-58)
+        std::vector<double> cache(f.cache_size);
+        for (uint32_t i = 0; i < f.cache_size; i++)
+            cache[i] = filmFilterFunction(f.filter, (2.0 * (double)(int)i) / (double)(f.cache_size - 1));
+        CK(cudaMalloc((void**)&ctx->d_film_cache, cache.size() * sizeof(double)));
+        CK(cudaMemcpy(ctx->d_film_cache, cache.data(), cache.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    ctx->film = f;
+    ctx->film_default = f.filter == MCRT_FILM_BOX && f.radius == 0.5;
+    return MCRT_OK;
 }
 
 int mcrt_render_rows_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step,

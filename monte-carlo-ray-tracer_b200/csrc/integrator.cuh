@@ -22,6 +22,7 @@
 #include "bsdf.cuh"
 #include "intersect.cuh"
 #include "photon.cuh"
+#include "film.cuh"
 
 // launch-bound knobs (overridable at build time for tuning experiments)
 // (measured on B200, r1: float traversal gains 25-30 % from 64 registers / 32 warps per SM, double
@@ -215,6 +216,7 @@ namespace mcrt
         RaySort sort;           // coherence sort of the path / shadow queues (null order = disabled)
         const uint32_t* sobol_bytes; // byte-sliced Sobol matrices [6][4][256] (makeSobolByteTable)
         EmitParams<R> emit;         // photon emission pass (mcrt_photon_emit) only
+        FilmParams filmp;           // reconstruction filter (default box: only `film` is used)
     };
 
     // ------------------------------------------------------------------------------------------
@@ -249,6 +251,29 @@ namespace mcrt
     MCRT_D void filmAddV(double* film, uint32_t index, const V3<R>& v)
     {
         filmAdd(film, index, (double)v.x, (double)v.y, (double)v.z);
+    }
+
+    // image pixel of a film index (rows may be interleaved over ranks)
+    template <class R>
+    MCRT_D uint32_t pixelOfFilmIndex(const WaveParams<R>& p, uint32_t film_index)
+    {
+        const uint32_t row = film_index / p.camera.width, col = film_index - row * p.camera.width;
+        return (p.row_first + row * p.row_step) * p.camera.width + col;
+    }
+
+    // Film::deposit of one radiance contribution of sample (pixel, sample)
+    // (FILM = false: the default box film, the kernels every benchmark and parity case runs)
+    template <bool FILM, class R>
+    MCRT_D void depositRadiance(const WaveParams<R>& p, uint32_t film_index, uint32_t pixel, uint32_t sample, const V3<R>& v)
+    {
+        if constexpr (!FILM)
+        {
+            filmAddV(p.film, film_index, v);
+        }
+        else
+        {
+            filmSplatSample(p.filmp, p.global_seed, pixel, sample, (double)v.x, (double)v.y, (double)v.z);
+        }
     }
 
     // Warp-aggregated append: one atomic per warp, lanes get consecutive slots.
@@ -317,7 +342,7 @@ namespace mcrt
         }
     }
 
-    template <class R>
+    template <class R, bool FILM>
     __global__ void __launch_bounds__(256) k_generate(WaveParams<R> p, int next)
     {
         Counters* c = p.counters;
@@ -359,6 +384,7 @@ namespace mcrt
                 film_index = local;
                 SamplerState smp = SamplerState::make(p.global_seed, pixel, sample, 0u);
                 cameraRay(p.camera, p.scene.scene_ior, pixel, smp, start, direction);
+                if constexpr (FILM) filmSplatSampleWeight(p.filmp, p.global_seed, pixel, sample);
             }
             out.ray_o[slot] = V4<R>(start, p.scene.scene_ior);
             out.ray_d[slot] = V4<R>(direction, R(1));
@@ -458,7 +484,7 @@ namespace mcrt
         return mix(V3<R>(R(1), R(0.5), R(0)), V3<R>(R(0), R(0.5), R(1)), fy);
     }
 
-    template <class R, int KIND>
+    template <class R, int KIND, bool FILM>
     __global__ void __launch_bounds__(128, MCRT_SHADE_MINBLOCKS) k_shade(WaveParams<R> p, int cur)
     {
         __shared__ SobolByteTables sobol_tab;
@@ -538,7 +564,7 @@ namespace mcrt
                 if (hit.prim == NO_PRIM)
                 {
                     // path-tracer.cpp:27-30; the photon mapper adds no sky (photon-mapper.cpp:292-295)
-                    if constexpr (KIND == 0) filmAddV(p.film, film_index, skyColor(ray.direction) * throughput);
+                    if constexpr (KIND == 0) depositRadiance<FILM>(p, film_index, meta.x, meta.y, skyColor(ray.direction) * throughput);
                     alive = false;
                 }
                 else
@@ -562,14 +588,14 @@ namespace mcrt
                     {
                         if (ray.depth == 0 || ray.dirac_delta)
                         {
-                            filmAddV(p.film, film_index, m.emittance * throughput);
+                            depositRadiance<FILM>(p, film_index, meta.x, meta.y, m.emittance * throughput);
                         }
                         else if (ls_light != NO_PRIM && sc.lights[ls_light].prim == hit.prim)
                         {
                             R cos_light_theta = dot(ia.out, ia.normal);
                             R light_pdf = pow2(ia.t) / (ps.area * cos_light_theta);
                             R mis_weight = powerHeuristic(ls_bsdf_pdf, light_pdf);
-                            filmAddV(p.film, film_index, (mis_weight * m.emittance / ls_select) * throughput);
+                            depositRadiance<FILM>(p, film_index, meta.x, meta.y, (mis_weight * m.emittance / ls_select) * throughput);
                         }
                     }
 
@@ -601,7 +627,7 @@ namespace mcrt
                             knn_q.nrm_n2 = V4<R>(ia.shading_cs.c2, ia.n2);
                             knn_q.out_rf = V4<R>(ia.out, ia.Rf);
                             knn_q.weight_t = V4<R>(throughput, ia.T);
-                            knn_q.meta = make_uint4(ps.material, film_index, ia.inside ? 1u : 0u, 0u);
+                            knn_q.meta = make_uint4(ps.material, film_index, ia.inside ? 1u : 0u, meta.y);
                         }
                     }
 
@@ -750,7 +776,7 @@ namespace mcrt
                 p.shadow.d[sslot] = V4<R>(sh_d, sh_area_cos);
                 p.shadow.k[sslot] = V4<R>(sh_k, sh_select);
                 p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
-                                                  sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, 0u);
+                                                  sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, meta.y);
                 if (sorting) { p.sort.shadow_key[sslot] = skey; p.sort.shadow_rank[sslot] = srank; }
             }
 
@@ -772,7 +798,7 @@ namespace mcrt
         if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
-    template <class R>
+    template <class R, bool FILM>
     __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
@@ -793,7 +819,7 @@ namespace mcrt
                 const V4<R> sk = p.shadow.k[i];
                 R light_pdf = pow2(h.t) / sd.w;
                 R mis_weight = powerHeuristic(light_pdf, so.w);
-                filmAddV(p.film, sm.y, sk.xyz() * (mis_weight / (light_pdf * sk.w)));
+                depositRadiance<FILM>(p, sm.y, pixelOfFilmIndex(p, sm.y), sm.w, sk.xyz() * (mis_weight / (light_pdf * sk.w)));
             }
         }
         flushStats(p.counters, cnt, rays, true, overflow);
@@ -872,7 +898,7 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.
-    template <class R, int SLOTS>
+    template <class R, int SLOTS, bool FILM>
     __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK, 4) k_knn(WaveParams<R> p)
     {
         extern __shared__ __align__(16) unsigned char knn_smem[];
@@ -935,7 +961,7 @@ namespace mcrt
             {
                 V3<R> radiance = which == 0 ? R(3) * sum * inv_max_r2 * Consts<R>::INV_PI
                                             : sum / (top_d2 * Consts<R>::PI);
-                filmAddV(p.film, qr.meta.y, radiance * qr.weight_t.xyz());
+                depositRadiance<FILM>(p, qr.meta.y, pixelOfFilmIndex(p, qr.meta.y), qr.meta.w, radiance * qr.weight_t.xyz());
             }
             __syncwarp();
         }
@@ -1220,6 +1246,17 @@ namespace mcrt
     }
 
     // Film::Splat::get for the box filter: mean of the samples, clamped at 0 (film.cpp:106-113)
+    // Film::Splat::get with accumulated weights (film.cpp:106-113)
+    static __global__ void k_resolve_film_weighted(const double* film, const double* wsum, double* out, size_t n_pixels)
+    {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * n_pixels; i += (size_t)gridDim.x * blockDim.x)
+        {
+            const double w = wsum[i / 3];
+            const double v = w == 0.0 ? 0.0 : film[i] / w;
+            out[i] = (v < 0.0) ? 0.0 : v;
+        }
+    }
+
     static __global__ void k_resolve_film(const double* film, double* out, size_t n_values, double weight)
     {
         for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x)

@@ -18,6 +18,11 @@ namespace mcrt
         k_sort_scatter<<<grid, 256, 0, s>>>(key, rank, rs.bin_start, rs.block_offset, order, n_ptr);
     }
 
+    void launchResolveFilmWeighted(const double* film, const double* wsum, double* out, size_t n_pixels, int grid, cudaStream_t s)
+    {
+        k_resolve_film_weighted<<<grid, 256, 0, s>>>(film, wsum, out, n_pixels);
+    }
+
     void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s)
     {
         k_resolve_film<<<grid, 256, 0, s>>>(film, out, n_values, weight);

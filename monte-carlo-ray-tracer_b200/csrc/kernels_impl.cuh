@@ -5,7 +5,8 @@ namespace mcrt
 {
     template <> void Launch<MCRT_REAL>::generate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {
-        k_generate<MCRT_REAL><<<grid, 256, 0, s>>>(p, next);
+        if (p.filmp.is_default_box) k_generate<MCRT_REAL, false><<<grid, 256, 0, s>>>(p, next);
+        else k_generate<MCRT_REAL, true><<<grid, 256, 0, s>>>(p, next);
     }
     template <> void Launch<MCRT_REAL>::extend(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
@@ -13,11 +14,13 @@ namespace mcrt
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        k_shade<MCRT_REAL, 0><<<grid * 2, 128, 0, s>>>(p, cur);
+        if (p.filmp.is_default_box) k_shade<MCRT_REAL, 0, false><<<grid * 2, 128, 0, s>>>(p, cur);
+        else k_shade<MCRT_REAL, 0, true><<<grid * 2, 128, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shadePhoton(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        k_shade<MCRT_REAL, 1><<<grid * 2, 128, 0, s>>>(p, cur);
+        if (p.filmp.is_default_box) k_shade<MCRT_REAL, 1, false><<<grid * 2, 128, 0, s>>>(p, cur);
+        else k_shade<MCRT_REAL, 1, true><<<grid * 2, 128, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::knn(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
@@ -25,18 +28,25 @@ namespace mcrt
         const size_t smem = knnSharedBytes(p.pm.k_nearest);
         // the photon maps hold at least k photons in every render that matters; if a map is smaller the
         // search clamps k itself and the register slots are simply not all used
+        if (!p.filmp.is_default_box)
+        {
+            // filtered film: the rare configuration, one generic instantiation
+            k_knn<MCRT_REAL, 0, true><<<g, b, smem, s>>>(p);
+            return;
+        }
         switch (knnSlotsFor(p.pm.k_nearest))
         {
-            case 1: k_knn<MCRT_REAL, 1><<<g, b, smem, s>>>(p); break;
-            case 2: k_knn<MCRT_REAL, 2><<<g, b, smem, s>>>(p); break;
-            case 4: k_knn<MCRT_REAL, 4><<<g, b, smem, s>>>(p); break;
-            case 8: k_knn<MCRT_REAL, 8><<<g, b, smem, s>>>(p); break;
-            default: k_knn<MCRT_REAL, 0><<<g, b, smem, s>>>(p); break;
+            case 1: k_knn<MCRT_REAL, 1, false><<<g, b, smem, s>>>(p); break;
+            case 2: k_knn<MCRT_REAL, 2, false><<<g, b, smem, s>>>(p); break;
+            case 4: k_knn<MCRT_REAL, 4, false><<<g, b, smem, s>>>(p); break;
+            case 8: k_knn<MCRT_REAL, 8, false><<<g, b, smem, s>>>(p); break;
+            default: k_knn<MCRT_REAL, 0, false><<<g, b, smem, s>>>(p); break;
         }
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
-        k_shadow<MCRT_REAL><<<grid, 256, 0, s>>>(p);
+        if (p.filmp.is_default_box) k_shadow<MCRT_REAL, false><<<grid, 256, 0, s>>>(p);
+        else k_shadow<MCRT_REAL, true><<<grid, 256, 0, s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {

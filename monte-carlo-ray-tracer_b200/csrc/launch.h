@@ -24,6 +24,7 @@ namespace mcrt
     void launchSortScan(uint32_t* hist, const RaySort& rs, cudaStream_t s);
     void launchSortScatter(const uint32_t* key, const uint32_t* rank, const RaySort& rs, uint32_t* order,
                            const uint32_t* n_ptr, int grid, cudaStream_t s);
+    void launchResolveFilmWeighted(const double* film, const double* wsum, double* out, size_t n_pixels, int grid, cudaStream_t s);
     void launchResolveFilm(const double* film, double* out, size_t n_values, double weight, int grid, cudaStream_t s);
     void launchKnnUser(const DevicePhotonMap& map, uint32_t k, const double* points, size_t n, uint32_t* out_index,
                        double* out_d2, uint32_t* out_count, uint32_t* overflow_flag, int grid, cudaStream_t s);

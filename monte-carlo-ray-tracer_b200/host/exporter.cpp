@@ -11,6 +11,7 @@
 #include "material/material.hpp"
 #include "material/fresnel.hpp"
 #include "camera/camera.hpp"
+#include "camera/filter.hpp"
 #include "integrator/photon-mapper/photon-mapper.hpp"
 
 namespace mcrt_host
@@ -197,6 +198,27 @@ namespace mcrt_host
         return o;
     }
 
+    mcrt_film flattenFilm(const Camera& c)
+    {
+        // Film keeps its filter as a std::function built from a plain function (film.cpp:25-45);
+        // the target's address names it.
+        typedef double (*Fn)(double);
+        const Fn* target = c.film.filter_function.target<Fn>();
+        if (!target) throw std::runtime_error("flattenFilm: unknown film filter");
+        mcrt_film f;
+        if (*target == static_cast<Fn>(Filter::box)) f.filter = MCRT_FILM_BOX;
+        else if (*target == static_cast<Fn>(Filter::MitchellNetravali<>)) f.filter = MCRT_FILM_MITCHELL_NETRAVALI;
+        else if (*target == static_cast<Fn>(Filter::CatmullRom)) f.filter = MCRT_FILM_CATMULL_ROM;
+        else if (*target == static_cast<Fn>(Filter::BSpline)) f.filter = MCRT_FILM_B_SPLINE;
+        else if (*target == static_cast<Fn>(Filter::Hermite)) f.filter = MCRT_FILM_HERMITE;
+        else if (*target == static_cast<Fn>(Filter::Gaussian)) f.filter = MCRT_FILM_GAUSSIAN;
+        else if (*target == static_cast<Fn>(Filter::Lanczos)) f.filter = MCRT_FILM_LANCZOS;
+        else throw std::runtime_error("flattenFilm: unknown film filter");
+        f.cache_size = (uint32_t)c.film.filter_cache.size();
+        f.radius = c.film.radius;
+        return f;
+    }
+
     void flattenPhotonMap(const PhotonMapper& pm, int which, FlatPhotonMap& out)
     {
         out = FlatPhotonMap();
@@ -336,6 +358,12 @@ namespace mcrt_host
         d.push_back(c.aperture_radius); d.push_back(c.focus_distance);
         w.addScalars(prefix + "_f64", d);
         w.addScalarsU32(prefix + "_u32", { c.width, c.height, c.thin_lens, sqrtspp });
+    }
+
+    void addFilmToPack(PackWriter& w, const std::string& prefix, const mcrt_film& f)
+    {
+        w.addScalarsU32(prefix + "_film_u32", { f.filter, f.cache_size });
+        w.addScalars(prefix + "_film_f64", { f.radius });
     }
 
     void addPhotonMapToPack(PackWriter& w, const std::string& prefix, const FlatPhotonMap& m)

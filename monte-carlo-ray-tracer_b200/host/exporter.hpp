@@ -57,6 +57,8 @@ namespace mcrt_host
 
     void flattenScene(const Scene& scene, FlatScene& out);
     mcrt_camera flattenCamera(const Camera& camera);
+    // the camera's Film (filter, radius, cache size; source/camera/film.cpp:19-59)
+    mcrt_film flattenFilm(const Camera& camera);
     // which: 0 caustic_map, 1 global_map
     void flattenPhotonMap(const PhotonMapper& pm, int which, FlatPhotonMap& out);
     void photonMapParams(const PhotonMapper& pm, uint32_t& k_nearest, uint32_t& direct_visualization);
@@ -83,5 +85,6 @@ namespace mcrt_host
 
     void addSceneToPack(PackWriter& w, const FlatScene& s);
     void addCameraToPack(PackWriter& w, const std::string& prefix, const mcrt_camera& c, uint32_t sqrtspp);
+    void addFilmToPack(PackWriter& w, const std::string& prefix, const mcrt_film& f);
     void addPhotonMapToPack(PackWriter& w, const std::string& prefix, const FlatPhotonMap& m);
 }

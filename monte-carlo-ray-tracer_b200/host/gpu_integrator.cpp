@@ -51,12 +51,10 @@ namespace mcrt_host
 
     std::vector<double> GpuRenderer::renderRows(const Camera& camera, uint32_t y0, uint32_t y1)
     {
-        // default film only: Filter::box with radius 0.5 deposits each sample into exactly one
-        // pixel with weight 1 (film.cpp:13-17,61-79)
-        if (camera.film.radius != 0.5 || !camera.film.filter_cache.empty())
-        {
-            throw std::runtime_error("GpuRenderer: only the default box film is on the GPU path");
-        }
+        // the camera's reconstruction filter; anything but the default box needs the whole frame
+        // in one call (the ABI reports MCRT_ERR_UNSUPPORTED otherwise)
+        const mcrt_film film = flattenFilm(camera);
+        check(mcrt_set_film(ctx_, &film), "mcrt_set_film");
         mcrt_camera cam = flattenCamera(camera);
         std::vector<double> out((size_t)cam.width * (y1 - y0) * 3);
         check(mcrt_render_rows(ctx_, &cam, y0, y1, (uint32_t)camera.sqrtspp, global_seed_, integrator_kind_,

@@ -757,4 +757,89 @@ void oracle_render_rows(void* h, const mcrt_camera* cam, uint32_t y0, uint32_t y
     if (rays) *rays = count;
 }
 
+// Film with a reconstruction filter (film.cpp:19-113, filter.hpp:8-66), whole frame. `film` is the
+// camera's "film" object after Film::Film resolved the default radius.
+namespace
+{
+    double mitchell(double B, double Cc, double x) // filter.hpp:15-38
+    {
+        const double k = 6.0 / (6.0 - 2.0 * B);
+        if (x < 1.0)
+        {
+            const double a = k * (12.0 - 9.0 * B - 6.0 * Cc) / 6.0;
+            const double b = k * (-18.0 + 12.0 * B + 6.0 * Cc) / 6.0;
+            const double d = k * (6.0 - 2.0 * B) / 6.0;
+            return d + (b + a * x) * x * x;
+        }
+        const double a = k * (-B - 6.0 * Cc) / 6.0;
+        const double b = k * (6.0 * B + 30.0 * Cc) / 6.0;
+        const double c = k * (-12.0 * B - 48.0 * Cc) / 6.0;
+        const double d = k * (8.0 * B + 24.0 * Cc) / 6.0;
+        return d + (c + (b + a * x) * x) * x;
+    }
+
+    double filterFunction(uint32_t filter, double x) // film.cpp:32-45
+    {
+        switch (filter)
+        {
+            case MCRT_FILM_MITCHELL_NETRAVALI: return mitchell(1.0 / 3.0, 1.0 / 3.0, x);
+            case MCRT_FILM_CATMULL_ROM: return mitchell(0.0, 0.5, x);
+            case MCRT_FILM_B_SPLINE: return mitchell(1.0, 0.0, x);
+            case MCRT_FILM_HERMITE: return mitchell(0.0, 0.0, x * 0.5);
+            case MCRT_FILM_GAUSSIAN: return std::exp(-2.0 * x * x) - std::exp(-2.0 * 2.0 * 2.0);
+            case MCRT_FILM_LANCZOS:
+                if (x == 0.0) return 1.0;
+                return 2.0 * std::sin(PI * x) * std::sin(PI * x / 2.0) / (PI * PI * x * x);
+            default: return 1.0;
+        }
+    }
+}
+
+void oracle_render_film(void* h, const mcrt_camera* cam, const mcrt_film* film, uint32_t sqrtspp, uint32_t seed, double* out)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    Sampler smp(seed);
+    const uint32_t spp = sqrtspp * sqrtspp;
+    const int64_t W = cam->width, H = cam->height;
+    const double radius = film->radius;
+    std::vector<double> cache(film->cache_size);
+    for (uint32_t i = 0; i < film->cache_size; i++) cache[i] = filterFunction(film->filter, (2.0 * (int)i) / (film->cache_size - 1));
+    const double inv_dx = film->cache_size ? (film->cache_size - 1) / radius : 0.0, two_inv_radius = 2.0 / radius;
+    auto filter = [&](double x)
+    {
+        if (cache.empty()) return filterFunction(film->filter, two_inv_radius * std::abs(x));
+        return cache[static_cast<size_t>(inv_dx * std::abs(x) + 0.5)];
+    };
+    std::vector<double> rgb((size_t)W * H * 3, 0.0), wsum((size_t)W * H, 0.0);
+    for (uint32_t pixel = 0; pixel < (uint32_t)(W * H); pixel++)
+    {
+        smp.initiate(pixel);
+        for (uint32_t i = 0; i < spp; i++)
+        {
+            smp.setIndex(i);
+            const double px = (double)(pixel % W) + smp.get(PIXEL), py = (double)(pixel / W) + smp.get(PIXEL + 1);
+            D3 v = sampleRay(s, cameraRay(*cam, s.d.scene_ior, pixel, smp), smp, nullptr);
+            const int64_t x0 = std::max((int64_t)(px + 0.5 - radius), (int64_t)0), y0 = std::max((int64_t)(py + 0.5 - radius), (int64_t)0);
+            const int64_t x1 = std::min((int64_t)(px - 0.5 + radius), W - 1), y1 = std::min((int64_t)(py - 0.5 + radius), H - 1);
+            for (int64_t y = y0; y <= y1; y++)
+            {
+                const double wy = filter(y + 0.5 - py);
+                for (int64_t x = x0; x <= x1; x++)
+                {
+                    const double w = wy * filter(x + 0.5 - px);
+                    double* o = &rgb[(size_t)(y * W + x) * 3];
+                    o[0] += v.x * w; o[1] += v.y * w; o[2] += v.z * w;
+                    wsum[(size_t)(y * W + x)] += w;
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < (size_t)W * H; i++)
+        for (int k = 0; k < 3; k++)
+        {
+            const double v = wsum[i] == 0.0 ? 0.0 : rgb[3 * i + k] / wsum[i];
+            out[3 * i + k] = v < 0.0 ? 0.0 : v;
+        }
+}
+
 } // extern "C"

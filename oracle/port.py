@@ -27,6 +27,7 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_render_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -73,6 +74,16 @@ class PortScene:
         pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
         out = np.zeros((len(rays), 3))
         lib().oracle_sample_rays(self.h, _p(rays), _p(pixel), _p(sample), len(rays), seed, _p(out))
+        return out
+
+    def render_film(self, camera, sqrtspp, seed):
+        """Whole frame through Film::deposit with the camera's reconstruction filter."""
+        rec = camera.film_rec()
+        default_radius = [0.5, 2.0, 2.0, 1.39, 1.0, 1.71, 2.0]   # film.cpp:32-45
+        if rec.radius <= 0.0:
+            rec.radius = default_radius[rec.filter]
+        out = np.zeros((camera.height, camera.width, 3))
+        lib().oracle_render_film(self.h, C.addressof(camera.rec), C.addressof(rec), sqrtspp, seed, _p(out))
         return out
 
     def render_rows(self, camera, y0, y1, sqrtspp, seed):

@@ -148,7 +148,7 @@ extern "C"
 
 // overrides_json keys (all optional): width, height, sqrtspp, bvh_type ("octree"|"binary_sah"|
 // "quaternary_sah"|"none"), bins_per_axis, emissions, caustic_factor, k_nearest_photons,
-// max_photons_per_octree_leaf, num_render_threads (used by the photon pass).
+// max_photons_per_octree_leaf, num_render_threads (used by the photon pass), film (the camera's "film" object).
 void* ref_open(const char* scenes_dir, const char* scene_file, const char* overrides_json,
                int camera_idx, int photon_map, char* err, size_t errlen)
 {
@@ -169,6 +169,7 @@ void* ref_open(const char* scenes_dir, const char* scene_file, const char* overr
         if (o.contains("width")) cam["image"]["width"] = o["width"];
         if (o.contains("height")) cam["image"]["height"] = o["height"];
         if (o.contains("sqrtspp")) cam["sqrtspp"] = o["sqrtspp"];
+        if (o.contains("film")) cam["film"] = o["film"];   // {"filter": ..., "radius": ..., "cache_size": ...}
         if (o.contains("bvh_type"))
         {
             std::string t = o["bvh_type"];
@@ -251,7 +252,12 @@ int ref_render(void* handle, int threads, uint32_t y0, uint32_t y1, double* out_
     if (y0 >= y1) return -1;
     if (threads < 1) threads = (int)std::thread::hardware_concurrency();
 
-    c.film = Film(W, H);
+    {
+        // fresh accumulators, same filter as Camera::Camera chose (camera.cpp:34-37)
+        const auto& cj = h->scene_json.at("cameras").at(h->camera_idx);
+        if (cj.find("film") != cj.end()) c.film = Film(W, H, cj.at("film"));
+        else c.film = Film(W, H);
+    }
 
     struct Bucket { size_t x0, y0, x1, y1; };
     std::vector<Bucket> buckets;
@@ -426,6 +432,7 @@ int ref_export_pack(void* handle, const char* path)
     mcrt_host::PackWriter w;
     mcrt_host::addSceneToPack(w, f);
     mcrt_host::addCameraToPack(w, "camera", mcrt_host::flattenCamera(*h->camera), (uint32_t)h->camera->sqrtspp);
+    mcrt_host::addFilmToPack(w, "camera", mcrt_host::flattenFilm(*h->camera));
     mcrt_host::FlatPhotonMap caustic, global;
     if (auto* pm = dynamic_cast<PhotonMapper*>(h->camera->integrator.get()))
     {

@@ -12,7 +12,8 @@ them) and an .npz with reference outputs at the pinned seed:
     tr_rays/tr_t/tr_prim/tr_uv/tr_interp
                  Scene::intersect on camera rays + random rays through the scene bounds
     total_rays/shadow_rays   Scene::intersect call counts of the full render
-plus sampler_kat.npz (Sampler streams) and bsdf_kat.npz (Fresnel / GGX values).
+plus sampler_kat.npz (Sampler streams), bsdf_kat.npz (Fresnel / GGX values) and film_kat.npz
+(Film::deposit / Film::scan with every reconstruction filter: full renders of one scene).
 """
 import os
 import sys
@@ -105,6 +106,52 @@ def make_case(cid, scene_file, overrides, photon_map, rng):
     s.close()
 
 
+# name -> the camera's "film" object (source/camera/film.cpp:19-59)
+FILMS = {
+    "mitchell": dict(filter="mitchell-netravali"),
+    "catmull_rom": dict(filter="catmull-rom"),
+    "b_spline": dict(filter="b-spline"),
+    "hermite": dict(filter="hermite"),
+    "gaussian_cached": dict(filter="gaussian", cache_size=256),
+    "lanczos_r3": dict(filter="lanczos", radius=3.0),
+    "lanczos_cached": dict(filter="Lanczos", radius=2.5, cache_size=64),
+    "box_r1p5": dict(filter="box", radius=1.5),
+    "box_default_cached": dict(filter="box", cache_size=16),
+}
+
+
+def make_film_kat():
+    import json
+    out = {}
+    for name, film in FILMS.items():
+        ref.set_seed(SEED)
+        s = ref.RefScene("hexagon_room.json", dict(width=64, height=48, sqrtspp=2, bvh_type="quaternary_sah", film=film))
+        if name == "mitchell":
+            s.export_pack(os.path.join(HERE, "film_hexagon_room_64.mcrtpack"))
+        image, _, _, _ = s.render(threads=1)
+        out["image_" + name] = image
+        print(f"film_kat {name}: mean={image.mean():.6f} min={image.min():.3e}")
+        s.close()
+    # photon-mapped render through a filtered film: same scene, overrides and (single-threaded, seeded)
+    # photon pass as pm_hexagon_room_64, whose pack holds the photon maps
+    ref.set_seed(SEED)
+    _, pm_over, _ = CASES["pm_hexagon_room_64"]
+    s = ref.RefScene("hexagon_room.json", dict(pm_over, film=FILMS["mitchell"]), photon_map=True)
+    tmp = os.path.join(HERE, "_pm_film_tmp.mcrtpack")
+    s.export_pack(tmp)
+    import importlib
+    mcrt = importlib.import_module("monte-carlo-ray-tracer_b200")
+    a, b = mcrt.read_pack(tmp), mcrt.read_pack(os.path.join(HERE, "pm_hexagon_room_64.mcrtpack"))
+    os.remove(tmp)
+    for key in b:
+        assert np.array_equal(a[key], b[key]), key     # same scene, same photon maps
+    image, _, _, _ = s.render(threads=1)
+    out["image_pm_mitchell"] = image
+    print(f"film_kat pm_mitchell: mean={image.mean():.6f}")
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "film_kat.npz"), seed=np.uint32(SEED), films=json.dumps(FILMS), **out)
+
+
 def make_sampler_kat(rng):
     ref.set_seed(SEED)
     n = 8192
@@ -162,3 +209,5 @@ if __name__ == "__main__":
         make_sampler_kat(rng)
     if not only or "bsdf_kat" in only:
         make_bsdf_kat(rng)
+    if not only or "film_kat" in only:
+        make_film_kat()

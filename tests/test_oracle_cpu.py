@@ -69,3 +69,27 @@ def test_image_config1_rows(scenes):
     cam = scene.cameras()[0]
     img, _ = ps.render_rows(cam, 96, 160, cam.sqrtspp, int(g["seed"]))
     assert np.abs(img - g["image"][96:160]).max() <= 1e-12 * max(1.0, np.abs(g["image"]).max())
+
+
+def _film_cases():
+    import json
+    k = np.load(os.path.join(GOLDEN, "film_kat.npz"))
+    return k, json.loads(str(k["films"]))
+
+
+@pytest.mark.parametrize("name", ["mitchell", "catmull_rom", "b_spline", "hermite", "gaussian_cached", "lanczos_r3",
+                                  "lanczos_cached", "box_r1p5", "box_default_cached"])
+def test_film_filters(name, mcrt):
+    # Film::deposit / Film::scan with the reference's reconstruction filters (film.cpp:61-113)
+    k, films = _film_cases()
+    scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, "film_hexagon_room_64.mcrtpack"))
+    cam = scene.cameras()[0]
+    assert cam.film is not None and cam.film["filter"] == mcrt.FILM_FILTERS["mitchell-netravali"]   # from the pack
+    cam.film = films[name]
+    ps = port.PortScene(scene)
+    try:
+        img = ps.render_film(cam, cam.sqrtspp, int(k["seed"]))
+    finally:
+        ps.close()
+    ref = k["image_" + name]
+    assert np.abs(img - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
