@@ -237,6 +237,33 @@ int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photon
                            const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out);
 void mcrt_octree_free_host(void* handle);
 
+/* SURVEY.md §8f-2 ("next"): BVH construction on the GPU. Replaces BVH::BVH (source/bvh/bvh.cpp:13-78):
+ * the binned-SAH builders recursiveBuildBinarySAH / recursiveBuildQuaternarySAH (bvh.cpp:165-432),
+ * the octree-derived hierarchy (bvh.cpp:130-163, octree.cpp:34-81), arbitrarySplit and compact
+ * (bvh.cpp:434-474). The result is the reference's tree node for node (same boxes, same
+ * depth-first order, same ordered_surfaces), because every decision of those builders depends
+ * only on counts and min/max unions.
+ *   prim_bounds   [n_prims][6] = Surface::Base::BB() {min.xyz, max.xyz} in Scene::surfaces order
+ *   scene_bounds  Scene::BB() (the root box, bvh.cpp:20)
+ *   type          the "bvh" object's "type" (bvh.cpp:24-56), bins_per_axis its "bins_per_axis"
+ *                 (<= 0: the reference's default, 16 binary / 8 quaternary)
+ * *out points into memory owned by *handle (release with mcrt_bvh_free): node arrays in the layout
+ * mcrt_scene_desc takes, and prim_order[i] = index into the caller's primitives of ordered
+ * primitive i. gpu_ms (optional): device time of the build. */
+enum { MCRT_BVH_OCTREE = 0, MCRT_BVH_BINARY_SAH = 1, MCRT_BVH_QUATERNARY_SAH = 2 };
+typedef struct mcrt_bvh_desc {
+    uint32_t n_nodes, n_prims;
+    const double* node_bounds;            /* [n_nodes][6] */
+    const uint32_t* node_first_prim;      /* LinearNode::start_surface */
+    const uint32_t* node_prim_count;      /* LinearNode::num_surfaces (0 = inner node) */
+    const uint32_t* node_next_sibling;    /* LinearNode::next_sibling */
+    const uint32_t* prim_order;           /* [n_prims] */
+    uint32_t build_rounds, kernel_launches;
+} mcrt_bvh_desc;
+int mcrt_bvh_build(mcrt_ctx* ctx, const double* prim_bounds, uint32_t n_prims, const double* scene_bounds6, int type,
+                   int bins_per_axis, void** handle, mcrt_bvh_desc* out, double* gpu_ms);
+void mcrt_bvh_free(void* handle);
+
 /* Replaces Camera::sampleImage (camera.cpp:101-145) for rows [y0, y1) with the default box
  * film (film.cpp:13-17): out_rgb[(y-y0)*W+x][3] = mean over sqrtspp² samples of
  * Integrator::sampleRay, clamped at 0 (film.cpp:112). Sample s of pixel p uses

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
+    "mcrt_bvh_build", "mcrt_bvh_free",
 ]
 
 
@@ -107,6 +108,15 @@ class PhotonMapDesc(C.Structure):
                 ("n_photons", C.c_uint64), ("photons", C.c_void_p)]
 
 
+class BvhDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_prims", C.c_uint32), ("node_bounds", C.c_void_p),
+                ("node_first_prim", C.c_void_p), ("node_prim_count", C.c_void_p), ("node_next_sibling", C.c_void_p),
+                ("prim_order", C.c_void_p), ("build_rounds", C.c_uint32), ("kernel_launches", C.c_uint32)]
+
+
+BVH_TYPES = {"octree": 0, "binary_sah": 1, "quaternary_sah": 2}
+
+
 class PhotonEmitParams(C.Structure):
     _fields_ = [("emissions", C.c_uint64), ("caustic_factor", C.c_double), ("max_photons_per_octree_leaf", C.c_uint32),
                 ("k_nearest_photons", C.c_uint32), ("direct_visualization", C.c_uint32), ("global_seed", C.c_uint32),
@@ -167,6 +177,10 @@ def lib():
                                       C.c_void_p, C.POINTER(Stats)]
         L.mcrt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.mcrt_set_film.argtypes = [C.c_void_p, C.POINTER(FilmRec)]
+        L.mcrt_bvh_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p), C.POINTER(BvhDesc), C.POINTER(C.c_double)]
+        L.mcrt_bvh_free.argtypes = [C.c_void_p]
+        L.mcrt_bvh_free.restype = None
         if L.mcrt_abi_version() != 1:
             raise McrtError("libmcrt_b200.so ABI version mismatch")
         _lib = L
@@ -252,6 +266,51 @@ class Scene:
             setattr(d, k, _ptr(a[k]))
         d.scene_ior = self.ior
         return d
+
+    # -- inputs / outputs of BVH::BVH (mcrt_bvh_build)
+    def prim_bounds(self):
+        """Surface::Base::BB() of every primitive, [n_prims, 6] (triangle.cpp:115-122, sphere.cpp:56-62,
+        quadric BB_)."""
+        a = self.a
+        out = np.zeros((self.n_prims, 6))
+        t, i = a["prim_type"], a["prim_index"]
+        tri = t == PRIM_TRIANGLE
+        if tri.any():
+            v = np.stack([a["tri_v0"].reshape(-1, 3), a["tri_v1"].reshape(-1, 3), a["tri_v2"].reshape(-1, 3)])[:, i[tri]]
+            out[tri, :3] = v.min(axis=0); out[tri, 3:] = v.max(axis=0)
+        sph = t == PRIM_SPHERE
+        if sph.any():
+            s = a["sphere_origin_radius"].reshape(-1, 4)[i[sph]]
+            out[sph, :3] = s[:, :3] - s[:, 3:4]; out[sph, 3:] = s[:, :3] + s[:, 3:4]
+        quad = t == PRIM_QUADRIC
+        if quad.any():
+            out[quad] = a["quadric_bounds"].reshape(-1, 6)[i[quad]]
+        return out
+
+    def reordered(self, order, bvh=None):
+        """Scene whose primitive k is this scene's primitive order[k]; node arrays from `bvh` (a dict as
+        returned by bvh_build) or none (Scene::intersect then scans all primitives, scene.cpp:159-171)."""
+        order = np.asarray(order, dtype=np.int64)
+        arrays = dict(self.a, **self.extra)
+        arrays["scene_ior"] = np.array([self.ior])
+        for k in ("prim_type", "prim_index", "prim_material", "prim_area"):
+            arrays[k] = self.a[k][order]
+        inverse = np.empty(len(order), dtype=np.int64)
+        inverse[order] = np.arange(len(order))
+        arrays["light_prim"] = inverse[self.a["light_prim"]].astype(np.uint32)
+        if "prim_original" in arrays:
+            arrays["prim_original"] = arrays["prim_original"][order]
+        for k, dt in (("node_bounds", np.float64), ("node_first_prim", np.uint32), ("node_prim_count", np.uint32),
+                      ("node_next_sibling", np.uint32)):
+            arrays[k] = np.ascontiguousarray(bvh[k], dtype=dt).reshape(-1) if bvh is not None else np.zeros(0, dtype=dt)
+        return Scene(arrays)
+
+    def unbuilt(self):
+        """The scene as BVH::BVH receives it: primitives in Scene::surfaces order, no hierarchy."""
+        return self.reordered(np.argsort(self.extra["prim_original"], kind="stable"))
+
+    def with_bvh(self, bvh):
+        return self.reordered(bvh["prim_order"], bvh)
 
     def cameras(self):
         """Cameras stored in the pack (the exporter writes the one the scene was opened with)."""
@@ -544,6 +603,37 @@ def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds):
     out = _map_arrays(d)
     lib().mcrt_octree_free_host(h)
     return out
+
+
+def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis=0, device=0):
+    """mcrt_bvh_build: the reference's BVH (bvh.cpp:13-78) over primitive boxes, built on the GPU.
+    -> dict(node_bounds [n,6], node_first_prim, node_prim_count, node_next_sibling, prim_order, gpu_ms, rounds)."""
+    prim_bounds = np.ascontiguousarray(prim_bounds, dtype=np.float64).reshape(-1, 6)
+    scene_bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64).reshape(6)
+    code = BVH_TYPES[bvh_type.lower()] if isinstance(bvh_type, str) else int(bvh_type)
+    ctx = C.c_void_p()
+    rc = lib().mcrt_init(device, C.byref(ctx))
+    if rc:
+        raise McrtError(f"mcrt_init({device}) failed: {rc} (no CUDA device? there is no CPU fallback)")
+    try:
+        h, d, ms = C.c_void_p(), BvhDesc(), C.c_double()
+        rc = lib().mcrt_bvh_build(ctx, _ptr(prim_bounds), len(prim_bounds), _ptr(scene_bounds), code, int(bins_per_axis),
+                                  C.byref(h), C.byref(d), C.byref(ms))
+        if rc:
+            raise McrtError(f"mcrt_bvh_build failed ({rc}): {lib().mcrt_last_error(ctx).decode()}")
+
+        def arr(ptr, count, dtype):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype).copy()
+        out = dict(node_bounds=arr(d.node_bounds, d.n_nodes * 6, np.float64).reshape(-1, 6),
+                   node_first_prim=arr(d.node_first_prim, d.n_nodes, np.uint32),
+                   node_prim_count=arr(d.node_prim_count, d.n_nodes, np.uint32),
+                   node_next_sibling=arr(d.node_next_sibling, d.n_nodes, np.uint32),
+                   prim_order=arr(d.prim_order, d.n_prims, np.uint32),
+                   gpu_ms=ms.value, rounds=int(d.build_rounds), kernel_launches=int(d.kernel_launches))
+        lib().mcrt_bvh_free(h)
+        return out
+    finally:
+        lib().mcrt_destroy(ctx)
 
 
 def shard_rows(height, rank, world_size):

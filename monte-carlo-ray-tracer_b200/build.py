@@ -18,6 +18,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("kernels_f64.cu", ["--fmad=false"]),
     ("kernels_f32.cu", []),
+    ("bvh_build.cu", ["--fmad=false"]),
     ("abi.cu", []),
 ]
 

@@ -12,6 +12,7 @@
 
 #include "mcrt_abi.h"
 #include "launch.h"
+#include "bvh_build.h"
 
 using namespace mcrt;
 
@@ -1286,6 +1287,35 @@ int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, 
     CK(cudaSetDevice(ctx->device));
     if (y1 <= y0) { ctx->error = "empty row range"; return MCRT_ERR_INVALID; }
     return renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_bvh_build(mcrt_ctx* ctx, const double* prim_bounds, uint32_t n_prims, const double* scene_bounds6, int type,
+                   int bins_per_axis, void** handle, mcrt_bvh_desc* out, double* gpu_ms)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!handle || !out) { ctx->error = "mcrt_bvh_build: null output"; return MCRT_ERR_INVALID; }
+    *handle = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    BvhBuildResult* r = new BvhBuildResult();
+    const int rc = buildBvhOnDevice(prim_bounds, n_prims, scene_bounds6, type, bins_per_axis, ctx->sm_count, ctx->stream, *r, ctx->error);
+    if (rc != MCRT_OK) { delete r; return rc; }
+    out->n_nodes = (uint32_t)r->node_first_prim.size();
+    out->n_prims = n_prims;
+    out->node_bounds = r->node_bounds.data();
+    out->node_first_prim = r->node_first_prim.data();
+    out->node_prim_count = r->node_prim_count.data();
+    out->node_next_sibling = r->node_next_sibling.data();
+    out->prim_order = r->prim_order.data();
+    out->build_rounds = r->iterations;
+    out->kernel_launches = r->kernel_launches;
+    if (gpu_ms) *gpu_ms = r->gpu_ms;
+    *handle = r;
+    return MCRT_OK;
+}
+
+void mcrt_bvh_free(void* handle)
+{
+    delete static_cast<BvhBuildResult*>(handle);
 }
 
 int mcrt_set_film(mcrt_ctx* ctx, const mcrt_film* film)

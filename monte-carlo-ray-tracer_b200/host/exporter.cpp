@@ -91,10 +91,18 @@ namespace mcrt_host
             return idx;
         };
 
+        std::unordered_map<const Surface::Base*, uint32_t> original_index;
+        for (size_t i = 0; i < scene.surfaces.size(); i++) original_index.emplace(scene.surfaces[i].get(), (uint32_t)i);
+        {
+            const BoundingBox bb = scene.BB();
+            for (int c = 0; c < 3; c++) { out.scene_bounds[c] = bb.min[c]; out.scene_bounds[3 + c] = bb.max[c]; }
+        }
+
         for (const auto& sp : *ordered)
         {
             const Surface::Base* s = sp.get();
             if (!s) throw std::runtime_error("exporter: null surface in ordered list");
+            out.prim_original.push_back(original_index.at(s));
             uint32_t prim = (uint32_t)out.prim_type.size();
             out.prim_of_surface.emplace(s, prim);
             out.prim_material.push_back(materialOf(s->material));
@@ -345,6 +353,8 @@ namespace mcrt_host
         w.add("light_prim", 1, s.light_prim);
         w.add("light_cdf", 5, s.light_cdf);
         w.addScalars("scene_ior", { s.scene_ior });
+        w.add("prim_original", 1, s.prim_original);
+        w.addScalars("scene_bounds", std::vector<double>(s.scene_bounds, s.scene_bounds + 6));
     }
 
     void addCameraToPack(PackWriter& w, const std::string& prefix, const mcrt_camera& c, uint32_t sqrtspp)

@@ -36,6 +36,10 @@ namespace mcrt_host
         std::vector<uint32_t> light_prim;
         std::vector<double> light_cdf;
         double scene_ior = 1.0;
+        // inputs of BVH::BVH (bvh.cpp:13-15), for mcrt_bvh_build: position of every ordered primitive
+        // in Scene::surfaces, and Scene::BB()
+        std::vector<uint32_t> prim_original;
+        double scene_bounds[6] = {0, 0, 0, 0, 0, 0};
 
         // ordered-primitive index of every Surface::Base object (pointer identity is what the
         // reference compares in integrator.cpp:70,101)

@@ -44,6 +44,9 @@ def lib():
         L.ref_sampler_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.ref_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_export_pack.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_bvh_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+        L.ref_bvh_arrays.argtypes = [C.c_void_p] * 6
+        L.ref_prim_bounds.argtypes = [C.c_void_p] * 3
         L.ref_fresnel_dielectric.restype = C.c_double
         L.ref_fresnel_dielectric.argtypes = [C.c_double] * 3
         L.ref_fresnel_conductor.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -130,6 +133,25 @@ class RefScene:
         if rc:
             raise RuntimeError("ref_knn: scene was not opened with photon_map=True")
         return ph, d2, cnt
+
+    def prim_bounds(self):
+        """Surface::BB() of Scene::surfaces in order, and Scene::BB()."""
+        b = np.zeros((self.n_prims, 6)); sb = np.zeros(6)
+        lib().ref_prim_bounds(self.h, _p(b), _p(sb))
+        return b, sb
+
+    def build_bvh(self, bvh_type, bins=0):
+        """BVH::BVH on this scene's surfaces, timed -> dict(node arrays, prim_order, seconds)."""
+        sec = C.c_double(); nn = C.c_uint32()
+        lib().ref_bvh_build(self.h, bvh_type.encode(), int(bins), C.byref(sec), C.byref(nn))
+        n = nn.value
+        out = dict(node_bounds=np.zeros((n, 6)), node_first_prim=np.zeros(n, np.uint32), node_prim_count=np.zeros(n, np.uint32),
+                   node_next_sibling=np.zeros(n, np.uint32), prim_order=np.zeros(self.n_prims, np.uint32))
+        if lib().ref_bvh_arrays(self.h, _p(out["node_bounds"]), _p(out["node_first_prim"]), _p(out["node_prim_count"]),
+                                _p(out["node_next_sibling"]), _p(out["prim_order"])):
+            raise RuntimeError("ref_bvh_arrays failed")
+        out["seconds"] = sec.value
+        return out
 
     def export_pack(self, path):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

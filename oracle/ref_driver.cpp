@@ -28,6 +28,7 @@
 
 #include <nlohmann/json.hpp>
 
+#include "bvh/bvh.hpp"
 #include "camera/camera.hpp"
 #include "common/option.hpp"
 #include "integrator/integrator.hpp"
@@ -91,6 +92,7 @@ namespace
         bool photon_map = false;
         nlohmann::json scene_json;
         int camera_idx = 0;
+        std::unique_ptr<BVH> extra_bvh;   // ref_bvh_build
     };
 
     void setError(char* err, size_t errlen, const std::string& msg)
@@ -424,6 +426,58 @@ int ref_knn(void* handle, int which, const double* points, size_t n, uint32_t k,
     return 0;
 }
 
+// BVH::BVH on the opened scene's surfaces (bvh.cpp:13-78), timed: the oracle of mcrt_bvh_build.
+// type: "octree" | "binary_sah" | "quaternary_sah"; bins <= 0 = the reference's default.
+int ref_bvh_build(void* handle, const char* type, int bins, double* seconds, uint32_t* n_nodes)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    const Scene& scene = h->camera->integrator->scene;
+    nlohmann::json j = nlohmann::json::object();
+    j["type"] = std::string(type);
+    if (bins > 0) j["bins_per_axis"] = bins;
+    CoutSilencer quiet;
+    auto t0 = std::chrono::steady_clock::now();
+    h->extra_bvh = std::make_unique<BVH>(scene.BB(), scene.surfaces, j);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (n_nodes) *n_nodes = (uint32_t)h->extra_bvh->linear_tree.size();
+    return 0;
+}
+
+// arrays of the BVH built by ref_bvh_build: LinearNode fields + ordered_surfaces as indices into Scene::surfaces
+int ref_bvh_arrays(void* handle, double* node_bounds, uint32_t* first, uint32_t* count, uint32_t* next, uint32_t* order)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    if (!h->extra_bvh) return -1;
+    const BVH& b = *h->extra_bvh;
+    const Scene& scene = h->camera->integrator->scene;
+    for (size_t i = 0; i < b.linear_tree.size(); i++)
+    {
+        const auto& n = b.linear_tree[i];
+        for (int c = 0; c < 3; c++) { node_bounds[6 * i + c] = n.BB.min[c]; node_bounds[6 * i + 3 + c] = n.BB.max[c]; }
+        first[i] = n.start_surface; count[i] = n.num_surfaces; next[i] = n.next_sibling;
+    }
+    std::unordered_map<const Surface::Base*, uint32_t> original;
+    for (size_t i = 0; i < scene.surfaces.size(); i++) original.emplace(scene.surfaces[i].get(), (uint32_t)i);
+    for (size_t i = 0; i < b.ordered_surfaces.size(); i++) order[i] = original.at(b.ordered_surfaces[i].get());
+    return 0;
+}
+
+// Surface::Base::BB() of Scene::surfaces in order + Scene::BB()
+int ref_prim_bounds(void* handle, double* bounds, double* scene_bounds)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    const Scene& scene = h->camera->integrator->scene;
+    for (size_t i = 0; i < scene.surfaces.size(); i++)
+    {
+        const BoundingBox bb = scene.surfaces[i]->BB();
+        for (int c = 0; c < 3; c++) { bounds[6 * i + c] = bb.min[c]; bounds[6 * i + 3 + c] = bb.max[c]; }
+    }
+    const BoundingBox sb = scene.BB();
+    for (int c = 0; c < 3; c++) { scene_bounds[c] = sb.min[c]; scene_bounds[3 + c] = sb.max[c]; }
+    return 0;
+}
+
 // Scene pack: scene + selected camera (+ photon maps when opened with photon_map).
 int ref_export_pack(void* handle, const char* path)
 {
@@ -433,6 +487,20 @@ int ref_export_pack(void* handle, const char* path)
     mcrt_host::addSceneToPack(w, f);
     mcrt_host::addCameraToPack(w, "camera", mcrt_host::flattenCamera(*h->camera), (uint32_t)h->camera->sqrtspp);
     mcrt_host::addFilmToPack(w, "camera", mcrt_host::flattenFilm(*h->camera));
+    {
+        // the "bvh" object the reference built this scene's BVH from (bvh.cpp:24-56): {has, type, bins_per_axis}
+        uint32_t has = 0, type = MCRT_BVH_OCTREE, bins = 0;
+        if (h->scene_json.contains("bvh"))
+        {
+            has = 1;
+            const auto& bj = h->scene_json.at("bvh");
+            std::string t = bj.value("type", std::string("OCTREE"));
+            std::transform(t.begin(), t.end(), t.begin(), ::toupper);
+            if (t == "QUATERNARY_SAH") { type = MCRT_BVH_QUATERNARY_SAH; bins = bj.value("bins_per_axis", 8); }
+            else if (t == "BINARY_SAH") { type = MCRT_BVH_BINARY_SAH; bins = bj.value("bins_per_axis", 16); }
+        }
+        w.addScalarsU32("bvh_params", { has, type, bins });
+    }
     mcrt_host::FlatPhotonMap caustic, global;
     if (auto* pm = dynamic_cast<PhotonMapper*>(h->camera->integrator.get()))
     {

@@ -198,7 +198,22 @@ def make_bsdf_kat(rng):
     print("bsdf_kat: n =", n)
 
 
+def remake_packs(only):
+    """Re-exports the scene packs only (pack format grew; the reference outputs in the .npz stay)."""
+    for cid, (scene_file, overrides, pm) in CASES.items():
+        if only and cid not in only:
+            continue
+        ref.set_seed(SEED)
+        s = ref.RefScene(scene_file, overrides, photon_map=pm)
+        s.export_pack(os.path.join(HERE, cid + ".mcrtpack"))
+        s.close()
+        print("pack", cid)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--packs-only":
+        remake_packs(sys.argv[2:])
+        sys.exit(0)
     only = sys.argv[1:]
     rng = np.random.default_rng(20260923)
     for cid, (scene_file, overrides, pm) in CASES.items():
