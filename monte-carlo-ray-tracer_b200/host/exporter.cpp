@@ -206,6 +206,35 @@ namespace mcrt_host
         return o;
     }
 
+    void primitiveBounds(const Scene& scene, std::vector<double>& prim_bounds, double scene_bounds[6])
+    {
+        prim_bounds.clear();
+        prim_bounds.reserve(6 * scene.surfaces.size());
+        for (const auto& s : scene.surfaces) pushBounds(prim_bounds, s->BB());
+        const BoundingBox bb = scene.BB();
+        for (int c = 0; c < 3; c++) { scene_bounds[c] = bb.min[c]; scene_bounds[3 + c] = bb.max[c]; }
+    }
+
+    void applyBvh(FlatScene& f, const mcrt_bvh_desc& bvh)
+    {
+        const size_t n = f.prim_type.size();
+        if (bvh.n_prims != n || !f.node_first_prim.empty()) throw std::runtime_error("applyBvh: scene/tree mismatch");
+        std::vector<uint32_t> inverse(n);
+        for (size_t i = 0; i < n; i++) inverse[bvh.prim_order[i]] = (uint32_t)i;
+        auto permute = [&](auto& v)
+        {
+            auto old = v;
+            for (size_t i = 0; i < n; i++) v[i] = old[bvh.prim_order[i]];
+        };
+        permute(f.prim_type); permute(f.prim_index); permute(f.prim_material); permute(f.prim_area); permute(f.prim_original);
+        for (auto& l : f.light_prim) l = inverse[l];
+        for (auto& kv : f.prim_of_surface) kv.second = inverse[kv.second];
+        f.node_bounds.assign(bvh.node_bounds, bvh.node_bounds + 6 * (size_t)bvh.n_nodes);
+        f.node_first_prim.assign(bvh.node_first_prim, bvh.node_first_prim + bvh.n_nodes);
+        f.node_prim_count.assign(bvh.node_prim_count, bvh.node_prim_count + bvh.n_nodes);
+        f.node_next_sibling.assign(bvh.node_next_sibling, bvh.node_next_sibling + bvh.n_nodes);
+    }
+
     mcrt_film flattenFilm(const Camera& c)
     {
         // Film keeps its filter as a std::function built from a plain function (film.cpp:25-45);

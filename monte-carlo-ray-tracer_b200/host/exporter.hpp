@@ -60,6 +60,12 @@ namespace mcrt_host
     };
 
     void flattenScene(const Scene& scene, FlatScene& out);
+    // Inputs of BVH::BVH (bvh.cpp:13-15) for mcrt_bvh_build: Surface::Base::BB() of Scene::surfaces in
+    // order ([n][6]) and Scene::BB().
+    void primitiveBounds(const Scene& scene, std::vector<double>& prim_bounds, double scene_bounds[6]);
+    // Re-orders a scene flattened WITHOUT a hierarchy (Scene built from a JSON without "bvh") into
+    // the order of a tree built by mcrt_bvh_build and attaches its node arrays.
+    void applyBvh(FlatScene& flat, const mcrt_bvh_desc& bvh);
     mcrt_camera flattenCamera(const Camera& camera);
     // the camera's Film (filter, radius, cache size; source/camera/film.cpp:19-59)
     mcrt_film flattenFilm(const Camera& camera);

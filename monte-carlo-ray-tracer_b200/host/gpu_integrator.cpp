@@ -1,6 +1,8 @@
 // See gpu_integrator.hpp. Compile with -fno-access-control against /root/reference/{source,lib/*}.
 #include "gpu_integrator.hpp"
 
+#include <cctype>
+
 #include "camera/camera.hpp"
 #include "integrator/integrator.hpp"
 #include "integrator/photon-mapper/photon-mapper.hpp"
@@ -17,7 +19,16 @@ namespace mcrt_host
         }
     }
 
-    GpuRenderer::GpuRenderer(const Camera& camera, int device, int precision)
+    GpuBvh GpuBvh::fromTypeName(std::string type, int bins_per_axis)
+    {
+        for (auto& c : type) c = (char)std::toupper((unsigned char)c);
+        GpuBvh b;
+        b.type = type == "QUATERNARY_SAH" ? MCRT_BVH_QUATERNARY_SAH : (type == "BINARY_SAH" ? MCRT_BVH_BINARY_SAH : MCRT_BVH_OCTREE);
+        b.bins_per_axis = bins_per_axis;
+        return b;
+    }
+
+    GpuRenderer::GpuRenderer(const Camera& camera, int device, int precision, const GpuBvh* gpu_bvh)
         : precision_(precision), integrator_kind_(MCRT_INTEGRATOR_PATH), global_seed_(Sampler::global_seed)
     {
         int rc = mcrt_init(device, &ctx_);
@@ -25,6 +36,20 @@ namespace mcrt_host
 
         FlatScene flat;
         flattenScene(camera.integrator->scene, flat);
+        if (gpu_bvh)
+        {
+            // BVH::BVH (bvh.cpp:13-78) on the GPU: same tree as the reference would have built
+            if (camera.integrator->scene.bvh) throw std::runtime_error("GpuRenderer: scene already has a CPU-built BVH");
+            std::vector<double> prim_bounds;
+            double scene_bounds[6];
+            primitiveBounds(camera.integrator->scene, prim_bounds, scene_bounds);
+            void* handle = nullptr;
+            mcrt_bvh_desc bvh{};
+            check(mcrt_bvh_build(ctx_, prim_bounds.data(), (uint32_t)(prim_bounds.size() / 6), scene_bounds, gpu_bvh->type,
+                                 gpu_bvh->bins_per_axis, &handle, &bvh, &bvh_build_ms_), "mcrt_bvh_build");
+            applyBvh(flat, bvh);
+            mcrt_bvh_free(handle);
+        }
         mcrt_scene_desc desc = flat.desc();
         uint64_t bytes = 0;
         check(mcrt_scene_upload(ctx_, &desc, &bytes), "mcrt_scene_upload");

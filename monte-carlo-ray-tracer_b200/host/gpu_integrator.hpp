@@ -23,18 +23,30 @@ class Camera;
 
 namespace mcrt_host
 {
+    // The scene JSON's "bvh" object (bvh.cpp:24-56) when the hierarchy is to be built on the GPU:
+    // construct the reference's Scene from a JSON with "bvh" erased (no CPU build) and pass this.
+    struct GpuBvh
+    {
+        int type = MCRT_BVH_OCTREE;     // MCRT_BVH_*
+        int bins_per_axis = 0;          // <= 0: the reference's default for the type
+        static GpuBvh fromTypeName(std::string type, int bins_per_axis);
+    };
+
     class GpuRenderer
     {
     public:
         // Takes the Scene (and photon maps, if the camera was built with a PhotonMapper) that the
         // reference constructed and uploads them to CUDA device `device`.
-        explicit GpuRenderer(const Camera& camera, int device = 0, int precision = MCRT_PRECISION_F64);
+        // gpu_bvh: build the BVH with mcrt_bvh_build instead of taking the one the reference built
+        // (the Scene must then have none).
+        explicit GpuRenderer(const Camera& camera, int device = 0, int precision = MCRT_PRECISION_F64,
+                             const GpuBvh* gpu_bvh = nullptr);
         ~GpuRenderer();
         GpuRenderer(const GpuRenderer&) = delete;
         GpuRenderer& operator=(const GpuRenderer&) = delete;
 
         // Camera::sampleImage: renders every row and stores Film::scan-equivalent values in
-        // camera.image(x, y). Throws if the camera uses a non-box film (not on the GPU path).
+        // camera.image(x, y), through the camera's own Film filter (mcrt_set_film).
         void sampleImage(Camera& camera);
 
         // Rows [y0, y1) as float64 RGB, row-major.
@@ -46,6 +58,7 @@ namespace mcrt_host
 
         const mcrt_stats& lastStats() const { return stats_; }
         uint64_t uploadedBytes() const { return h2d_bytes_; }
+        double bvhBuildMs() const { return bvh_build_ms_; }   // device time of mcrt_bvh_build (0: not used)
 
     private:
         void check(int rc, const char* what) const;
@@ -56,5 +69,6 @@ namespace mcrt_host
         uint32_t global_seed_;
         mcrt_stats stats_{};
         uint64_t h2d_bytes_ = 0;
+        double bvh_build_ms_ = 0.0;
     };
 }

@@ -1,7 +1,9 @@
 // Headless stand-in for the reference's main.cpp (source/main.cpp:10-61) that renders through the
 // GPU path: same scene directory / JSON / camera index / integrator choice, same Camera object,
 // same Image::save — only Camera::sampleImage is replaced by GpuRenderer::sampleImage.
-// usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map 0|1] [f64|f32]
+// usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map 0|1] [f64|f32] [gpu_bvh 0|1]
+// gpu_bvh = 1: the scene's "bvh" object is taken out of the JSON (the reference then builds no
+// hierarchy) and the same tree is built by mcrt_bvh_build.
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -18,7 +20,7 @@ int main(int argc, char* argv[])
 {
     if (argc < 3)
     {
-        std::cerr << "usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map] [f64|f32]\n";
+        std::cerr << "usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map] [f64|f32] [gpu_bvh]\n";
         return 2;
     }
     try
@@ -32,10 +34,19 @@ int main(int argc, char* argv[])
         std::ifstream in(dir / argv[2]);
         nlohmann::json j;
         in >> j;
+        const bool gpu_bvh = argc > 6 && std::atoi(argv[6]) != 0 && j.contains("bvh") && !photon_map;
+        mcrt_host::GpuBvh bvh;
+        if (gpu_bvh)
+        {
+            const auto& b = j.at("bvh");
+            bvh = mcrt_host::GpuBvh::fromTypeName(b.value("type", std::string("OCTREE")), b.value("bins_per_axis", 0));
+            j.erase("bvh");
+        }
         Option option(dir / argv[2], "", camera_idx, photon_map);
-        Camera camera(j, option);                    // reference: scene load, BVH build, photon pass
+        Camera camera(j, option);                    // reference: scene load, (BVH build,) photon pass
 
-        mcrt_host::GpuRenderer gpu(camera, 0, precision);
+        mcrt_host::GpuRenderer gpu(camera, 0, precision, gpu_bvh ? &bvh : nullptr);
+        if (gpu_bvh) std::cout << "bvh built on the GPU in " << gpu.bvhBuildMs() << " ms" << std::endl;
         auto t0 = std::chrono::steady_clock::now();
         gpu.sampleImage(camera);                     // GPU: the hot path
         auto t1 = std::chrono::steady_clock::now();
