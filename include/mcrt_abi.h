@@ -237,6 +237,26 @@ int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photon
                            const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out);
 void mcrt_octree_free_host(void* handle);
 
+/* SURVEY.md §8f-4 ("next", image half): Image::save (source/camera/image.cpp:37-51) without the file:
+ * auto exposure (getExposure, image.cpp:63-73: histogram median -> 0.5), tone-mapping operator
+ * (pixel-operators.cpp:7-51), auto gain (getGain, image.cpp:78-88: 99th percentile -> 0.99), sRGB
+ * gamma (srgb.hpp:54-62) and truncation to bytes in B,G,R order. `params` = the camera's "image"
+ * object (image.cpp:10-35). rgb: [height][width][3] float64 as mcrt_render_rows returns it;
+ * out_bgr: [height][width][3] bytes = the reference's .tga after its 18-byte header.
+ * mcrt_image_tonemap takes HOST buffers, mcrt_image_tonemap_dev DEVICE pointers (e.g. the
+ * framebuffer of mcrt_render_rows_dev, so that 6 MB of bytes leave the GPU instead of 50 MB). */
+enum { MCRT_TONEMAP_HABLE = 0, MCRT_TONEMAP_ACES = 1, MCRT_TONEMAP_LINEAR = 2 };
+typedef struct mcrt_image_params {
+    uint32_t plain;                 /* "plain": no tone mapping, no auto exposure / gain */
+    uint32_t tonemapper;            /* MCRT_TONEMAP_HABLE (default) | MCRT_TONEMAP_ACES */
+    double exposure_compensation;   /* EV */
+    double gain_compensation;       /* EV */
+} mcrt_image_params;
+int mcrt_image_tonemap(mcrt_ctx* ctx, const double* rgb, uint32_t width, uint32_t height, const mcrt_image_params* params,
+                       uint8_t* out_bgr, double* exposure_factor, double* gain_factor);
+int mcrt_image_tonemap_dev(mcrt_ctx* ctx, const double* rgb_dev, uint32_t width, uint32_t height,
+                           const mcrt_image_params* params, uint8_t* out_bgr_dev, double* exposure_factor, double* gain_factor);
+
 /* SURVEY.md §8f-2 ("next"): BVH construction on the GPU. Replaces BVH::BVH (source/bvh/bvh.cpp:13-78):
  * the binned-SAH builders recursiveBuildBinarySAH / recursiveBuildQuaternarySAH (bvh.cpp:165-432),
  * the octree-derived hierarchy (bvh.cpp:130-163, octree.cpp:34-81), arbitrarySplit and compact

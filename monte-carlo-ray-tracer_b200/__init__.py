@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
-    "mcrt_bvh_build", "mcrt_bvh_free",
+    "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
 ]
 
 
@@ -108,6 +108,18 @@ class PhotonMapDesc(C.Structure):
                 ("n_photons", C.c_uint64), ("photons", C.c_void_p)]
 
 
+class ImageParams(C.Structure):
+    """The camera's "image" object (image.cpp:10-35) without the size."""
+    _fields_ = [("plain", C.c_uint32), ("tonemapper", C.c_uint32), ("exposure_compensation", C.c_double),
+                ("gain_compensation", C.c_double)]
+
+    @classmethod
+    def from_json(cls, image):
+        tm = str(image.get("tonemapper", "HABLE")).upper()
+        return cls(int(bool(image.get("plain", False))), 1 if tm == "ACES" else 0,
+                   float(image.get("exposure_compensation", 0.0)), float(image.get("gain_compensation", 0.0)))
+
+
 class BvhDesc(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_prims", C.c_uint32), ("node_bounds", C.c_void_p),
                 ("node_first_prim", C.c_void_p), ("node_prim_count", C.c_void_p), ("node_next_sibling", C.c_void_p),
@@ -181,6 +193,10 @@ def lib():
                                      C.POINTER(C.c_void_p), C.POINTER(BvhDesc), C.POINTER(C.c_double)]
         L.mcrt_bvh_free.argtypes = [C.c_void_p]
         L.mcrt_bvh_free.restype = None
+        tm_args = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ImageParams), C.c_void_p,
+                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.mcrt_image_tonemap.argtypes = tm_args
+        L.mcrt_image_tonemap_dev.argtypes = tm_args
         if L.mcrt_abi_version() != 1:
             raise McrtError("libmcrt_b200.so ABI version mismatch")
         _lib = L
@@ -492,6 +508,23 @@ class Integrator:
                                                        C.c_void_p(out_dev_ptr), C.byref(st)))
         self.last_stats = st.as_dict()
         return self.last_stats
+
+    # -- Image::save without the file: float64 [H, W, 3] -> bytes [H, W, 3] in B,G,R order (the .tga payload)
+    def tonemap(self, rgb, image=None):
+        params = image if isinstance(image, ImageParams) else ImageParams.from_json(image or {})
+        rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+        h, w = rgb.shape[:2]
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        e, g = C.c_double(), C.c_double()
+        self._check(lib().mcrt_image_tonemap(self.ctx, _ptr(rgb), w, h, C.byref(params), _ptr(out), C.byref(e), C.byref(g)))
+        return out, e.value, g.value
+
+    def tonemap_dev(self, rgb_dev_ptr, out_dev_ptr, width, height, image=None):
+        params = image if isinstance(image, ImageParams) else ImageParams.from_json(image or {})
+        e, g = C.c_double(), C.c_double()
+        self._check(lib().mcrt_image_tonemap_dev(self.ctx, C.c_void_p(rgb_dev_ptr), width, height, C.byref(params),
+                                                 C.c_void_p(out_dev_ptr), C.byref(e), C.byref(g)))
+        return e.value, g.value
 
     def sampler_stream(self, pixel, sample, n_shuffles):
         pixel = np.ascontiguousarray(pixel, dtype=np.uint32)

@@ -19,6 +19,7 @@ UNITS = [
     ("kernels_f64.cu", ["--fmad=false"]),
     ("kernels_f32.cu", []),
     ("bvh_build.cu", ["--fmad=false"]),
+    ("image.cu", ["--fmad=false"]),
     ("abi.cu", []),
 ]
 

@@ -13,6 +13,7 @@
 #include "mcrt_abi.h"
 #include "launch.h"
 #include "bvh_build.h"
+#include "image.h"
 
 using namespace mcrt;
 
@@ -1287,6 +1288,34 @@ int mcrt_render_rows_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, 
     CK(cudaSetDevice(ctx->device));
     if (y1 <= y0) { ctx->error = "empty row range"; return MCRT_ERR_INVALID; }
     return renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_image_tonemap_dev(mcrt_ctx* ctx, const double* rgb_dev, uint32_t width, uint32_t height,
+                           const mcrt_image_params* params, uint8_t* out_bgr_dev, double* exposure_factor, double* gain_factor)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!rgb_dev || !out_bgr_dev || !params || width == 0 || height == 0) { ctx->error = "mcrt_image_tonemap: invalid arguments"; return MCRT_ERR_INVALID; }
+    if (params->tonemapper > MCRT_TONEMAP_ACES) { ctx->error = "mcrt_image_tonemap: unknown tonemapper"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    return imageTonemapOnDevice(rgb_dev, width, height, *params, out_bgr_dev, ctx->sm_count, ctx->stream, exposure_factor, gain_factor, ctx->error);
+}
+
+int mcrt_image_tonemap(mcrt_ctx* ctx, const double* rgb, uint32_t width, uint32_t height, const mcrt_image_params* params,
+                       uint8_t* out_bgr, double* exposure_factor, double* gain_factor)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!rgb || !out_bgr || !params || width == 0 || height == 0) { ctx->error = "mcrt_image_tonemap: invalid arguments"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height;
+    double* d_rgb = nullptr; uint8_t* d_out = nullptr;
+    CK(cudaMalloc((void**)&d_rgb, n * 3 * sizeof(double)));
+    if (cudaMalloc((void**)&d_out, n * 3) != cudaSuccess) { cudaFree(d_rgb); ctx->error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
+    int rc = MCRT_OK;
+    if (cudaMemcpyAsync(d_rgb, rgb, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->error = "upload failed"; rc = MCRT_ERR_CUDA; }
+    if (rc == MCRT_OK) rc = mcrt_image_tonemap_dev(ctx, d_rgb, width, height, params, d_out, exposure_factor, gain_factor);
+    if (rc == MCRT_OK && cudaMemcpy(out_bgr, d_out, n * 3, cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->error = "copy back failed"; rc = MCRT_ERR_CUDA; }
+    cudaFree(d_rgb); cudaFree(d_out);
+    return rc;
 }
 
 int mcrt_bvh_build(mcrt_ctx* ctx, const double* prim_bounds, uint32_t n_prims, const double* scene_bounds6, int type,

@@ -842,4 +842,80 @@ void oracle_render_film(void* h, const mcrt_camera* cam, const mcrt_film* film, 
         }
 }
 
+// Image::save without the file (image.cpp:37-88, histogram.cpp, pixel-operators.cpp, srgb.hpp:54-62)
+namespace
+{
+    void tonemapOp(uint32_t op, const double in[3], double out[3])
+    {
+        if (op == MCRT_TONEMAP_LINEAR) { for (int c = 0; c < 3; c++) out[c] = in[c]; return; }
+        if (op == MCRT_TONEMAP_ACES)
+        {
+            const double v[3] = {0.59719 * in[0] + 0.35458 * in[1] + 0.04823 * in[2], 0.07600 * in[0] + 0.90834 * in[1] + 0.01566 * in[2],
+                                 0.02840 * in[0] + 0.13383 * in[1] + 0.83777 * in[2]};
+            double r[3];
+            for (int c = 0; c < 3; c++) r[c] = (v[c] * (v[c] + 0.0245786) - 0.000090537) / (v[c] * (0.983729 * v[c] + 0.4329510) + 0.238081);
+            const double o[3] = {1.60475 * r[0] + -0.53108 * r[1] + -0.07367 * r[2], -0.10208 * r[0] + 1.10813 * r[1] + -0.00605 * r[2],
+                                 -0.00327 * r[0] + -0.07276 * r[1] + 1.07602 * r[2]};
+            for (int c = 0; c < 3; c++) out[c] = std::min(std::max(o[c], 0.0), 1.0);
+            return;
+        }
+        const double A = 0.15, B = 0.50, Cc = 0.10, D = 0.20, E = 0.02, F = 0.30, W = 11.2;
+        auto f = [&](double x) { return ((x * (A * x + Cc * B) + D * E) / (x * (A * x + B) + D * F)) - E / F; };
+        for (int c = 0; c < 3; c++) out[c] = f(in[c]) / f(W);
+    }
+
+    double histogramLevel(const std::vector<double>& data, double pct)
+    {
+        const size_t bins = 65536;
+        double mx = std::numeric_limits<double>::lowest();
+        for (double v : data) { if (v < 0.0) return 0.0; if (mx < v) mx = v; }
+        if (!(mx > 0.0)) return 0.0;
+        const double bin_size = mx / bins;
+        std::vector<size_t> counts(bins, 0);
+        for (double v : data) counts[std::min((size_t)(v / bin_size), bins - 1)]++;
+        const size_t num = (size_t)(data.size() * pct);
+        size_t count = 0;
+        for (size_t i = 0; i < bins; i++) { count += counts[i]; if (count >= num) return (i + 1) * bin_size; }
+        return 0.0;
+    }
+}
+
+void oracle_image_tonemap(const double* rgb, uint32_t width, uint32_t height, const mcrt_image_params* prm, uint8_t* out_bgr,
+                          double* exposure_factor, double* gain_factor)
+{
+    const size_t n = (size_t)width * height;
+    const uint32_t op = prm->plain ? (uint32_t)MCRT_TONEMAP_LINEAR : prm->tonemapper;
+    double exposure = 1.0, gain = 1.0;
+    if (!prm->plain)
+    {
+        std::vector<double> b(n);
+        for (size_t i = 0; i < n; i++) b[i] = (rgb[3 * i] + rgb[3 * i + 1] + rgb[3 * i + 2]) / 3.0;
+        double L = histogramLevel(b, 0.5);
+        exposure = (L > 0.0 ? 0.5 / L : 1.0) * std::pow(2, prm->exposure_compensation);
+        for (size_t i = 0; i < n; i++)
+        {
+            const double q[3] = {rgb[3 * i] * exposure, rgb[3 * i + 1] * exposure, rgb[3 * i + 2] * exposure};
+            double t[3];
+            tonemapOp(op, q, t);
+            b[i] = (t[0] + t[1] + t[2]) / 3.0;
+        }
+        L = histogramLevel(b, 0.99);
+        gain = (L > 0.0 ? 0.99 / L : 1.0) * std::pow(2, prm->gain_compensation);
+    }
+    for (size_t i = 0; i < n; i++)
+    {
+        const double q[3] = {rgb[3 * i] * exposure, rgb[3 * i + 1] * exposure, rgb[3 * i + 2] * exposure};
+        double t[3];
+        tonemapOp(op, q, t);
+        for (int c = 0; c < 3; c++)
+        {
+            const double x = t[c] * gain;
+            const double g = x <= 0.0031308 ? 12.92 * x : 1.055 * std::pow(x, 1.0 / 2.4) - 0.055;
+            out_bgr[3 * i + (2 - c)] = (uint8_t)(std::min(std::max(g, 0.0), 1.0) * std::nextafter(256.0, 0.0));
+        }
+    }
+    if (exposure_factor) *exposure_factor = exposure;
+    if (gain_factor) *gain_factor = gain;
+}
+
 } // extern "C"

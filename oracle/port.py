@@ -27,6 +27,7 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_image_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_render_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
@@ -41,6 +42,16 @@ def sampler_stream(pixel, sample, n_shuffles, seed):
     out = np.zeros((len(pixel), 7), dtype=np.uint32)
     lib().oracle_sampler_stream(_p(pixel), _p(sample), len(pixel), n_shuffles, seed, _p(out))
     return out
+
+
+def image_tonemap(rgb, params):
+    """Image::save restated; params = the product's ImageParams ctypes struct (layout only)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+    h, w = rgb.shape[:2]
+    out = np.zeros((h, w, 3), dtype=np.uint8)
+    e, g = C.c_double(), C.c_double()
+    lib().oracle_image_tonemap(_p(rgb), w, h, C.addressof(params), _p(out), C.byref(e), C.byref(g))
+    return out, e.value, g.value
 
 
 class PortScene:

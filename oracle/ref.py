@@ -47,6 +47,7 @@ def lib():
         L.ref_bvh_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
         L.ref_bvh_arrays.argtypes = [C.c_void_p] * 6
         L.ref_prim_bounds.argtypes = [C.c_void_p] * 3
+        L.ref_image_save.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_fresnel_dielectric.restype = C.c_double
         L.ref_fresnel_dielectric.argtypes = [C.c_double] * 3
         L.ref_fresnel_conductor.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -158,6 +159,19 @@ class RefScene:
         if lib().ref_export_pack(self.h, path.encode()):
             raise RuntimeError("ref_export_pack failed")
         return path
+
+
+def image_save(rgb, image):
+    """Image::save on an [H, W, 3] float64 image; `image` = the camera's "image" JSON object without the
+    size. -> (bytes [H, W, 3] in B,G,R order, exposure factor, gain factor)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+    h, w = rgb.shape[:2]
+    out = np.zeros((h, w, 3), dtype=np.uint8)
+    e, g = C.c_double(), C.c_double()
+    rc = lib().ref_image_save(json.dumps(dict(image, width=w, height=h)).encode(), _p(rgb), _p(out), C.byref(e), C.byref(g))
+    if rc:
+        raise RuntimeError(f"ref_image_save failed: {rc}")
+    return out, e.value, g.value
 
 
 def sampler_stream(pixel, sample, n_shuffles):

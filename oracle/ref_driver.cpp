@@ -23,6 +23,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <unistd.h>
 #include <thread>
 #include <vector>
 
@@ -424,6 +425,39 @@ int ref_knn(void* handle, int which, const double* points, size_t n, uint32_t k,
         }
     }
     return 0;
+}
+
+// Image::save (image.cpp:37-51) on caller pixels: `image_json` is a camera's "image" object; the bytes
+// are what the reference writes after the TGA header. Also returns getExposure()*exposure_scale
+// and getGain()*gain_scale.
+int ref_image_save(const char* image_json, const double* rgb, uint8_t* out_bgr, double* exposure_factor, double* gain_factor)
+{
+    try
+    {
+        Image img(nlohmann::json::parse(image_json));
+        for (size_t i = 0; i < img.num_pixels; i++) img.blob[i] = glm::dvec3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        const double e = img.plain ? 1.0 : img.getExposure() * img.exposure_scale;
+        const double g = img.plain ? 1.0 : img.getGain(e) * img.gain_scale;
+        if (exposure_factor) *exposure_factor = e;
+        if (gain_factor) *gain_factor = g;
+        char name[] = "/tmp/mcrt_ref_image_XXXXXX";
+        int fd = mkstemp(name);
+        if (fd < 0) return -2;
+        close(fd);
+        img.save(name);                       // writes name + ".tga"
+        std::string tga = std::string(name) + ".tga";
+        std::ifstream in(tga, std::ios::binary);
+        in.seekg(18);
+        in.read(reinterpret_cast<char*>(out_bgr), (std::streamsize)(img.num_pixels * 3));
+        const bool ok = (size_t)in.gcount() == img.num_pixels * 3;
+        in.close();
+        std::remove(tga.c_str()); std::remove(name);
+        return ok ? 0 : -3;
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
 }
 
 // BVH::BVH on the opened scene's surfaces (bvh.cpp:13-78), timed: the oracle of mcrt_bvh_build.

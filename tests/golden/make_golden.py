@@ -152,6 +152,40 @@ def make_film_kat():
     np.savez_compressed(os.path.join(HERE, "film_kat.npz"), seed=np.uint32(SEED), films=json.dumps(FILMS), **out)
 
 
+# the camera's "image" object (image.cpp:10-35) minus the size
+IMAGE_CONFIGS = {
+    "hable": {},
+    "aces": {"tonemapper": "ACES"},
+    "plain": {"plain": True},
+    "hable_ev": {"exposure_compensation": -0.25, "gain_compensation": 0.5},
+    "aces_ev": {"tonemapper": "aces", "exposure_compensation": 1.0},
+}
+
+
+def make_image_kat():
+    """Image::save (auto exposure, tone mapping, auto gain, gamma, bytes) of reference renders and of
+    synthetic HDR images -> image_kat.npz. Inputs that are golden images are referenced by name."""
+    import json
+    rng = np.random.default_rng(7)
+    inputs = {}
+    for cid in ("c2_hexagon_room_96", "veach_mis_64", "metals_64"):
+        inputs["golden:" + cid] = np.load(os.path.join(HERE, cid + ".npz"))["image"]
+    inputs["hdr_lognormal_128"] = np.exp(rng.normal(-1.0, 2.0, (128, 128, 3)))
+    inputs["black_16"] = np.zeros((16, 16, 3))
+    sparse = np.zeros((32, 32, 3)); sparse[5, 7] = (3.0, 2.0, 1.0); sparse[20:, :10] = 0.25
+    inputs["sparse_32"] = sparse
+    out = {}
+    for iname, img in inputs.items():
+        if not iname.startswith("golden:"):
+            out["input/" + iname] = img
+        for cname, cfg in IMAGE_CONFIGS.items():
+            b, e, g = ref.image_save(img, cfg)
+            out[f"bytes/{iname}/{cname}"] = b
+            out[f"factors/{iname}/{cname}"] = np.array([e, g])
+            print(f"image_kat {iname} {cname}: exposure {e:.6g} gain {g:.6g} mean byte {b.mean():.2f}")
+    np.savez_compressed(os.path.join(HERE, "image_kat.npz"), inputs=json.dumps(list(inputs)), configs=json.dumps(IMAGE_CONFIGS), **out)
+
+
 def make_sampler_kat(rng):
     ref.set_seed(SEED)
     n = 8192
@@ -226,3 +260,5 @@ if __name__ == "__main__":
         make_bsdf_kat(rng)
     if not only or "film_kat" in only:
         make_film_kat()
+    if not only or "image_kat" in only:
+        make_image_kat()

@@ -93,3 +93,30 @@ def test_film_filters(name, mcrt):
         ps.close()
     ref = k["image_" + name]
     assert np.abs(img - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def _image_cases():
+    import json
+    k = np.load(os.path.join(GOLDEN, "image_kat.npz"))
+    cases = []
+    for iname in json.loads(str(k["inputs"])):
+        for cname in json.loads(str(k["configs"])):
+            cases.append((iname, cname))
+    return cases
+
+
+def image_kat_input(k, iname):
+    if iname.startswith("golden:"):
+        return np.load(os.path.join(GOLDEN, iname[7:] + ".npz"))["image"]
+    return k["input/" + iname]
+
+
+@pytest.mark.parametrize("iname,cname", _image_cases())
+def test_image_pipeline(iname, cname, mcrt):
+    # Image::save: auto exposure / tone mapping / auto gain / gamma / bytes (image.cpp:37-88)
+    import json
+    k = np.load(os.path.join(GOLDEN, "image_kat.npz"))
+    params = mcrt.ImageParams.from_json(json.loads(str(k["configs"]))[cname])
+    got, e, g = port.image_tonemap(image_kat_input(k, iname), params)
+    assert np.array_equal(got, k[f"bytes/{iname}/{cname}"])
+    assert (e, g) == tuple(k[f"factors/{iname}/{cname}"])
