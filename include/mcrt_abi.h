@@ -249,8 +249,8 @@ enum { MCRT_TONEMAP_HABLE = 0, MCRT_TONEMAP_ACES = 1, MCRT_TONEMAP_LINEAR = 2 };
 typedef struct mcrt_image_params {
     uint32_t plain;                 /* "plain": no tone mapping, no auto exposure / gain */
     uint32_t tonemapper;            /* MCRT_TONEMAP_HABLE (default) | MCRT_TONEMAP_ACES */
-    double exposure_compensation;   /* EV */
-    double gain_compensation;       /* EV */
+    double exposure_scale;          /* 2^exposure_compensation, Image::exposure_scale (image.cpp:21) */
+    double gain_scale;              /* 2^gain_compensation, Image::gain_scale (image.cpp:22) */
 } mcrt_image_params;
 int mcrt_image_tonemap(mcrt_ctx* ctx, const double* rgb, uint32_t width, uint32_t height, const mcrt_image_params* params,
                        uint8_t* out_bgr, double* exposure_factor, double* gain_factor);

@@ -10,6 +10,7 @@ Everything that computes runs in libmcrt_b200.so on the GPU; this module only ma
 There is no CPU fallback: importing works anywhere (so that symbols can be checked), but any compute
 call without the built library or without a CUDA device raises."""
 import ctypes as C
+import math
 import os
 import struct
 
@@ -110,14 +111,14 @@ class PhotonMapDesc(C.Structure):
 
 class ImageParams(C.Structure):
     """The camera's "image" object (image.cpp:10-35) without the size."""
-    _fields_ = [("plain", C.c_uint32), ("tonemapper", C.c_uint32), ("exposure_compensation", C.c_double),
-                ("gain_compensation", C.c_double)]
+    _fields_ = [("plain", C.c_uint32), ("tonemapper", C.c_uint32), ("exposure_scale", C.c_double),
+                ("gain_scale", C.c_double)]
 
     @classmethod
     def from_json(cls, image):
         tm = str(image.get("tonemapper", "HABLE")).upper()
         return cls(int(bool(image.get("plain", False))), 1 if tm == "ACES" else 0,
-                   float(image.get("exposure_compensation", 0.0)), float(image.get("gain_compensation", 0.0)))
+                   math.pow(2, image.get("exposure_compensation", 0.0)), math.pow(2, image.get("gain_compensation", 0.0)))
 
 
 class BvhDesc(C.Structure):

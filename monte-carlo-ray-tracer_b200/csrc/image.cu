@@ -190,8 +190,7 @@ int imageTonemapOnDevice(const double* d_rgb, uint32_t width, uint32_t height, c
     {
         IK(cudaMalloc((void**)&d_state, sizeof(ImageState)));
         if (cudaMalloc((void**)&d_counts, HIST_BINS * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_state); error = "cudaMalloc failed"; return MCRT_ERR_CUDA; }
-        // image.cpp:21-22, 39-40
-        const double exposure_scale = std::pow(2, prm.exposure_compensation), gain_scale = std::pow(2, prm.gain_compensation);
+        const double exposure_scale = prm.exposure_scale, gain_scale = prm.gain_scale;   // image.cpp:21-22, 39-40
         double L = 0.0;
         int rc = histogramLevel(d_rgb, n, 0, op, 1.0, 0.5, d_state, d_counts, grid, s, L, error);
         if (rc == MCRT_OK)

@@ -3,7 +3,10 @@
 
 #include <cctype>
 
+#include <fstream>
+
 #include "camera/camera.hpp"
+#include "camera/pixel-operators.hpp"
 #include "integrator/integrator.hpp"
 #include "integrator/photon-mapper/photon-mapper.hpp"
 #include "sampling/sampler.hpp"
@@ -97,6 +100,30 @@ namespace mcrt_host
                 const double* p = &rgb[((size_t)y * W + x) * 3];
                 camera.image(x, y) = glm::dvec3(p[0], p[1], p[2]); // what film.scan(x, y) would return
             }
+    }
+
+    void GpuRenderer::saveImage(const Camera& camera)
+    {
+        const Image& img = camera.image;
+        typedef glm::dvec3 (*Op)(const glm::dvec3&);
+        const Op* op = img.tonemap.target<Op>();
+        if (!op) throw std::runtime_error("GpuRenderer::saveImage: unknown tone mapping operator");
+        mcrt_image_params prm{};
+        prm.plain = img.plain ? 1u : 0u;
+        prm.tonemapper = *op == static_cast<Op>(filmicACES) ? MCRT_TONEMAP_ACES : MCRT_TONEMAP_HABLE;
+        prm.exposure_scale = img.exposure_scale;
+        prm.gain_scale = img.gain_scale;
+        std::vector<uint8_t> bytes(img.num_pixels * 3);
+        static_assert(sizeof(glm::dvec3) == 3 * sizeof(double), "Image::blob must be packed doubles");
+        check(mcrt_image_tonemap(ctx_, reinterpret_cast<const double*>(img.blob.data()), (uint32_t)img.width, (uint32_t)img.height,
+                                 &prm, bytes.data(), nullptr, nullptr), "mcrt_image_tonemap");
+        // Image::HeaderTGA (image.hpp:37-48): uncompressed 24 bpp true colour, top-left origin
+        uint8_t header[18] = {0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 24, 32};
+        header[12] = (uint8_t)(img.width & 0xFF); header[13] = (uint8_t)(img.width >> 8);
+        header[14] = (uint8_t)(img.height & 0xFF); header[15] = (uint8_t)(img.height >> 8);
+        std::ofstream out(camera.savename + ".tga", std::ios::binary);
+        out.write(reinterpret_cast<const char*>(header), sizeof(header));
+        out.write(reinterpret_cast<const char*>(bytes.data()), (std::streamsize)bytes.size());
     }
 
     std::vector<double> GpuRenderer::sampleRays(const std::vector<mcrt_ray>& rays, const std::vector<uint32_t>& pixel,

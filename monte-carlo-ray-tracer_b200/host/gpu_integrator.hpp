@@ -49,6 +49,10 @@ namespace mcrt_host
         // camera.image(x, y), through the camera's own Film filter (mcrt_set_film).
         void sampleImage(Camera& camera);
 
+        // Camera::saveImage / Image::save (image.cpp:37-51) with exposure, tone mapping, gain, gamma and
+        // byte conversion on the GPU (mcrt_image_tonemap); writes camera.savename + ".tga".
+        void saveImage(const Camera& camera);
+
         // Rows [y0, y1) as float64 RGB, row-major.
         std::vector<double> renderRows(const Camera& camera, uint32_t y0, uint32_t y1);
 

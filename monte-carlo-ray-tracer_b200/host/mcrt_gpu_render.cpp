@@ -1,9 +1,10 @@
 // Headless stand-in for the reference's main.cpp (source/main.cpp:10-61) that renders through the
 // GPU path: same scene directory / JSON / camera index / integrator choice, same Camera object,
 // same Image::save — only Camera::sampleImage is replaced by GpuRenderer::sampleImage.
-// usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map 0|1] [f64|f32] [gpu_bvh 0|1]
+// usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map 0|1] [f64|f32] [gpu_bvh 0|1] [gpu_image 0|1]
 // gpu_bvh = 1: the scene's "bvh" object is taken out of the JSON (the reference then builds no
-// hierarchy) and the same tree is built by mcrt_bvh_build.
+// hierarchy) and the same tree is built by mcrt_bvh_build. gpu_image = 1: Image::save's exposure /
+// tone mapping / gamma run on the GPU too (mcrt_image_tonemap) instead of camera.saveImage().
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -20,7 +21,7 @@ int main(int argc, char* argv[])
 {
     if (argc < 3)
     {
-        std::cerr << "usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map] [f64|f32] [gpu_bvh]\n";
+        std::cerr << "usage: mcrt_gpu_render <scenes_dir> <scene.json> [camera_idx] [photon_map] [f64|f32] [gpu_bvh] [gpu_image]\n";
         return 2;
     }
     try
@@ -50,7 +51,8 @@ int main(int argc, char* argv[])
         auto t0 = std::chrono::steady_clock::now();
         gpu.sampleImage(camera);                     // GPU: the hot path
         auto t1 = std::chrono::steady_clock::now();
-        camera.saveImage();                          // reference: exposure, tonemap, TGA
+        if (argc > 7 && std::atoi(argv[7]) != 0) gpu.saveImage(camera);   // GPU: exposure, tonemap, gamma; same TGA
+        else camera.saveImage();                     // reference: exposure, tonemap, TGA
 
         const mcrt_stats& st = gpu.lastStats();
         double rays = double(st.extension_rays + st.shadow_rays);

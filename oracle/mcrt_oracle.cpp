@@ -891,7 +891,7 @@ void oracle_image_tonemap(const double* rgb, uint32_t width, uint32_t height, co
         std::vector<double> b(n);
         for (size_t i = 0; i < n; i++) b[i] = (rgb[3 * i] + rgb[3 * i + 1] + rgb[3 * i + 2]) / 3.0;
         double L = histogramLevel(b, 0.5);
-        exposure = (L > 0.0 ? 0.5 / L : 1.0) * std::pow(2, prm->exposure_compensation);
+        exposure = (L > 0.0 ? 0.5 / L : 1.0) * prm->exposure_scale;
         for (size_t i = 0; i < n; i++)
         {
             const double q[3] = {rgb[3 * i] * exposure, rgb[3 * i + 1] * exposure, rgb[3 * i + 2] * exposure};
@@ -900,7 +900,7 @@ void oracle_image_tonemap(const double* rgb, uint32_t width, uint32_t height, co
             b[i] = (t[0] + t[1] + t[2]) / 3.0;
         }
         L = histogramLevel(b, 0.99);
-        gain = (L > 0.0 ? 0.99 / L : 1.0) * std::pow(2, prm->gain_compensation);
+        gain = (L > 0.0 ? 0.99 / L : 1.0) * prm->gain_scale;
     }
     for (size_t i = 0; i < n; i++)
     {
