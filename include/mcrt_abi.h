@@ -221,7 +221,9 @@ typedef struct mcrt_photon_emit_params {
  * Octree<Photon> construction + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244)
  * — and installs the two maps in the context exactly as mcrt_photon_upload would. The photon
  * multiset and the octree structure equal the reference's (photons inside one leaf may be stored
- * in a different order: the reference's order depends on its thread schedule). */
+ * in a different order: the reference's order depends on its thread schedule). The octrees are
+ * built on the device from the emission buffers (the photons never visit the host); in `stats`,
+ * gpu_ms_total is the emission wavefront and gpu_ms_knn the octree construction. */
 int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision,
                      uint64_t* n_caustic, uint64_t* n_global, mcrt_stats* stats);
 
@@ -236,6 +238,10 @@ int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out);
 int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf,
                            const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out);
 void mcrt_octree_free_host(void* handle);
+/* The same construction on the GPU (what mcrt_photon_emit runs on its emission buffers): same
+ * octants, same photon order as mcrt_octree_build_host. Release *handle with mcrt_octree_free_host. */
+int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf,
+                      const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out, double* gpu_ms);
 
 /* SURVEY.md §8f-4 ("next", image half): Image::save (source/camera/image.cpp:37-51) without the file:
  * auto exposure (getExposure, image.cpp:63-73: histogram median -> 0.5), tone-mapping operator

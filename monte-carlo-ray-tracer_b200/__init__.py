@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
-    "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
+    "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev", "mcrt_octree_build",
 ]
 
 
@@ -174,6 +174,8 @@ def lib():
                                        C.POINTER(C.c_uint64), C.POINTER(Stats)]
         L.mcrt_photon_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(PhotonMapDesc)]
         L.mcrt_octree_build_host.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PhotonMapDesc)]
+        L.mcrt_octree_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p),
+                                        C.POINTER(PhotonMapDesc), C.POINTER(C.c_double)]
         L.mcrt_octree_free_host.argtypes = [C.c_void_p]
         L.mcrt_octree_free_host.restype = None
         render_args = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -574,13 +576,27 @@ class PhotonMapper(Integrator):
                                            C.byref(nc), C.byref(ng), C.byref(st)))
         self.last_stats = st.as_dict()
         self.k_nearest = int(k_nearest_photons)
-        maps = []
-        for which in (0, 1):
-            d = PhotonMapDesc()
-            self._check(lib().mcrt_photon_download(self.ctx, which, C.byref(d)))
-            maps.append(_map_arrays(d))
-        self._maps = (maps[0], maps[1], int(k_nearest_photons), int(bool(direct_visualization)))
+        # the maps stay in HBM (octrees are built there too); host copies only when somebody asks
+        self._host_maps = None
+        self._emitted = (int(k_nearest_photons), int(bool(direct_visualization)))
+        self.n_photons = (nc.value, ng.value)
         return nc.value, ng.value
+
+    @property
+    def _maps(self):
+        if self._host_maps is None and getattr(self, "_emitted", None) is not None:
+            maps = []
+            for which in (0, 1):
+                d = PhotonMapDesc()
+                self._check(lib().mcrt_photon_download(self.ctx, which, C.byref(d)))
+                maps.append(_map_arrays(d))
+            self._host_maps = (maps[0], maps[1]) + self._emitted
+        return self._host_maps
+
+    @_maps.setter
+    def _maps(self, value):
+        self._host_maps = value
+        self._emitted = None
 
     @staticmethod
     def _map_desc(m):
@@ -666,6 +682,28 @@ def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis=0, device=0):
                    gpu_ms=ms.value, rounds=int(d.build_rounds), kernel_launches=int(d.kernel_launches))
         lib().mcrt_bvh_free(h)
         return out
+    finally:
+        lib().mcrt_destroy(ctx)
+
+
+def build_photon_octree_gpu(photons, max_photons_per_octree_leaf, scene_bounds, device=0):
+    """mcrt_octree_build: the octree construction of mcrt_photon_emit on the GPU, on caller photons.
+    -> (map arrays as build_photon_octree returns, gpu_ms)."""
+    photons = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 8)
+    bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64)
+    ctx = C.c_void_p()
+    rc = lib().mcrt_init(device, C.byref(ctx))
+    if rc:
+        raise McrtError(f"mcrt_init({device}) failed: {rc} (no CUDA device? there is no CPU fallback)")
+    try:
+        h, d, ms = C.c_void_p(), PhotonMapDesc(), C.c_double()
+        rc = lib().mcrt_octree_build(ctx, _ptr(photons), len(photons), int(max_photons_per_octree_leaf), _ptr(bounds),
+                                     C.byref(h), C.byref(d), C.byref(ms))
+        if rc:
+            raise McrtError(f"mcrt_octree_build failed ({rc}): {lib().mcrt_last_error(ctx).decode()}")
+        out = _map_arrays(d)
+        lib().mcrt_octree_free_host(h)
+        return out, ms.value
     finally:
         lib().mcrt_destroy(ctx)
 

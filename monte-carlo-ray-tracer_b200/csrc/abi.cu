@@ -98,6 +98,10 @@ struct mcrt_ctx
         std::vector<float> photons;
     } built_map[2];
     bool built_valid = false;
+    // maps built on the device by mcrt_photon_emit / mcrt_octree_build; host copies are made on demand
+    PhotonOctreeDevice built_dev[2];
+    bool built_host_current[2] = { false, false };
+    double photon_build_ms = 0.0;
     // emission pass inputs (device), set by mcrt_photon_emit around runWavefront
     const unsigned long long* d_emit_offsets = nullptr;
     const void* d_emit_flux = nullptr;
@@ -1220,25 +1224,59 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
     if (rc) { cleanup(); return rc; }
 
     const Counters& c = ctx->h_counters[0];
-    std::vector<float> photons[2];
+    const uint64_t n_stored[2] = { c.n_photons[0], c.n_photons[1] };
+    if (n_caustic) *n_caustic = n_stored[0];
+    if (n_global) *n_global = n_stored[1];
+    if (n_stored[0] >= 0xFFFFFFFFull || n_stored[1] >= 0xFFFFFFFFull) { cleanup(); ctx->error = "photon map with >= 2^32 photons unsupported"; return MCRT_ERR_UNSUPPORTED; }
+
+    // Octree<Photon> + LinearOctree::compact on the device, straight from the emission buffers into
+    // the layout k_knn walks: the photons never visit the host.
+    freeAll(ctx->photon_allocs);
+    ctx->has_photons = false; ctx->built_valid = false;
+    ctx->photon_build_ms = 0.0;
     for (int w = 0; w < 2; w++)
     {
-        photons[w].resize((size_t)c.n_photons[w] * 8);
-        if (c.n_photons[w])
-        {
-            cudaError_t e = cudaMemcpy(photons[w].data(), ctx->d_emit_photons[w], (size_t)c.n_photons[w] * 32, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) { cleanup(); ctx->error = cudaGetErrorString(e); return MCRT_ERR_CUDA; }
-        }
+        ctx->built_host_current[w] = false;
+        rc = buildPhotonOctreeOnDevice(ctx->d_emit_photons[w], (uint32_t)n_stored[w], params->scene_bounds, params->max_photons_per_octree_leaf,
+                                       ctx->sm_count, ctx->stream, ctx->photon_allocs, ctx->built_dev[w], ctx->error);
+        if (rc) { cleanup(); return rc; }
+        ctx->photon_map[w].octants = ctx->built_dev[w].octants;
+        ctx->photon_map[w].photons = ctx->built_dev[w].photons;
+        ctx->photon_map[w].n_octants = ctx->built_dev[w].n_octants;
+        ctx->photon_map[w].n_photons = ctx->built_dev[w].n_photons;
+        ctx->photon_build_ms += ctx->built_dev[w].gpu_ms;
     }
     cleanup();
-    if (n_caustic) *n_caustic = c.n_photons[0];
-    if (n_global) *n_global = c.n_photons[1];
-
-    for (int w = 0; w < 2; w++) buildHostOctree(photons[w], params->max_photons_per_octree_leaf, params->scene_bounds, ctx->built_map[w]);
+    if (params->k_nearest_photons > 1024) { ctx->error = "k_nearest_photons > 1024 unsupported"; return MCRT_ERR_UNSUPPORTED; }
+    ctx->k_nearest = params->k_nearest_photons;
+    ctx->direct_visualization = params->direct_visualization;
+    ctx->has_photons = true;
     ctx->built_valid = true;
-    mcrt_photon_map_desc d[2];
-    for (int w = 0; w < 2; w++) mcrt_photon_download(ctx, w, &d[w]);
-    return mcrt_photon_upload(ctx, &d[0], &d[1], params->k_nearest_photons, params->direct_visualization, nullptr);
+    if (stats) stats->gpu_ms_knn = ctx->photon_build_ms;   // emission pass: this field reports the octree build
+    return MCRT_OK;
+}
+
+// host copy of a device-built map (mcrt_photon_download, mcrt_octree_build)
+static int downloadBuiltMap(mcrt_ctx* ctx, const PhotonOctreeDevice& d, mcrt_ctx::HostPhotonMap& m)
+{
+    m = mcrt_ctx::HostPhotonMap();
+    std::vector<DeviceOctant> oct(d.n_octants);
+    m.octant_next.resize(d.n_octants);
+    m.photons.resize((size_t)d.n_photons * 8);
+    if (d.n_octants)
+    {
+        CK(cudaMemcpy(oct.data(), d.octants, oct.size() * sizeof(DeviceOctant), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(m.octant_next.data(), d.next_sibling, (size_t)d.n_octants * 4, cudaMemcpyDeviceToHost));
+    }
+    if (d.n_photons) CK(cudaMemcpy(m.photons.data(), d.photons, (size_t)d.n_photons * 32, cudaMemcpyDeviceToHost));
+    m.octant_bounds.resize(6 * (size_t)d.n_octants);
+    m.octant_start.resize(d.n_octants); m.octant_count.resize(d.n_octants); m.octant_leaf.resize(d.n_octants);
+    for (uint32_t i = 0; i < d.n_octants; i++)
+    {
+        for (int k = 0; k < 3; k++) { m.octant_bounds[6 * (size_t)i + k] = oct[i].bmin[k]; m.octant_bounds[6 * (size_t)i + 3 + k] = oct[i].bmax[k]; }
+        m.octant_start[i] = oct[i].start; m.octant_count[i] = oct[i].count; m.octant_leaf[i] = (uint8_t)oct[i].leaf;
+    }
+    return MCRT_OK;
 }
 
 static void describeHostMap(const mcrt_ctx::HostPhotonMap& m, mcrt_photon_map_desc* out)
@@ -1266,6 +1304,34 @@ int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photon
     return MCRT_OK;
 }
 
+int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf, const double* scene_bounds6,
+                      void** handle, mcrt_photon_map_desc* out, double* gpu_ms)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!handle || !out || !scene_bounds6 || max_photons_per_octree_leaf == 0 || (n && !photons) || n >= 0xFFFFFFFFull)
+    { ctx->error = "mcrt_octree_build: invalid arguments"; return MCRT_ERR_INVALID; }
+    *handle = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<void*> keep;
+    float4* d_in = nullptr;
+    if (n)
+    {
+        CK(cudaMalloc((void**)&d_in, n * 32));
+        keep.push_back(d_in);
+        if (cudaMemcpyAsync(d_in, photons, n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { freeAll(keep); ctx->error = "upload failed"; return MCRT_ERR_CUDA; }
+    }
+    PhotonOctreeDevice dev;
+    int rc = buildPhotonOctreeOnDevice(d_in, (uint32_t)n, scene_bounds6, max_photons_per_octree_leaf, ctx->sm_count, ctx->stream, keep, dev, ctx->error);
+    auto* m = new mcrt_ctx::HostPhotonMap();
+    if (rc == MCRT_OK) rc = downloadBuiltMap(ctx, dev, *m);
+    freeAll(keep);
+    if (rc != MCRT_OK) { delete m; return rc; }
+    describeHostMap(*m, out);
+    if (gpu_ms) *gpu_ms = dev.gpu_ms;
+    *handle = m;
+    return MCRT_OK;
+}
+
 void mcrt_octree_free_host(void* handle)
 {
     delete static_cast<mcrt_ctx::HostPhotonMap*>(handle);
@@ -1276,6 +1342,13 @@ int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out)
     if (!ctx) return MCRT_ERR_INVALID;
     if (!out || (which != 0 && which != 1)) { ctx->error = "mcrt_photon_download: invalid arguments"; return MCRT_ERR_INVALID; }
     if (!ctx->built_valid) { ctx->error = "no maps built by mcrt_photon_emit"; return MCRT_ERR_NO_PHOTONS; }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->built_host_current[which])
+    {
+        int rc = downloadBuiltMap(ctx, ctx->built_dev[which], ctx->built_map[which]);
+        if (rc) return rc;
+        ctx->built_host_current[which] = true;
+    }
     describeHostMap(ctx->built_map[which], out);
     return MCRT_OK;
 }

@@ -85,8 +85,30 @@ namespace
         uint32_t n_children, first_child;
         uint32_t vchild[8];   // bin group -> child node
         uint32_t cursor;      // scatter cursor into [begin, end)
-        uint32_t subtree, df, next_sibling, _pad;
+        uint32_t subtree, df, next_sibling, depth;
     };
+
+    // where a primitive's box comes from: [n][6] doubles, or photons (2 float4 each, position in
+    // {p0.w, p1.x, p1.y}) whose box is the point itself
+    struct BoxSource
+    {
+        const double* bounds;
+        const float4* points;
+    };
+
+    __device__ inline void loadBox(const BoxSource& src, uint32_t prim, double b[6])
+    {
+        if (src.points)
+        {
+            const float4 p0 = src.points[2 * (size_t)prim], p1 = src.points[2 * (size_t)prim + 1];
+            b[0] = b[3] = (double)p0.w; b[1] = b[4] = (double)p1.x; b[2] = b[5] = (double)p1.y;
+        }
+        else
+        {
+            const double* q = src.bounds + 6 * (size_t)prim;
+            for (int k = 0; k < 6; k++) b[k] = q[k];
+        }
+    }
 
     struct BuildCounters
     {
@@ -101,7 +123,7 @@ namespace
         c.plan = PLAN_NONE; c.axis[0] = c.axis[1] = 0; c.arb_n = 0; c.slot = 0; c.split[0] = c.split[1] = 0; c.split_round = NONE;
         c.n_children = 0; c.first_child = NONE;
         for (int k = 0; k < 8; k++) c.vchild[k] = NONE;
-        c.subtree = 1; c.df = 0; c.next_sibling = 0; c._pad = 0;
+        c.subtree = 1; c.df = 0; c.next_sibling = 0; c.depth = 0;
     }
 
     // BoundingBox::area (bounding-box.cpp:35-40) of a box held as keys
@@ -140,7 +162,7 @@ namespace
     }
 
     // centroid_extent.merge(s->BB().centroid()) over the node's primitives (bvh.cpp:175-180, 297-302)
-    __global__ void __launch_bounds__(256) k_extent(BNode* nodes, const uint32_t* idx, const uint32_t* node_of, const double* bounds, uint32_t n)
+    __global__ void __launch_bounds__(256) k_extent(BNode* nodes, const uint32_t* idx, const uint32_t* node_of, BoxSource src, uint32_t n)
     {
         const uint32_t stride = gridDim.x * blockDim.x;
         for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride)
@@ -153,7 +175,8 @@ namespace
             long long c[3] = {0, 0, 0};
             if (need)
             {
-                const double* b = bounds + 6 * (size_t)idx[p];
+                double b[6];
+                loadBox(src, idx[p], b);
                 for (int k = 0; k < 3; k++) c[k] = dkey((b[3 + k] + b[k]) / 2.0);   // BoundingBox::centroid
             }
             const uint32_t nd0 = __shfl_sync(FULL, nd, 0);
@@ -255,7 +278,7 @@ namespace
     }
 
     // bins[idx].first++; bins[idx].second.merge(s->BB()) (bvh.cpp:203-209, 325-335)
-    __global__ void __launch_bounds__(256) k_bin(const BNode* nodes, const uint32_t* idx, const uint32_t* node_of, const double* bounds,
+    __global__ void __launch_bounds__(256) k_bin(const BNode* nodes, const uint32_t* idx, const uint32_t* node_of, BoxSource src,
                                                   uint32_t n, Bin* bins, uint32_t bin_stride, uint32_t* bin_of, int B, uint32_t chunk)
     {
         extern __shared__ unsigned char smem_raw[];
@@ -280,7 +303,8 @@ namespace
                 __syncthreads();
                 for (uint32_t p = c0 + threadIdx.x; p < c1; p += blockDim.x)
                 {
-                    const double* b = bounds + 6 * (size_t)idx[p];
+                    double b[6];
+                    loadBox(src, idx[p], b);
                     const uint32_t bin = binOf(N, b, B);
                     bin_of[p] = bin;
                     binAccumulate(&sbins[bin], b);
@@ -302,7 +326,8 @@ namespace
                     const BNode& N = nodes[node_of[p]];
                     const bool open = (N.state == ST_ACTIVE) && (N.plan == PLAN_BIN2 || N.plan == PLAN_BIN4 || N.plan == PLAN_OCT);
                     if (!open) continue;
-                    const double* b = bounds + 6 * (size_t)idx[p];
+                    double b[6];
+                    loadBox(src, idx[p], b);
                     const uint32_t bin = binOf(N, b, B);
                     bin_of[p] = bin;
                     binAccumulate(&bins[(size_t)N.slot * bin_stride + bin], b);
@@ -313,7 +338,7 @@ namespace
 
     // BVH::arbitrarySplit (bvh.cpp:434-474): child = (position in S) % N; S is ordered by original
     // primitive index, so the position is the rank of the index inside the node. One block per node.
-    __global__ void __launch_bounds__(256) k_arb_bin(const BNode* nodes, const uint32_t* active, const uint32_t* idx, const double* bounds,
+    __global__ void __launch_bounds__(256) k_arb_bin(const BNode* nodes, const uint32_t* active, const uint32_t* idx, BoxSource src,
                                                       Bin* bins, uint32_t bin_stride, uint32_t* bin_of)
     {
         const BNode& N = nodes[active[blockIdx.x]];
@@ -337,7 +362,9 @@ namespace
             {
                 const uint32_t bin = rank % N.arb_n;
                 bin_of[p] = bin;
-                binAccumulate(&bins[(size_t)N.slot * bin_stride + bin], bounds + 6 * (size_t)mine);
+                double b[6];
+                loadBox(src, mine, b);
+                binAccumulate(&bins[(size_t)N.slot * bin_stride + bin], b);
             }
         }
     }
@@ -376,7 +403,8 @@ namespace
     constexpr int SPLIT_WARPS = 4;
     __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(BNode* nodes, const uint32_t* active, uint32_t n_active, const Bin* bins,
                                                                 uint32_t bin_stride, int B, uint32_t round, BuildCounters* counters,
-                                                                uint32_t* active_next, uint32_t node_capacity)
+                                                                uint32_t* active_next, uint32_t node_capacity, uint32_t leaf_max,
+                                                                uint32_t depth_cap)
     {
         extern __shared__ unsigned char smem_raw[];
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -484,7 +512,8 @@ namespace
             for (int d = 0; d < 3; d++) { C.bb[d] = g[v].mn[d]; C.bb[3 + d] = g[v].mx[d]; }
             C.begin = offset; C.end = offset + (uint32_t)g[v].count; C.cursor = offset;
             C.kind = N.kind;
-            C.state = (C.end - C.begin) <= LEAF_SURFACES ? ST_LEAF : ST_ACTIVE;
+            C.depth = N.depth + 1;
+            C.state = ((C.end - C.begin) <= leaf_max || C.depth >= depth_cap) ? ST_LEAF : ST_ACTIVE;
             if (plan == PLAN_OCT)
             {
                 // Octree::insert, octree.cpp:50-60
@@ -545,19 +574,20 @@ namespace
         }
     }
 
-    // every node's surface list is in original order: sort the leaves
-    __global__ void k_sort_leaves(const BNode* nodes, uint32_t n_nodes, uint32_t* idx)
+    // every node's surface list is in original order: rank-sort each leaf, one warp per node
+    __global__ void __launch_bounds__(128) k_sort_leaves(const BNode* nodes, uint32_t n_nodes, const uint32_t* idx, uint32_t* idx_out)
     {
-        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         if (i >= n_nodes) return;
         const BNode& N = nodes[i];
         if (N.state != ST_LEAF) return;
-        for (uint32_t a = N.begin + 1; a < N.end; a++)
+        const uint32_t begin = N.begin, end = N.end;
+        for (uint32_t a = begin + lane; a < end; a += 32)
         {
             const uint32_t v = idx[a];
-            uint32_t b = a;
-            while (b > N.begin && idx[b - 1] > v) { idx[b] = idx[b - 1]; b--; }
-            idx[b] = v;
+            uint32_t rank = 0;
+            for (uint32_t b = begin; b < end; b++) rank += idx[b] < v ? 1u : 0u;   // indices are unique
+            idx_out[begin + rank] = v;
         }
     }
 
@@ -600,6 +630,47 @@ namespace
         out_next[d] = N.next_sibling;
     }
 
+    // LinearOctree<Photon> in the layout k_knn walks (photon.cuh: DeviceOctant), depth-first order:
+    // tight box of the contained photons, [start, start+count) = all photons below the octant
+    // (LinearOctant::contained_data), children in octant order (linear-octree.cpp:201-244)
+    __global__ void k_emit_octants(const BNode* nodes, uint32_t n_nodes, DeviceOctant* out, uint32_t* out_next)
+    {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n_nodes) return;
+        const BNode& N = nodes[i];
+        DeviceOctant o;
+        for (int k = 0; k < 3; k++) { o.bmin[k] = keyd(N.bb[k]); o.bmax[k] = keyd(N.bb[3 + k]); }
+        o.start = N.begin; o.count = N.end - N.begin;
+        o.leaf = N.state == ST_LEAF ? 1u : 0u;
+        o.n_children = N.state == ST_INNER ? N.n_children : 0u;
+        for (uint32_t k = 0; k < 8; k++) o.children[k] = k < o.n_children ? nodes[N.first_child + k].df : OCTANT_NULL;
+        out[N.df] = o;
+        out_next[N.df] = N.next_sibling ? N.next_sibling : OCTANT_NULL;
+    }
+
+    __global__ void k_gather_points(const uint32_t* idx, const float4* in, float4* out, uint32_t n)
+    {
+        for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        {
+            const uint32_t src = idx[p];
+            out[2 * (size_t)p] = in[2 * (size_t)src]; out[2 * (size_t)p + 1] = in[2 * (size_t)src + 1];
+        }
+    }
+
+    // a leaf octant's box is the box of its own photons; for a single-leaf tree nobody has binned them
+    __global__ void k_root_leaf_box(BNode* nodes, const float4* points, uint32_t n)
+    {
+        if (blockIdx.x || threadIdx.x) return;
+        BNode& N = nodes[0];
+        for (int k = 0; k < 3; k++) { N.bb[k] = KEY_EMPTY_MIN; N.bb[3 + k] = KEY_EMPTY_MAX; }
+        for (uint32_t i = 0; i < n; i++)
+        {
+            const float4 p0 = points[2 * (size_t)i], p1 = points[2 * (size_t)i + 1];
+            const long long k3[3] = {dkey((double)p0.w), dkey((double)p1.x), dkey((double)p1.y)};
+            for (int k = 0; k < 3; k++) { N.bb[k] = k3[k] < N.bb[k] ? k3[k] : N.bb[k]; N.bb[3 + k] = k3[k] > N.bb[3 + k] ? k3[k] : N.bb[3 + k]; }
+        }
+    }
+
     struct DeviceBuffers
     {
         std::vector<void*> allocs;
@@ -612,6 +683,13 @@ namespace
             return static_cast<T*>(p);
         }
     };
+
+    struct CoreResult
+    {
+        BNode* d_nodes = nullptr;
+        uint32_t* d_idx = nullptr;     // final primitive order
+        uint32_t n_nodes = 0, rounds = 0, launches = 0;
+    };
 }
 
 #define BK(call)                                                                      \
@@ -619,6 +697,91 @@ namespace
         cudaError_t e_ = (call);                                                      \
         if (e_ != cudaSuccess) { error = std::string(#call) + ": " + cudaGetErrorString(e_); return MCRT_ERR_CUDA; } \
     } while (0)
+
+// The build rounds + leaf sort + depth-first numbering shared by the BVH and the photon octree.
+static int buildCore(DeviceBuffers& mem, BoxSource src, uint32_t n, const BNode& root, bool octree, int B, uint32_t bin_stride,
+                     uint32_t leaf_max, uint32_t depth_cap, uint32_t node_capacity, int sm_count, cudaStream_t s, cudaEvent_t ev_start,
+                     CoreResult& res, std::string& error)
+{
+    const uint32_t max_active = n / (leaf_max + 1) + 2;
+    uint32_t* d_idx[2] = {mem.get<uint32_t>(n), mem.get<uint32_t>(n)};
+    uint32_t* d_node_of[2] = {mem.get<uint32_t>(n), mem.get<uint32_t>(n)};
+    uint32_t* d_bin_of = mem.get<uint32_t>(n);
+    BNode* d_nodes = mem.get<BNode>(node_capacity);
+    uint32_t* d_active[2] = {mem.get<uint32_t>(max_active), mem.get<uint32_t>(max_active)};
+    Bin* d_bins = mem.get<Bin>((size_t)max_active * bin_stride);
+    BuildCounters* d_counters = mem.get<BuildCounters>(1);
+    if (!d_idx[0] || !d_idx[1] || !d_node_of[0] || !d_node_of[1] || !d_bin_of || !d_nodes || !d_active[0] || !d_active[1] || !d_bins || !d_counters)
+    { error = "hierarchy build: out of device memory"; return MCRT_ERR_CUDA; }
+
+    BK(cudaMemcpyAsync(d_nodes, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+    const int grid = sm_count * 8;
+    uint32_t launches = 0;
+    BK(cudaEventRecord(ev_start, s));   // allocations and the input copy stay outside the reported build time
+    k_init<<<grid, 256, 0, s>>>(d_idx[0], d_node_of[0], n); launches++;
+
+    const uint32_t zero_active = 0;
+    BuildCounters hc; hc.n_nodes = 1; hc.n_active_next = 0; hc._a = hc._b = 0;
+    BK(cudaMemcpyAsync(d_counters, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
+    BK(cudaMemcpyAsync(d_active[0], &zero_active, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+
+    const size_t split_smem = (size_t)SPLIT_WARPS * bin_stride * sizeof(Bin);
+    const size_t bin_smem = (size_t)bin_stride * sizeof(Bin);
+    if (split_smem > 48 * 1024) BK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem));
+    // k_bin chunk: every block handles contiguous chunks, large enough to amortise the shared bins
+    const uint32_t chunk = 4096;
+
+    std::vector<uint32_t> gen;   // node id boundaries per round
+    gen.push_back(0); gen.push_back(1);
+    uint32_t n_active = root.state == ST_ACTIVE ? 1u : 0u, round = 0;
+    int cur = 0;
+    while (n_active > 0)
+    {
+        if (n_active > max_active) { error = "hierarchy build: internal error (open node list overflow)"; return MCRT_ERR_CUDA; }
+        const size_t n_bins = (size_t)n_active * bin_stride;
+        k_init_bins<<<(unsigned)std::min<size_t>((n_bins + 255) / 256, (size_t)grid), 256, 0, s>>>(d_bins, n_bins); launches++;
+        if (!octree) { k_extent<<<grid, 256, 0, s>>>(d_nodes, d_idx[cur], d_node_of[cur], src, n); launches++; }
+        k_plan<<<(n_active + 127) / 128, 128, 0, s>>>(d_nodes, d_active[cur], n_active, B);
+        k_bin<<<grid, 256, bin_smem, s>>>(d_nodes, d_idx[cur], d_node_of[cur], src, n, d_bins, bin_stride, d_bin_of, B, chunk);
+        if (!octree) { k_arb_bin<<<n_active, 256, 0, s>>>(d_nodes, d_active[cur], d_idx[cur], src, d_bins, bin_stride, d_bin_of); launches++; }
+        k_split<<<(n_active + SPLIT_WARPS - 1) / SPLIT_WARPS, 32 * SPLIT_WARPS, split_smem, s>>>(
+            d_nodes, d_active[cur], n_active, d_bins, bin_stride, B, round, d_counters, d_active[cur ^ 1], node_capacity, leaf_max, depth_cap);
+        k_scatter<<<grid, 256, 0, s>>>(d_nodes, d_idx[cur], d_node_of[cur], d_bin_of, n, round, B, d_idx[cur ^ 1], d_node_of[cur ^ 1]);
+        launches += 4;
+        BK(cudaMemcpyAsync(&hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        BK(cudaStreamSynchronize(s));
+        BK(cudaGetLastError());
+        if (hc.n_nodes > node_capacity) { error = "hierarchy build: node pool overflow (degenerate input: coincident points?)"; return MCRT_ERR_UNSUPPORTED; }
+        n_active = hc.n_active_next;
+        gen.push_back(hc.n_nodes);
+        hc.n_active_next = 0;
+        BK(cudaMemcpyAsync(d_counters, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
+        cur ^= 1;
+        round++;
+        if (round > 4096) { error = "hierarchy build does not terminate (coincident centroids?)"; return MCRT_ERR_UNSUPPORTED; }
+    }
+    const uint32_t n_nodes = hc.n_nodes;
+
+    k_sort_leaves<<<(unsigned)(((size_t)n_nodes * 32 + 127) / 128), 128, 0, s>>>(d_nodes, n_nodes, d_idx[cur], d_idx[cur ^ 1]); launches++;
+    cur ^= 1;
+    for (size_t g = gen.size() - 1; g-- > 0;)
+        if (gen[g + 1] > gen[g]) { k_subtree<<<(gen[g + 1] - gen[g] + 127) / 128, 128, 0, s>>>(d_nodes, gen[g], gen[g + 1]); launches++; }
+    for (size_t g = 0; g + 1 < gen.size(); g++)
+        if (gen[g + 1] > gen[g]) { k_number<<<(gen[g + 1] - gen[g] + 127) / 128, 128, 0, s>>>(d_nodes, gen[g], gen[g + 1]); launches++; }
+    res.d_nodes = d_nodes; res.d_idx = d_idx[cur]; res.n_nodes = n_nodes; res.rounds = round; res.launches = launches;
+    return MCRT_OK;
+}
+
+static void initRoot(BNode& root, uint32_t n, uint32_t kind, uint32_t leaf_max)
+{
+    std::memset(&root, 0, sizeof(root));
+    for (int k = 0; k < 3; k++) { root.bb[k] = KEY_EMPTY_MIN; root.bb[3 + k] = KEY_EMPTY_MAX; root.cext[k] = KEY_EMPTY_MIN; root.cext[3 + k] = KEY_EMPTY_MAX; }
+    root.begin = 0; root.end = n; root.cursor = 0;
+    root.kind = kind;
+    root.state = n <= leaf_max ? ST_LEAF : ST_ACTIVE;
+    root.split_round = NONE; root.first_child = NONE; root.subtree = 1;
+    for (int k = 0; k < 8; k++) root.vchild[k] = NONE;
+}
 
 int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n, const double scene_bounds[6], int type, int bins_per_axis,
                      int sm_count, cudaStream_t s, BvhBuildResult& out, std::string& error)
@@ -635,29 +798,14 @@ int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n, const double sc
     DeviceBuffers mem;
     // SAH splits always have two non-empty sides (<= 2n-1 nodes); octree cells can chain single children
     const uint32_t node_capacity = (type == MCRT_BVH_OCTREE ? 4u : 2u) * n + 64u;
-    const uint32_t max_active = n / (LEAF_SURFACES + 1) + 2;
     double* d_bounds = mem.get<double>(6 * (size_t)n);
-    uint32_t* d_idx[2] = {mem.get<uint32_t>(n), mem.get<uint32_t>(n)};
-    uint32_t* d_node_of[2] = {mem.get<uint32_t>(n), mem.get<uint32_t>(n)};
-    uint32_t* d_bin_of = mem.get<uint32_t>(n);
-    BNode* d_nodes = mem.get<BNode>(node_capacity);
-    uint32_t* d_active[2] = {mem.get<uint32_t>(max_active), mem.get<uint32_t>(max_active)};
-    Bin* d_bins = mem.get<Bin>((size_t)max_active * bin_stride);
-    BuildCounters* d_counters = mem.get<BuildCounters>(1);
-    if (!d_bounds || !d_idx[0] || !d_idx[1] || !d_node_of[0] || !d_node_of[1] || !d_bin_of || !d_nodes || !d_active[0] || !d_active[1] || !d_bins || !d_counters)
-    { error = "mcrt_bvh_build: out of device memory"; return MCRT_ERR_CUDA; }
-
+    if (!d_bounds) { error = "mcrt_bvh_build: out of device memory"; return MCRT_ERR_CUDA; }
     BK(cudaMemcpyAsync(d_bounds, prim_bounds_host, 6 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
 
     // root (bvh.cpp:19-20, 31-32, 38-39, 46-49)
     BNode root;
-    std::memset(&root, 0, sizeof(root));
-    for (int k = 0; k < 3; k++) { root.bb[k] = dkey(scene_bounds[k]); root.bb[3 + k] = dkey(scene_bounds[3 + k]); root.cext[k] = KEY_EMPTY_MIN; root.cext[3 + k] = KEY_EMPTY_MAX; }
-    root.begin = 0; root.end = n; root.cursor = 0;
-    root.kind = type == MCRT_BVH_OCTREE ? KIND_OCT : (type == MCRT_BVH_BINARY_SAH ? KIND_BIN : KIND_QUAT);
-    root.state = n <= LEAF_SURFACES ? ST_LEAF : ST_ACTIVE;
-    root.split_round = NONE; root.first_child = NONE; root.subtree = 1;
-    for (int k = 0; k < 8; k++) root.vchild[k] = NONE;
+    initRoot(root, n, type == MCRT_BVH_OCTREE ? KIND_OCT : (type == MCRT_BVH_BINARY_SAH ? KIND_BIN : KIND_QUAT), LEAF_SURFACES);
+    for (int k = 0; k < 3; k++) { root.bb[k] = dkey(scene_bounds[k]); root.bb[3 + k] = dkey(scene_bounds[3 + k]); }
     if (type == MCRT_BVH_OCTREE)
     {
         const double dims[3] = {scene_bounds[3] - scene_bounds[0], scene_bounds[4] - scene_bounds[1], scene_bounds[5] - scene_bounds[2]};
@@ -681,71 +829,22 @@ int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n, const double sc
                 }
         }
     }
-    BK(cudaMemcpyAsync(d_nodes, &root, sizeof(root), cudaMemcpyHostToDevice, s));
 
     cudaEvent_t ev0, ev1;
     BK(cudaEventCreate(&ev0)); BK(cudaEventCreate(&ev1));
     struct EventGuard { cudaEvent_t a, b; ~EventGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{ev0, ev1};
-
-    const int grid = sm_count * 8;
-    uint32_t launches = 0;
-    BK(cudaEventRecord(ev0, s));
-    k_init<<<grid, 256, 0, s>>>(d_idx[0], d_node_of[0], n); launches++;
-
-    const uint32_t zero_active = 0;
-    BuildCounters hc; hc.n_nodes = 1; hc.n_active_next = 0; hc._a = hc._b = 0;
-    BK(cudaMemcpyAsync(d_counters, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
-    BK(cudaMemcpyAsync(d_active[0], &zero_active, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-
-    const size_t split_smem = (size_t)SPLIT_WARPS * bin_stride * sizeof(Bin);
-    const size_t bin_smem = (size_t)bin_stride * sizeof(Bin);
-    if (split_smem > 48 * 1024) BK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem));
-    // k_bin chunk: every block handles contiguous chunks, large enough to amortise the shared bins
-    const uint32_t chunk = 4096;
-
-    std::vector<uint32_t> gen;   // node id boundaries per round
-    gen.push_back(0); gen.push_back(1);
-    uint32_t n_active = root.state == ST_ACTIVE ? 1u : 0u, round = 0;
-    int cur = 0;
-    while (n_active > 0)
-    {
-        if (n_active > max_active) { error = "mcrt_bvh_build: internal error (open node list overflow)"; return MCRT_ERR_CUDA; }
-        const size_t n_bins = (size_t)n_active * bin_stride;
-        k_init_bins<<<(unsigned)std::min<size_t>((n_bins + 255) / 256, (size_t)grid), 256, 0, s>>>(d_bins, n_bins); launches++;
-        if (type != MCRT_BVH_OCTREE) { k_extent<<<grid, 256, 0, s>>>(d_nodes, d_idx[cur], d_node_of[cur], d_bounds, n); launches++; }
-        k_plan<<<(n_active + 127) / 128, 128, 0, s>>>(d_nodes, d_active[cur], n_active, B);
-        k_bin<<<grid, 256, bin_smem, s>>>(d_nodes, d_idx[cur], d_node_of[cur], d_bounds, n, d_bins, bin_stride, d_bin_of, B, chunk);
-        if (type != MCRT_BVH_OCTREE) { k_arb_bin<<<n_active, 256, 0, s>>>(d_nodes, d_active[cur], d_idx[cur], d_bounds, d_bins, bin_stride, d_bin_of); launches++; }
-        k_split<<<(n_active + SPLIT_WARPS - 1) / SPLIT_WARPS, 32 * SPLIT_WARPS, split_smem, s>>>(
-            d_nodes, d_active[cur], n_active, d_bins, bin_stride, B, round, d_counters, d_active[cur ^ 1], node_capacity);
-        k_scatter<<<grid, 256, 0, s>>>(d_nodes, d_idx[cur], d_node_of[cur], d_bin_of, n, round, B, d_idx[cur ^ 1], d_node_of[cur ^ 1]);
-        launches += 5;
-        BK(cudaMemcpyAsync(&hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
-        BK(cudaStreamSynchronize(s));
-        BK(cudaGetLastError());
-        n_active = hc.n_active_next;
-        gen.push_back(hc.n_nodes);
-        hc.n_active_next = 0;
-        BK(cudaMemcpyAsync(d_counters, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
-        cur ^= 1;
-        round++;
-        if (round > 4096) { error = "mcrt_bvh_build: build does not terminate (coincident centroids?)"; return MCRT_ERR_UNSUPPORTED; }
-    }
-    const uint32_t n_nodes = hc.n_nodes;
-    if (n_nodes > node_capacity) { error = "mcrt_bvh_build: internal error (node pool overflow)"; return MCRT_ERR_CUDA; }
-
-    k_sort_leaves<<<(n_nodes + 127) / 128, 128, 0, s>>>(d_nodes, n_nodes, d_idx[cur]); launches++;
-    for (size_t g = gen.size() - 1; g-- > 0;)
-        if (gen[g + 1] > gen[g]) { k_subtree<<<(gen[g + 1] - gen[g] + 127) / 128, 128, 0, s>>>(d_nodes, gen[g], gen[g + 1]); launches++; }
-    for (size_t g = 0; g + 1 < gen.size(); g++)
-        if (gen[g + 1] > gen[g]) { k_number<<<(gen[g + 1] - gen[g] + 127) / 128, 128, 0, s>>>(d_nodes, gen[g], gen[g + 1]); launches++; }
-
-    double* d_out_bounds = mem.get<double>(6 * (size_t)n_nodes);
-    uint32_t* d_out_first = mem.get<uint32_t>(n_nodes);
-    uint32_t* d_out_count = mem.get<uint32_t>(n_nodes);
-    uint32_t* d_out_next = mem.get<uint32_t>(n_nodes);
+    double* d_out_bounds = mem.get<double>(6 * (size_t)node_capacity);
+    uint32_t* d_out_first = mem.get<uint32_t>(node_capacity);
+    uint32_t* d_out_count = mem.get<uint32_t>(node_capacity);
+    uint32_t* d_out_next = mem.get<uint32_t>(node_capacity);
     if (!d_out_bounds || !d_out_first || !d_out_count || !d_out_next) { error = "mcrt_bvh_build: out of device memory"; return MCRT_ERR_CUDA; }
-    k_emit<<<(n_nodes + 127) / 128, 128, 0, s>>>(d_nodes, n_nodes, d_out_bounds, d_out_first, d_out_count, d_out_next); launches++;
+    CoreResult core;
+    BoxSource src; src.bounds = d_bounds; src.points = nullptr;
+    const int rc = buildCore(mem, src, n, root, type == MCRT_BVH_OCTREE, B, bin_stride, LEAF_SURFACES, 0xFFFFFFFFu, node_capacity, sm_count, s, ev0, core, error);
+    if (rc != MCRT_OK) return rc;
+    const uint32_t n_nodes = core.n_nodes;
+
+    k_emit<<<(n_nodes + 127) / 128, 128, 0, s>>>(core.d_nodes, n_nodes, d_out_bounds, d_out_first, d_out_count, d_out_next);
     BK(cudaEventRecord(ev1, s));
 
     out.node_bounds.resize(6 * (size_t)n_nodes);
@@ -755,14 +854,64 @@ int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n, const double sc
     BK(cudaMemcpyAsync(out.node_first_prim.data(), d_out_first, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     BK(cudaMemcpyAsync(out.node_prim_count.data(), d_out_count, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     BK(cudaMemcpyAsync(out.node_next_sibling.data(), d_out_next, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    BK(cudaMemcpyAsync(out.prim_order.data(), d_idx[cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    BK(cudaMemcpyAsync(out.prim_order.data(), core.d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     BK(cudaStreamSynchronize(s));
     BK(cudaGetLastError());
     float ms = 0.f;
     BK(cudaEventElapsedTime(&ms, ev0, ev1));
     out.gpu_ms = ms;
-    out.iterations = round;
-    out.kernel_launches = launches;
+    out.iterations = core.rounds;
+    out.kernel_launches = core.launches + 1;
+    return MCRT_OK;
+}
+
+// Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244) on
+// photons already in device memory: the same rounds with 8 bins = octants of the node's cell, a
+// node is internal iff it holds more than max_node_data photons (and sits above level 64, the
+// guard the host builder has too), boxes = tight boxes of the contained photons.
+int buildPhotonOctreeOnDevice(const float4* d_photons, uint32_t n, const double cell[6], uint32_t max_node_data, int sm_count,
+                              cudaStream_t s, std::vector<void*>& keep, PhotonOctreeDevice& out, std::string& error)
+{
+    out = PhotonOctreeDevice();
+    if (n == 0) return MCRT_OK;
+    if (!d_photons || !cell || max_node_data == 0) { error = "photon octree: invalid arguments"; return MCRT_ERR_INVALID; }
+    DeviceBuffers mem;
+    // Node pool: real maps have ~n / (max_node_data / 4) octants (water_caustics: 12.3 M photons, 186 k
+    // octants at 200 per leaf); 16x that plus slack, never more than the 4n + 64 of the BVH octree.
+    // Exhausting it (adversarial input) fails the build with an error, it does not corrupt memory.
+    const uint64_t cap64 = std::min<uint64_t>(4ull * n + 64, 16ull * n / std::max<uint32_t>(1u, max_node_data / 4u) + 65536ull);
+    const uint32_t node_capacity = (uint32_t)std::min<uint64_t>(cap64, 0x7FFFFFFFull);
+    BNode root;
+    initRoot(root, n, KIND_OCT, max_node_data);
+    for (int k = 0; k < 6; k++) root.cube[k] = cell[k];
+
+    cudaEvent_t ev0, ev1;
+    BK(cudaEventCreate(&ev0)); BK(cudaEventCreate(&ev1));
+    struct EventGuard { cudaEvent_t a, b; ~EventGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{ev0, ev1};
+    CoreResult core;
+    BoxSource src; src.bounds = nullptr; src.points = d_photons;
+    const int rc = buildCore(mem, src, n, root, true, 8, 8, max_node_data, 64, node_capacity, sm_count, s, ev0, core, error);
+    if (rc != MCRT_OK) return rc;
+    if (core.n_nodes == 1) k_root_leaf_box<<<1, 32, 0, s>>>(core.d_nodes, d_photons, n);
+
+    DeviceOctant* d_oct = nullptr; uint32_t* d_next = nullptr; float4* d_sorted = nullptr;
+    if (cudaMalloc((void**)&d_oct, (size_t)core.n_nodes * sizeof(DeviceOctant)) != cudaSuccess ||
+        cudaMalloc((void**)&d_next, (size_t)core.n_nodes * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&d_sorted, (size_t)n * 2 * sizeof(float4)) != cudaSuccess)
+    {
+        cudaFree(d_oct); cudaFree(d_next); cudaFree(d_sorted);
+        error = "photon octree: out of device memory"; return MCRT_ERR_CUDA;
+    }
+    keep.push_back(d_oct); keep.push_back(d_next); keep.push_back(d_sorted);
+    k_emit_octants<<<(core.n_nodes + 127) / 128, 128, 0, s>>>(core.d_nodes, core.n_nodes, d_oct, d_next);
+    k_gather_points<<<sm_count * 8, 256, 0, s>>>(core.d_idx, d_photons, d_sorted, n);
+    BK(cudaEventRecord(ev1, s));
+    BK(cudaStreamSynchronize(s));
+    BK(cudaGetLastError());
+    float ms = 0.f;
+    BK(cudaEventElapsedTime(&ms, ev0, ev1));
+    out.octants = d_oct; out.next_sibling = d_next; out.photons = d_sorted;
+    out.n_octants = core.n_nodes; out.n_photons = n; out.gpu_ms = ms; out.rounds = core.rounds;
     return MCRT_OK;
 }
 }

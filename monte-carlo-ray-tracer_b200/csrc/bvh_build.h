@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include "photon.cuh"
+
 namespace mcrt
 {
     struct BvhBuildResult
@@ -19,6 +21,22 @@ namespace mcrt
         uint32_t iterations = 0;      // breadth-first build rounds
         uint32_t kernel_launches = 0;
     };
+
+    // LinearOctree<Photon> built on the device, in the layout k_knn walks; memory is pushed to `keep`
+    struct PhotonOctreeDevice
+    {
+        const DeviceOctant* octants = nullptr;
+        const uint32_t* next_sibling = nullptr;   // LinearOctant::next_sibling (OCTANT_NULL terminated), for downloads
+        const float4* photons = nullptr;          // LinearOctree::ordered_data, 2 float4 per photon
+        uint32_t n_octants = 0, rounds = 0;
+        uint64_t n_photons = 0;
+        double gpu_ms = 0.0;
+    };
+
+    // d_photons: device, 2 float4 per photon as k_emit_shade stores them; cell: the root Octree box
+    int buildPhotonOctreeOnDevice(const float4* d_photons, uint32_t n_photons, const double cell[6], uint32_t max_node_data,
+                                  int sm_count, cudaStream_t stream, std::vector<void*>& keep, PhotonOctreeDevice& out,
+                                  std::string& error);
 
     // type: MCRT_BVH_*; returns an mcrt_status code, message in `error`
     int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n_prims, const double scene_bounds[6], int type,

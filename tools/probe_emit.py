@@ -20,10 +20,10 @@ for mode in a.modes.split(","):
                         max_photons_per_octree_leaf=int(params[2]), k_nearest_photons=50, scene_bounds=params[3:9]))
     wall = time.time() - t
     st = pm.last_stats
-    nc, ng = pm._maps[0]["photons"].size // 8, pm._maps[1]["photons"].size // 8
-    print(f"{mode} emit: emissions={int(a.emissions * a.caustic_factor)} photon_rays={st['extension_rays']} gpu_ms={st['gpu_ms_total']:.1f} "
-          f"({st['extension_rays'] / st['gpu_ms_total'] / 1e3:.1f} Mray/s) wall_incl_octree_build_and_upload={wall:.2f}s caustic={nc} global={ng} "
-          f"octants={pm._maps[0]['octant_leaf'].size}+{pm._maps[1]['octant_leaf'].size} iters={st['wavefront_iterations']}", flush=True)
+    nc, ng = pm.n_photons
+    print(f"{mode} emit: emissions={int(a.emissions * a.caustic_factor)} photon_rays={st['extension_rays']} emission_gpu_ms={st['gpu_ms_total']:.1f} "
+          f"({st['extension_rays'] / st['gpu_ms_total'] / 1e3:.1f} Mray/s) octree_build_gpu_ms={st['gpu_ms_knn']:.1f} "
+          f"wall_whole_photon_pass={wall:.3f}s caustic={nc} global={ng} iters={st['wavefront_iterations']}", flush=True)
     pm.set_option("stage_timing", 1)
     for r in range(2):
         img = pm.render_rows(cam); st = pm.last_stats
