@@ -231,17 +231,14 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
  * valid until the next mcrt_photon_emit / mcrt_destroy. */
 int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out);
 
-/* The octree construction step of mcrt_photon_emit alone, on caller photons (host only, no GPU
- * needed): Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81,
- * linear-octree.cpp:201-244). photons: [n][8] floats {flux.xyz, pos.xyz, phi, theta}. *out points
- * into memory owned by *handle; release with mcrt_octree_free_host. */
-int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf,
-                           const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out);
-void mcrt_octree_free_host(void* handle);
-/* The same construction on the GPU (what mcrt_photon_emit runs on its emission buffers): same
- * octants, same photon order as mcrt_octree_build_host. Release *handle with mcrt_octree_free_host. */
+/* The octree construction step of mcrt_photon_emit alone, on caller photons: Octree<Photon>
+ * insertion + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244) on the GPU.
+ * photons: HOST, [n][8] floats {flux.xyz, pos.xyz, phi, theta} (copied to the device); the result
+ * (same octants as the reference's LinearOctree; photons of a leaf in input order) is copied back:
+ * *out points into host memory owned by *handle, release it with mcrt_octree_free. */
 int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf,
                       const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out, double* gpu_ms);
+void mcrt_octree_free(void* handle);
 
 /* SURVEY.md §8f-4 ("next", image half): Image::save (source/camera/image.cpp:37-51) without the file:
  * auto exposure (getExposure, image.cpp:63-73: histogram median -> 0.5), tone-mapping operator

@@ -26,11 +26,11 @@ NO_PRIM = 0xFFFFFFFF
 
 ABI_SYMBOLS = [
     "mcrt_abi_version", "mcrt_init", "mcrt_destroy", "mcrt_last_error", "mcrt_scene_upload",
-    "mcrt_photon_upload", "mcrt_photon_emit", "mcrt_photon_download", "mcrt_octree_build_host",
-    "mcrt_octree_free_host", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
+    "mcrt_photon_upload", "mcrt_photon_emit", "mcrt_photon_download", "mcrt_octree_build",
+    "mcrt_octree_free", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
-    "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev", "mcrt_octree_build",
+    "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
 ]
 
 
@@ -173,11 +173,10 @@ def lib():
         L.mcrt_photon_emit.argtypes = [C.c_void_p, C.POINTER(PhotonEmitParams), C.c_int, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64), C.POINTER(Stats)]
         L.mcrt_photon_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(PhotonMapDesc)]
-        L.mcrt_octree_build_host.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PhotonMapDesc)]
         L.mcrt_octree_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p),
                                         C.POINTER(PhotonMapDesc), C.POINTER(C.c_double)]
-        L.mcrt_octree_free_host.argtypes = [C.c_void_p]
-        L.mcrt_octree_free_host.restype = None
+        L.mcrt_octree_free.argtypes = [C.c_void_p]
+        L.mcrt_octree_free.restype = None
         render_args = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_render_rows.argtypes = render_args
@@ -642,53 +641,9 @@ def _map_arrays(d):
             "photons": arr(d.photons, C.c_float, 8 * npn, np.float32)}
 
 
-def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds):
-    """Host-only octree construction of mcrt_photon_emit (Octree<Photon> + LinearOctree::compact)."""
-    photons = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 8)
-    bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64)
-    h, d = C.c_void_p(), PhotonMapDesc()
-    rc = lib().mcrt_octree_build_host(_ptr(photons), len(photons), int(max_photons_per_octree_leaf), _ptr(bounds), C.byref(h), C.byref(d))
-    if rc:
-        raise McrtError(f"mcrt_octree_build_host failed: {rc}")
-    out = _map_arrays(d)
-    lib().mcrt_octree_free_host(h)
-    return out
-
-
-def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis=0, device=0):
-    """mcrt_bvh_build: the reference's BVH (bvh.cpp:13-78) over primitive boxes, built on the GPU.
-    -> dict(node_bounds [n,6], node_first_prim, node_prim_count, node_next_sibling, prim_order, gpu_ms, rounds)."""
-    prim_bounds = np.ascontiguousarray(prim_bounds, dtype=np.float64).reshape(-1, 6)
-    scene_bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64).reshape(6)
-    code = BVH_TYPES[bvh_type.lower()] if isinstance(bvh_type, str) else int(bvh_type)
-    ctx = C.c_void_p()
-    rc = lib().mcrt_init(device, C.byref(ctx))
-    if rc:
-        raise McrtError(f"mcrt_init({device}) failed: {rc} (no CUDA device? there is no CPU fallback)")
-    try:
-        h, d, ms = C.c_void_p(), BvhDesc(), C.c_double()
-        rc = lib().mcrt_bvh_build(ctx, _ptr(prim_bounds), len(prim_bounds), _ptr(scene_bounds), code, int(bins_per_axis),
-                                  C.byref(h), C.byref(d), C.byref(ms))
-        if rc:
-            raise McrtError(f"mcrt_bvh_build failed ({rc}): {lib().mcrt_last_error(ctx).decode()}")
-
-        def arr(ptr, count, dtype):
-            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype).copy()
-        out = dict(node_bounds=arr(d.node_bounds, d.n_nodes * 6, np.float64).reshape(-1, 6),
-                   node_first_prim=arr(d.node_first_prim, d.n_nodes, np.uint32),
-                   node_prim_count=arr(d.node_prim_count, d.n_nodes, np.uint32),
-                   node_next_sibling=arr(d.node_next_sibling, d.n_nodes, np.uint32),
-                   prim_order=arr(d.prim_order, d.n_prims, np.uint32),
-                   gpu_ms=ms.value, rounds=int(d.build_rounds), kernel_launches=int(d.kernel_launches))
-        lib().mcrt_bvh_free(h)
-        return out
-    finally:
-        lib().mcrt_destroy(ctx)
-
-
-def build_photon_octree_gpu(photons, max_photons_per_octree_leaf, scene_bounds, device=0):
+def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds, device=0):
     """mcrt_octree_build: the octree construction of mcrt_photon_emit on the GPU, on caller photons.
-    -> (map arrays as build_photon_octree returns, gpu_ms)."""
+    -> (dict of octant_bounds, octant_start, octant_count, octant_next, octant_leaf, photons; gpu_ms)."""
     photons = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 8)
     bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64)
     ctx = C.c_void_p()
@@ -702,7 +657,7 @@ def build_photon_octree_gpu(photons, max_photons_per_octree_leaf, scene_bounds, 
         if rc:
             raise McrtError(f"mcrt_octree_build failed ({rc}): {lib().mcrt_last_error(ctx).decode()}")
         out = _map_arrays(d)
-        lib().mcrt_octree_free_host(h)
+        lib().mcrt_octree_free(h)
         return out, ms.value
     finally:
         lib().mcrt_destroy(ctx)

@@ -7,7 +7,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "mcrt_abi.h"
@@ -721,180 +720,6 @@ namespace
 
     // ---------------------------------------------------------------------------------------
     // Octree<Photon> + LinearOctree::compact on the host (octree.cpp:34-81, linear-octree.cpp:201-244).
-    // The reference inserts photons one by one; a node ends up internal exactly when more than
-    // max_node_data photons fall into its box, and child boxes are derived from the parent's box by
-    // fixed arithmetic, so the finished tree is a function of the photon set alone. This builder
-    // produces that tree top-down: partition the node's photons into octants (stable counting sort),
-    // recurse in octant order = the DFS order compact() emits.
-    struct OctreeBuilder
-    {
-        const float* in;            // photons, 8 floats each
-        uint32_t max_node_data;
-        mcrt_ctx::HostPhotonMap* out;
-        std::vector<float> scratch;
-
-        // photons [begin, end) of `data` belong to this node; returns the node's tight bounds
-        void build(std::vector<float>& data, uint64_t begin, uint64_t end, const double* bmin, const double* bmax, bool last, int depth = 0)
-        {
-            const uint64_t count = end - begin;
-            const uint32_t idx = (uint32_t)out->octant_leaf.size();
-            // (the reference recurses without bound when > max_node_data photons coincide; stop at 64 levels)
-            const bool split = count > max_node_data && depth < 64;
-            out->octant_leaf.push_back(split ? 0 : 1);
-            out->octant_start.push_back(begin);
-            out->octant_count.push_back(count);
-            out->octant_next.push_back(0xFFFFFFFFu);
-            out->octant_bounds.resize(out->octant_bounds.size() + 6);
-            double lo[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
-            double hi[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
-            for (uint64_t i = begin; i < end; i++)
-                for (int c = 0; c < 3; c++)
-                {
-                    const double v = (double)data[8 * i + 3 + c];
-                    if (lo[c] > v) lo[c] = v;
-                    if (hi[c] < v) hi[c] = v;
-                }
-            if (split)
-            {
-                // BoundingBox::centroid / dimensions (bounding-box.cpp:25-33), child boxes octree.cpp:51-60
-                double centroid[3], half[3];
-                for (int c = 0; c < 3; c++) { centroid[c] = (bmax[c] + bmin[c]) / 2.0; half[c] = (bmax[c] - bmin[c]) / 2.0; }
-                uint64_t counts[8] = { 0 }, starts[9];
-                auto octantOf = [&](const float* ph)
-                {
-                    int o = 0;
-                    for (int c = 0; c < 3; c++) if ((double)ph[3 + c] >= centroid[c]) o |= (4 >> c);   // octree.cpp:73-79
-                    return o;
-                };
-                for (uint64_t i = begin; i < end; i++) counts[octantOf(&data[8 * i])]++;
-                starts[0] = begin;
-                for (int o = 0; o < 8; o++) starts[o + 1] = starts[o] + counts[o];
-                scratch.resize(8 * count);
-                uint64_t cursor[8];
-                for (int o = 0; o < 8; o++) cursor[o] = starts[o] - begin;
-                for (uint64_t i = begin; i < end; i++)
-                {
-                    const int o = octantOf(&data[8 * i]);
-                    std::memcpy(&scratch[8 * cursor[o]++], &data[8 * i], 32);
-                }
-                std::memcpy(&data[8 * begin], scratch.data(), 32 * count);
-                int last_used = -1;
-                for (int o = 0; o < 8; o++) if (counts[o]) last_used = o;
-                for (int o = 0; o < 8; o++)
-                {
-                    if (!counts[o]) continue;   // empty leaves are dropped (linear-octree.cpp:222-229)
-                    double cmin[3], cmax[3];
-                    for (int c = 0; c < 3; c++)
-                    {
-                        const double new_origin = centroid[c] + half[c] * ((o & (4 >> c)) ? 0.5 : -0.5);
-                        const double h = half[c] * 0.5;
-                        cmin[c] = new_origin - h; cmax[c] = new_origin + h;
-                    }
-                    build(data, starts[o], starts[o + 1], cmin, cmax, o == last_used, depth + 1);
-                }
-            }
-            for (int c = 0; c < 3; c++) { out->octant_bounds[6 * idx + c] = lo[c]; out->octant_bounds[6 * idx + 3 + c] = hi[c]; }
-            out->octant_next[idx] = last ? 0xFFFFFFFFu : (uint32_t)out->octant_leaf.size();
-        }
-    };
-
-    // Parallel front end: the top two levels are partitioned serially, the (up to 64) subtrees are
-    // built by worker threads into fragments with local node indices, then concatenated in octant
-    // (= depth-first) order with the sibling links rebased. Same tree as the serial builder.
-    struct OctreeFragment
-    {
-        mcrt_ctx::HostPhotonMap map;   // photons unused
-    };
-
-    void appendFragment(mcrt_ctx::HostPhotonMap& dst, const mcrt_ctx::HostPhotonMap& src, bool last)
-    {
-        const uint32_t offset = (uint32_t)dst.octant_leaf.size();
-        dst.octant_bounds.insert(dst.octant_bounds.end(), src.octant_bounds.begin(), src.octant_bounds.end());
-        dst.octant_start.insert(dst.octant_start.end(), src.octant_start.begin(), src.octant_start.end());
-        dst.octant_count.insert(dst.octant_count.end(), src.octant_count.begin(), src.octant_count.end());
-        dst.octant_leaf.insert(dst.octant_leaf.end(), src.octant_leaf.begin(), src.octant_leaf.end());
-        for (uint32_t v : src.octant_next) dst.octant_next.push_back(v == 0xFFFFFFFFu ? v : v + offset);
-        // the fragment's root was built as "last"; give it its real sibling link
-        dst.octant_next[offset] = last ? 0xFFFFFFFFu : (uint32_t)dst.octant_leaf.size();
-    }
-
-    void buildSubtreeParallel(std::vector<float>& data, uint64_t begin, uint64_t end, const double* bmin, const double* bmax,
-                              uint32_t max_node_data, int depth, mcrt_ctx::HostPhotonMap& out)
-    {
-        const uint64_t count = end - begin;
-        // MCRT_OCTREE_PAR_MIN: test hook to push small inputs through the parallel path
-        static const uint64_t par_min = []() { const char* e = std::getenv("MCRT_OCTREE_PAR_MIN"); return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)200000; }();
-        if (depth >= 2 || count <= max_node_data || count < par_min)
-        {
-            OctreeBuilder b;
-            b.in = data.data(); b.max_node_data = max_node_data; b.out = &out;
-            b.build(data, begin, end, bmin, bmax, true, depth);
-            return;
-        }
-        // this node (internal): bounds over its photons, octant partition exactly as OctreeBuilder::build
-        double lo[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
-        double hi[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
-        double centroid[3], half[3];
-        for (int c = 0; c < 3; c++) { centroid[c] = (bmax[c] + bmin[c]) / 2.0; half[c] = (bmax[c] - bmin[c]) / 2.0; }
-        auto octantOf = [&](const float* ph)
-        {
-            int o = 0;
-            for (int c = 0; c < 3; c++) if ((double)ph[3 + c] >= centroid[c]) o |= (4 >> c);
-            return o;
-        };
-        uint64_t counts[8] = { 0 }, starts[9];
-        for (uint64_t i = begin; i < end; i++)
-        {
-            for (int c = 0; c < 3; c++) { const double v = (double)data[8 * i + 3 + c]; if (lo[c] > v) lo[c] = v; if (hi[c] < v) hi[c] = v; }
-            counts[octantOf(&data[8 * i])]++;
-        }
-        starts[0] = begin;
-        for (int o = 0; o < 8; o++) starts[o + 1] = starts[o] + counts[o];
-        {
-            std::vector<float> scratch(8 * count);
-            uint64_t cursor[8];
-            for (int o = 0; o < 8; o++) cursor[o] = starts[o] - begin;
-            for (uint64_t i = begin; i < end; i++) std::memcpy(&scratch[8 * cursor[octantOf(&data[8 * i])]++], &data[8 * i], 32);
-            std::memcpy(&data[8 * begin], scratch.data(), 32 * count);
-        }
-        mcrt_ctx::HostPhotonMap frag[8];
-        std::vector<std::thread> workers;
-        for (int o = 0; o < 8; o++)
-        {
-            if (!counts[o]) continue;
-            workers.emplace_back([&, o]()
-            {
-                double cmin[3], cmax[3];
-                for (int c = 0; c < 3; c++)
-                {
-                    const double new_origin = centroid[c] + half[c] * ((o & (4 >> c)) ? 0.5 : -0.5);
-                    const double h = half[c] * 0.5;
-                    cmin[c] = new_origin - h; cmax[c] = new_origin + h;
-                }
-                buildSubtreeParallel(data, starts[o], starts[o + 1], cmin, cmax, max_node_data, depth + 1, frag[o]);
-            });
-        }
-        for (auto& w : workers) w.join();
-        out.octant_leaf.push_back(0);
-        out.octant_start.push_back(begin);
-        out.octant_count.push_back(count);
-        out.octant_next.push_back(0xFFFFFFFFu);
-        for (int c = 0; c < 3; c++) out.octant_bounds.push_back(lo[c]);
-        for (int c = 0; c < 3; c++) out.octant_bounds.push_back(hi[c]);
-        int last_used = -1;
-        for (int o = 0; o < 8; o++) if (counts[o]) last_used = o;
-        for (int o = 0; o < 8; o++) if (counts[o]) appendFragment(out, frag[o], o == last_used);
-    }
-
-    void buildHostOctree(std::vector<float>& photons, uint32_t max_node_data, const double* bounds, mcrt_ctx::HostPhotonMap& out)
-    {
-        out = mcrt_ctx::HostPhotonMap();
-        const uint64_t n = photons.size() / 8;
-        if (n == 0) return;
-        buildSubtreeParallel(photons, 0, n, bounds, bounds + 3, max_node_data, 0, out);
-        out.photons = std::move(photons);
-    }
-
     int renderDispatch(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step, uint32_t n_rows,
                        uint32_t sqrtspp, uint32_t global_seed, int integrator_kind, int precision, double* out_dev,
                        mcrt_stats* stats)
@@ -1292,18 +1117,6 @@ static void describeHostMap(const mcrt_ctx::HostPhotonMap& m, mcrt_photon_map_de
     out->photons = m.photons.data();
 }
 
-int mcrt_octree_build_host(const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf, const double* scene_bounds6,
-                           void** handle, mcrt_photon_map_desc* out)
-{
-    if (!handle || !out || !scene_bounds6 || max_photons_per_octree_leaf == 0 || (n && !photons)) return MCRT_ERR_INVALID;
-    auto* m = new mcrt_ctx::HostPhotonMap();
-    std::vector<float> data(photons, photons + 8 * n);
-    buildHostOctree(data, max_photons_per_octree_leaf, scene_bounds6, *m);
-    describeHostMap(*m, out);
-    *handle = m;
-    return MCRT_OK;
-}
-
 int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t max_photons_per_octree_leaf, const double* scene_bounds6,
                       void** handle, mcrt_photon_map_desc* out, double* gpu_ms)
 {
@@ -1332,7 +1145,7 @@ int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t 
     return MCRT_OK;
 }
 
-void mcrt_octree_free_host(void* handle)
+void mcrt_octree_free(void* handle)
 {
     delete static_cast<mcrt_ctx::HostPhotonMap*>(handle);
 }

@@ -868,7 +868,8 @@ int buildBvhOnDevice(const double* prim_bounds_host, uint32_t n, const double sc
 // Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244) on
 // photons already in device memory: the same rounds with 8 bins = octants of the node's cell, a
 // node is internal iff it holds more than max_node_data photons (and sits above level 64, the
-// guard the host builder has too), boxes = tight boxes of the contained photons.
+// guard against coincident photons; the reference would recurse forever), boxes = tight boxes of the
+// contained photons.
 int buildPhotonOctreeOnDevice(const float4* d_photons, uint32_t n, const double cell[6], uint32_t max_node_data, int sm_count,
                               cudaStream_t s, std::vector<void*>& keep, PhotonOctreeDevice& out, std::string& error)
 {

@@ -842,6 +842,105 @@ void oracle_render_film(void* h, const mcrt_camera* cam, const mcrt_film* film, 
         }
 }
 
+// Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244),
+// restated top-down. The reference inserts photons one by one; a node ends up internal exactly when
+// more than max_node_data photons fall into its box, and child boxes follow from the parent's by
+// fixed arithmetic, so the finished tree is a function of the photon set alone: partition the
+// node's photons into octants (stable), recurse in octant order = the order compact() emits.
+namespace
+{
+    struct OctreeOut
+    {
+        std::vector<double> bounds;
+        std::vector<uint64_t> start, count;
+        std::vector<uint32_t> next;
+        std::vector<uint8_t> leaf;
+        std::vector<float> photons;
+    };
+
+    void octreeBuild(OctreeOut& out, std::vector<float>& data, std::vector<float>& scratch, uint64_t begin, uint64_t end,
+                     const double* bmin, const double* bmax, uint32_t max_node_data, bool last, int depth)
+    {
+        const uint64_t count = end - begin;
+        const uint32_t idx = (uint32_t)out.leaf.size();
+        // (the reference recurses without bound when > max_node_data photons coincide; stop at 64 levels)
+        const bool split = count > max_node_data && depth < 64;
+        out.leaf.push_back(split ? 0 : 1);
+        out.start.push_back(begin);
+        out.count.push_back(count);                 // LinearOctant::contained_data: everything below
+        out.next.push_back(0xFFFFFFFFu);
+        out.bounds.resize(out.bounds.size() + 6);
+        double lo[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
+        double hi[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
+        for (uint64_t i = begin; i < end; i++)
+            for (int c = 0; c < 3; c++)
+            {
+                const double v = (double)data[8 * i + 3 + c];
+                if (lo[c] > v) lo[c] = v;
+                if (hi[c] < v) hi[c] = v;
+            }
+        if (split)
+        {
+            // BoundingBox::centroid / dimensions (bounding-box.cpp:25-33), child boxes octree.cpp:51-60
+            double centroid[3], half[3];
+            for (int c = 0; c < 3; c++) { centroid[c] = (bmax[c] + bmin[c]) / 2.0; half[c] = (bmax[c] - bmin[c]) / 2.0; }
+            auto octantOf = [&](const float* ph)
+            {
+                int o = 0;
+                for (int c = 0; c < 3; c++) if ((double)ph[3 + c] >= centroid[c]) o |= (4 >> c);   // octree.cpp:73-79
+                return o;
+            };
+            uint64_t counts[8] = { 0 }, starts[9], cursor[8];
+            for (uint64_t i = begin; i < end; i++) counts[octantOf(&data[8 * i])]++;
+            starts[0] = begin;
+            for (int o = 0; o < 8; o++) starts[o + 1] = starts[o] + counts[o];
+            scratch.resize(8 * count);
+            for (int o = 0; o < 8; o++) cursor[o] = starts[o] - begin;
+            for (uint64_t i = begin; i < end; i++)
+            {
+                const int o = octantOf(&data[8 * i]);
+                std::memcpy(&scratch[8 * cursor[o]++], &data[8 * i], 32);
+            }
+            std::memcpy(&data[8 * begin], scratch.data(), 32 * count);
+            int last_used = -1;
+            for (int o = 0; o < 8; o++) if (counts[o]) last_used = o;
+            for (int o = 0; o < 8; o++)
+            {
+                if (!counts[o]) continue;   // empty leaves are dropped (linear-octree.cpp:222-229)
+                double cmin[3], cmax[3];
+                for (int c = 0; c < 3; c++)
+                {
+                    const double new_origin = centroid[c] + half[c] * ((o & (4 >> c)) ? 0.5 : -0.5);
+                    const double h = half[c] * 0.5;
+                    cmin[c] = new_origin - h; cmax[c] = new_origin + h;
+                }
+                octreeBuild(out, data, scratch, starts[o], starts[o + 1], cmin, cmax, max_node_data, o == last_used, depth + 1);
+            }
+        }
+        for (int c = 0; c < 3; c++) { out.bounds[6 * idx + c] = lo[c]; out.bounds[6 * idx + 3 + c] = hi[c]; }
+        out.next[idx] = last ? 0xFFFFFFFFu : (uint32_t)out.leaf.size();
+    }
+}
+
+// photons: [n][8] floats {flux.xyz, pos.xyz, phi, theta}; scene_bounds6 = the root Octree box
+// (photon-mapper.cpp:49-51). *out points into memory owned by *handle (oracle_octree_free).
+void oracle_octree_build(const float* photons, uint64_t n, uint32_t max_node_data, const double* scene_bounds6, void** handle,
+                         mcrt_photon_map_desc* out)
+{
+    auto* o = new OctreeOut();
+    o->photons.assign(photons, photons + 8 * n);
+    std::vector<float> scratch;
+    if (n) octreeBuild(*o, o->photons, scratch, 0, n, scene_bounds6, scene_bounds6 + 3, max_node_data, true, 0);
+    std::memset(out, 0, sizeof(*out));
+    out->n_octants = (uint32_t)o->leaf.size();
+    out->octant_bounds = o->bounds.data(); out->octant_start = o->start.data(); out->octant_count = o->count.data();
+    out->octant_next_sibling = o->next.data(); out->octant_leaf = o->leaf.data();
+    out->n_photons = n; out->photons = o->photons.data();
+    *handle = o;
+}
+
+void oracle_octree_free(void* handle) { delete static_cast<OctreeOut*>(handle); }
+
 // Image::save without the file (image.cpp:37-88, histogram.cpp, pixel-operators.cpp, srgb.hpp:54-62)
 namespace
 {

@@ -27,6 +27,8 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        L.oracle_octree_free.argtypes = [C.c_void_p]
         L.oracle_image_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_render_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
@@ -41,6 +43,18 @@ def sampler_stream(pixel, sample, n_shuffles, seed):
     pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
     out = np.zeros((len(pixel), 7), dtype=np.uint32)
     lib().oracle_sampler_stream(_p(pixel), _p(sample), len(pixel), n_shuffles, seed, _p(out))
+    return out
+
+
+def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds, desc_type, map_arrays):
+    """Octree<Photon> + LinearOctree::compact restated (scalar, host). desc_type / map_arrays: the
+    product's PhotonMapDesc struct and its numpy unpacker (layout only)."""
+    photons = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 8)
+    bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64)
+    h, d = C.c_void_p(), desc_type()
+    lib().oracle_octree_build(_p(photons), len(photons), int(max_photons_per_octree_leaf), _p(bounds), C.byref(h), C.addressof(d))
+    out = map_arrays(d)
+    lib().oracle_octree_free(h)
     return out
 
 
