@@ -240,6 +240,28 @@ int mcrt_octree_build(mcrt_ctx* ctx, const float* photons, uint64_t n, uint32_t 
                       const double* scene_bounds6, void** handle, mcrt_photon_map_desc* out, double* gpu_ms);
 void mcrt_octree_free(void* handle);
 
+/* SURVEY.md §8f-3 ("next"): scene ingest. Scene::parseOBJ (source/scene/scene.cpp:238-324) as a
+ * parallel mmap-based reader with identical results: "v" / "vn" lines and the first three corners
+ * of every "f" line, zero-based (idx - 1 in size_t arithmetic). tri_vt / tri_vn hold only the faces
+ * whose three corners all carry that index, exactly as the reference's separate lists do. Host
+ * code, no GPU involved. *out points into memory owned by *handle (mcrt_obj_free). A missing file
+ * or a negative index (the reference prints / throws) returns MCRT_ERR_INVALID with the message. */
+typedef struct mcrt_obj_mesh {
+    uint64_t n_vertices, n_normals, n_tri_v, n_tri_vt, n_tri_vn;
+    const double* vertices;     /* [n_vertices][3] */
+    const double* normals;      /* [n_normals][3] */
+    const uint64_t* tri_v;      /* [n_tri_v][3] */
+    const uint64_t* tri_vt;     /* [n_tri_vt][3] */
+    const uint64_t* tri_vn;     /* [n_tri_vn][3] */
+} mcrt_obj_mesh;
+int mcrt_obj_load(const char* path, int threads, void** handle, mcrt_obj_mesh* out, char* err, size_t errlen);
+void mcrt_obj_free(void* handle);
+/* Scene::generateVertexNormals (scene.cpp:326-355): normalised sum of face normal x area x corner
+ * angle over the incident triangles, added in triangle order (bit-identical sums), parallel over
+ * vertices. out_normals: [n_vertices][3]. */
+int mcrt_obj_vertex_normals(const double* vertices, uint64_t n_vertices, const uint64_t* tri_v, uint64_t n_triangles,
+                            int threads, double* out_normals);
+
 /* SURVEY.md §8f-4 ("next", image half): Image::save (source/camera/image.cpp:37-51) without the file:
  * auto exposure (getExposure, image.cpp:63-73: histogram median -> 0.5), tone-mapping operator
  * (pixel-operators.cpp:7-51), auto gain (getGain, image.cpp:78-88: 99th percentile -> 0.99), sRGB

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "mcrt_octree_free", "mcrt_render_rows", "mcrt_render_rows_dev", "mcrt_render_rows_strided_dev",
     "mcrt_trace_closest",
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
+    "mcrt_obj_load", "mcrt_obj_free", "mcrt_obj_vertex_normals",
     "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
 ]
 
@@ -121,6 +122,12 @@ class ImageParams(C.Structure):
                    math.pow(2, image.get("exposure_compensation", 0.0)), math.pow(2, image.get("gain_compensation", 0.0)))
 
 
+class ObjMeshRec(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint64), ("n_normals", C.c_uint64), ("n_tri_v", C.c_uint64), ("n_tri_vt", C.c_uint64),
+                ("n_tri_vn", C.c_uint64), ("vertices", C.c_void_p), ("normals", C.c_void_p), ("tri_v", C.c_void_p),
+                ("tri_vt", C.c_void_p), ("tri_vn", C.c_void_p)]
+
+
 class BvhDesc(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_prims", C.c_uint32), ("node_bounds", C.c_void_p),
                 ("node_first_prim", C.c_void_p), ("node_prim_count", C.c_void_p), ("node_next_sibling", C.c_void_p),
@@ -195,6 +202,10 @@ def lib():
                                      C.POINTER(C.c_void_p), C.POINTER(BvhDesc), C.POINTER(C.c_double)]
         L.mcrt_bvh_free.argtypes = [C.c_void_p]
         L.mcrt_bvh_free.restype = None
+        L.mcrt_obj_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(ObjMeshRec), C.c_char_p, C.c_size_t]
+        L.mcrt_obj_free.argtypes = [C.c_void_p]
+        L.mcrt_obj_free.restype = None
+        L.mcrt_obj_vertex_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         tm_args = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(ImageParams), C.c_void_p,
                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.mcrt_image_tonemap.argtypes = tm_args
@@ -659,6 +670,68 @@ def build_photon_octree(photons, max_photons_per_octree_leaf, scene_bounds, devi
         out = _map_arrays(d)
         lib().mcrt_octree_free(h)
         return out, ms.value
+    finally:
+        lib().mcrt_destroy(ctx)
+
+
+def load_obj(path, threads=0):
+    """mcrt_obj_load: Scene::parseOBJ (scene.cpp:238-324), parallel. -> dict(vertices [n,3], normals [n,3],
+    tri_v / tri_vt / tri_vn [m,3] uint64)."""
+    h, d = C.c_void_p(), ObjMeshRec()
+    err = C.create_string_buffer(512)
+    rc = lib().mcrt_obj_load(os.fsencode(path), int(threads), C.byref(h), C.byref(d), err, 512)
+    if rc:
+        raise McrtError(err.value.decode() or f"mcrt_obj_load failed: {rc}")
+
+    def arr(ptr, count, dtype):
+        if not ptr or count == 0:
+            return np.zeros((0, 3), dtype=dtype)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * 3 * 8,)).view(dtype).reshape(-1, 3).copy()
+    out = dict(vertices=arr(d.vertices, d.n_vertices, np.float64), normals=arr(d.normals, d.n_normals, np.float64),
+               tri_v=arr(d.tri_v, d.n_tri_v, np.uint64), tri_vt=arr(d.tri_vt, d.n_tri_vt, np.uint64),
+               tri_vn=arr(d.tri_vn, d.n_tri_vn, np.uint64))
+    lib().mcrt_obj_free(h)
+    return out
+
+
+def vertex_normals(vertices, tri_v, threads=0):
+    """mcrt_obj_vertex_normals: Scene::generateVertexNormals (scene.cpp:326-355). -> [n_vertices, 3]."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    tri_v = np.ascontiguousarray(tri_v, dtype=np.uint64).reshape(-1, 3)
+    out = np.zeros_like(vertices)
+    rc = lib().mcrt_obj_vertex_normals(_ptr(vertices), len(vertices), _ptr(tri_v), len(tri_v), int(threads), _ptr(out))
+    if rc:
+        raise McrtError("mcrt_obj_vertex_normals: triangle index out of range")
+    return out
+
+
+def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis=0, device=0):
+    """mcrt_bvh_build: the reference's BVH (bvh.cpp:13-78) over primitive boxes, built on the GPU.
+    -> dict(node_bounds [n,6], node_first_prim, node_prim_count, node_next_sibling, prim_order, gpu_ms, rounds)."""
+    prim_bounds = np.ascontiguousarray(prim_bounds, dtype=np.float64).reshape(-1, 6)
+    scene_bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64).reshape(6)
+    code = BVH_TYPES[bvh_type.lower()] if isinstance(bvh_type, str) else int(bvh_type)
+    ctx = C.c_void_p()
+    rc = lib().mcrt_init(device, C.byref(ctx))
+    if rc:
+        raise McrtError(f"mcrt_init({device}) failed: {rc} (no CUDA device? there is no CPU fallback)")
+    try:
+        h, d, ms = C.c_void_p(), BvhDesc(), C.c_double()
+        rc = lib().mcrt_bvh_build(ctx, _ptr(prim_bounds), len(prim_bounds), _ptr(scene_bounds), code, int(bins_per_axis),
+                                  C.byref(h), C.byref(d), C.byref(ms))
+        if rc:
+            raise McrtError(f"mcrt_bvh_build failed ({rc}): {lib().mcrt_last_error(ctx).decode()}")
+
+        def arr(ptr, count, dtype):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype).copy()
+        out = dict(node_bounds=arr(d.node_bounds, d.n_nodes * 6, np.float64).reshape(-1, 6),
+                   node_first_prim=arr(d.node_first_prim, d.n_nodes, np.uint32),
+                   node_prim_count=arr(d.node_prim_count, d.n_nodes, np.uint32),
+                   node_next_sibling=arr(d.node_next_sibling, d.n_nodes, np.uint32),
+                   prim_order=arr(d.prim_order, d.n_prims, np.uint32),
+                   gpu_ms=ms.value, rounds=int(d.build_rounds), kernel_launches=int(d.kernel_launches))
+        lib().mcrt_bvh_free(h)
+        return out
     finally:
         lib().mcrt_destroy(ctx)
 

@@ -20,6 +20,7 @@ UNITS = [
     ("kernels_f32.cu", []),
     ("bvh_build.cu", ["--fmad=false"]),
     ("image.cu", ["--fmad=false"]),
+    ("obj_abi.cu", ["--fmad=false"]),
     ("abi.cu", []),
 ]
 
@@ -39,7 +40,9 @@ def build(force=False, verbose=False, defines=(), suffix=""):
     lib = os.path.join(HERE, f"libmcrt_b200{suffix}.so")
     objdir = os.path.join(HERE, "build" + suffix)
     os.makedirs(objdir, exist_ok=True)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mcrt_abi.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mcrt_abi.h"),
+                                                              os.path.join(HERE, "host", "obj_loader.cpp"),
+                                                              os.path.join(HERE, "host", "obj_loader.hpp")]
     newest = max(os.path.getmtime(d) for d in deps)
     jobs, objs = [], []
     for src, extra in UNITS:

@@ -47,6 +47,9 @@ def lib():
         L.ref_bvh_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
         L.ref_bvh_arrays.argtypes = [C.c_void_p] * 6
         L.ref_prim_bounds.argtypes = [C.c_void_p] * 3
+        L.ref_obj_parse.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_obj_copy.argtypes = [C.c_void_p] * 5
+        L.ref_vertex_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_image_save.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_fresnel_dielectric.restype = C.c_double
         L.ref_fresnel_dielectric.argtypes = [C.c_double] * 3
@@ -153,6 +156,26 @@ class RefScene:
             raise RuntimeError("ref_bvh_arrays failed")
         out["seconds"] = sec.value
         return out
+
+    def parse_obj(self, path):
+        """Scene::parseOBJ -> dict(vertices, normals, tri_v, tri_vt, tri_vn, seconds); raises if the reference threw."""
+        counts = np.zeros(5, dtype=np.uint64); sec = C.c_double()
+        if lib().ref_obj_parse(self.h, os.fsencode(path), _p(counts), C.byref(sec)):
+            raise RuntimeError("Scene::parseOBJ threw")
+        c = [int(x) for x in counts]
+        out = dict(vertices=np.zeros((c[0], 3)), normals=np.zeros((c[1], 3)), tri_v=np.zeros((c[2], 3), np.uint64),
+                   tri_vt=np.zeros((c[3], 3), np.uint64), tri_vn=np.zeros((c[4], 3), np.uint64))
+        lib().ref_obj_copy(_p(out["vertices"]), _p(out["normals"]), _p(out["tri_v"]), _p(out["tri_vt"]), _p(out["tri_vn"]))
+        out["seconds"] = sec.value
+        return out
+
+    def vertex_normals(self, vertices, tri_v):
+        """Scene::generateVertexNormals -> ([n, 3], seconds)."""
+        vertices = np.ascontiguousarray(vertices, dtype=np.float64); tri_v = np.ascontiguousarray(tri_v, dtype=np.uint64)
+        out = np.zeros_like(vertices); sec = C.c_double()
+        if lib().ref_vertex_normals(self.h, _p(vertices), len(vertices), _p(tri_v), len(tri_v), _p(out), C.byref(sec)):
+            raise RuntimeError("Scene::generateVertexNormals threw")
+        return out, sec.value
 
     def export_pack(self, path):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

@@ -427,6 +427,70 @@ int ref_knn(void* handle, int which, const double* points, size_t n, uint32_t k,
     return 0;
 }
 
+// Scene::parseOBJ (scene.cpp:238-324) on any file, through the opened scene object; results are kept
+// in the handle and copied out by ref_obj_copy. Returns 0, or -1 if the reference threw.
+namespace
+{
+    struct ParsedObj
+    {
+        std::vector<glm::dvec3> v, n;
+        std::vector<std::vector<size_t>> tv, tvt, tvn;
+    } g_obj;
+}
+
+int ref_obj_parse(void* handle, const char* path, uint64_t counts[5], double* seconds)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    const Scene& scene = h->camera->integrator->scene;
+    g_obj = ParsedObj();
+    try
+    {
+        CoutSilencer quiet;
+        auto t0 = std::chrono::steady_clock::now();
+        scene.parseOBJ(path, g_obj.v, g_obj.n, g_obj.tv, g_obj.tvt, g_obj.tvn);
+        auto t1 = std::chrono::steady_clock::now();
+        if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+    counts[0] = g_obj.v.size(); counts[1] = g_obj.n.size(); counts[2] = g_obj.tv.size(); counts[3] = g_obj.tvt.size(); counts[4] = g_obj.tvn.size();
+    return 0;
+}
+
+void ref_obj_copy(double* v, double* n, uint64_t* tv, uint64_t* tvt, uint64_t* tvn)
+{
+    for (size_t i = 0; i < g_obj.v.size(); i++) for (int c = 0; c < 3; c++) v[3 * i + c] = g_obj.v[i][c];
+    for (size_t i = 0; i < g_obj.n.size(); i++) for (int c = 0; c < 3; c++) n[3 * i + c] = g_obj.n[i][c];
+    auto copy = [](const std::vector<std::vector<size_t>>& src, uint64_t* dst) { for (size_t i = 0; i < src.size(); i++) for (int c = 0; c < 3; c++) dst[3 * i + c] = src[i][c]; };
+    copy(g_obj.tv, tv); copy(g_obj.tvt, tvt); copy(g_obj.tvn, tvn);
+}
+
+// Scene::generateVertexNormals (scene.cpp:326-355)
+int ref_vertex_normals(void* handle, const double* vertices, uint64_t n_vertices, const uint64_t* tri_v, uint64_t n_tris, double* out, double* seconds)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    const Scene& scene = h->camera->integrator->scene;
+    std::vector<glm::dvec3> v(n_vertices), n;
+    for (size_t i = 0; i < n_vertices; i++) v[i] = glm::dvec3(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
+    std::vector<std::vector<size_t>> t(n_tris, std::vector<size_t>(3));
+    for (size_t i = 0; i < n_tris; i++) for (int c = 0; c < 3; c++) t[i][c] = tri_v[3 * i + c];
+    try
+    {
+        auto t0 = std::chrono::steady_clock::now();
+        scene.generateVertexNormals(n, v, t);
+        auto t1 = std::chrono::steady_clock::now();
+        if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+    for (size_t i = 0; i < n.size(); i++) for (int c = 0; c < 3; c++) out[3 * i + c] = n[i][c];
+    return 0;
+}
+
 // Image::save (image.cpp:37-51) on caller pixels: `image_json` is a camera's "image" object; the bytes
 // are what the reference writes after the TGA header. Also returns getExposure()*exposure_scale
 // and getGain()*gain_scale.

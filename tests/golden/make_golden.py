@@ -186,6 +186,24 @@ def make_image_kat():
     np.savez_compressed(os.path.join(HERE, "image_kat.npz"), inputs=json.dumps(list(inputs)), configs=json.dumps(IMAGE_CONFIGS), **out)
 
 
+def make_obj_kat():
+    """Scene::parseOBJ / generateVertexNormals on the OBJ fixtures written for this repository
+    (tests/golden/quirks.obj) -> obj_kat.npz."""
+    s = ref.RefScene("ior_test.json", dict(width=8, height=8, sqrtspp=1))
+    r = s.parse_obj(os.path.join(HERE, "quirks.obj"))
+    try:
+        s.parse_obj(os.path.join(HERE, "quirks_negative.obj"))
+        threw = False
+    except RuntimeError:
+        threw = True
+    valid = (r["tri_v"] < len(r["vertices"])).all(axis=1)
+    normals, _ = s.vertex_normals(r["vertices"], r["tri_v"][valid])
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "obj_kat.npz"), vertices=r["vertices"], normals=r["normals"], tri_v=r["tri_v"],
+                        tri_vt=r["tri_vt"], tri_vn=r["tri_vn"], negative_throws=np.uint8(threw), generated_normals=normals)
+    print("obj_kat:", {k: v.shape for k, v in r.items() if hasattr(v, "shape")}, "negative throws:", threw)
+
+
 def make_sampler_kat(rng):
     ref.set_seed(SEED)
     n = 8192
@@ -262,3 +280,5 @@ if __name__ == "__main__":
         make_film_kat()
     if not only or "image_kat" in only:
         make_image_kat()
+    if not only or "obj_kat" in only:
+        make_obj_kat()

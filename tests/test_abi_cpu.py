@@ -67,3 +67,15 @@ def test_shard_rows_partition(mcrt):
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(n - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_python_mirror_is_complete(mcrt):
+    # the helpers the GPU tests and tools call must exist (catches an accidentally dropped function on CPU)
+    for name in ("Scene", "Camera", "PathTracer", "PhotonMapper", "read_pack", "bvh_build", "build_photon_octree", "load_obj",
+                 "vertex_normals", "shard_rows", "ImageParams", "FILM_FILTERS", "BVH_TYPES"):
+        assert hasattr(mcrt, name), name
+    for name in ("render_rows", "render_rows_dev", "render_rows_strided_dev", "sampleRay", "intersect", "tonemap", "tonemap_dev",
+                 "set_film", "set_option", "sampler_stream"):
+        assert hasattr(mcrt.Integrator, name), name
+    for name in ("prim_bounds", "reordered", "unbuilt", "with_bvh", "cameras", "photon_maps"):
+        assert hasattr(mcrt.Scene, name), name
