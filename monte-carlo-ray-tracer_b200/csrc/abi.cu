@@ -80,6 +80,8 @@ struct mcrt_ctx
     double* d_film_wsum = nullptr;
     size_t film_wsum_values = 0;
     double* d_film_cache = nullptr;
+    double* d_host_out = nullptr;      // staging of mcrt_render_rows (host-buffer entry point)
+    size_t host_out_values = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_poll[2] = { nullptr, nullptr };
 
     // photon maps (PhotonMapper::caustic_map / global_map) + k-NN query queues
@@ -353,6 +355,10 @@ namespace
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.materials, a.materials, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.lights, a.lights, bytes))) return rc;
         d.n_nodes = s.n_nodes; d.n_prims = s.n_prims; d.n_lights = s.n_lights;
+        d.tris_only = 1;
+        for (uint32_t i = 0; i < s.n_prims; i++) if (s.prim_type[i] != MCRT_PRIM_TRIANGLE) { d.tris_only = 0; break; }
+        d.material_flags_any = 0;   // selects the k_shade feature set (kernels_impl.cuh)
+        for (const auto& m : a.materials) d.material_flags_any |= m.flags;
         d.scene_ior = (R)s.scene_ior;
         d.scene_scale = (R)ctx->scene_scale;
         return MCRT_OK;
@@ -803,6 +809,7 @@ void mcrt_destroy(mcrt_ctx* ctx)
     if (ctx->d_film) cudaFree(ctx->d_film);
     if (ctx->d_film_wsum) cudaFree(ctx->d_film_wsum);
     if (ctx->d_film_cache) cudaFree(ctx->d_film_cache);
+    if (ctx->d_host_out) cudaFree(ctx->d_host_out);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1279,15 +1286,22 @@ int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint
     if (!out_rgb || !camera || y1 <= y0) { ctx->error = "mcrt_render_rows: invalid arguments"; return MCRT_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     const size_t values = (size_t)camera->width * (y1 - y0) * 3;
-    double* d_out = nullptr;
-    CK(cudaMalloc((void**)&d_out, values * sizeof(double)));
-    int rc = renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, d_out, stats);
+    // device staging for the resolved frame: kept in the context (grow-only), so that a render call
+    // costs no cudaMalloc / cudaFree (both synchronise the device)
+    if (ctx->host_out_values < values)
+    {
+        if (ctx->d_host_out) cudaFree(ctx->d_host_out);
+        ctx->d_host_out = nullptr; ctx->host_out_values = 0;
+        CK(cudaMalloc((void**)&ctx->d_host_out, values * sizeof(double)));
+        ctx->host_out_values = values;
+    }
+    int rc = renderDispatch(ctx, camera, y0, 1, y1 - y0, sqrtspp, global_seed, integrator_kind, precision, ctx->d_host_out, stats);
     if (rc == MCRT_OK)
     {
-        cudaError_t e = cudaMemcpy(out_rgb, d_out, values * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpyAsync(out_rgb, ctx->d_host_out, values * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->error = cudaGetErrorString(e); rc = MCRT_ERR_CUDA; }
     }
-    cudaFree(d_out);
     return rc;
 }
 

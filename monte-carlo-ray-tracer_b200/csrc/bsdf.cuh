@@ -102,32 +102,32 @@ namespace mcrt
     }
 
     // ---------------------------------------------------------------------------- Material
-    template <class R> MCRT_D V3<R> matDiffuseReflection(const Material<R>& m, const V3<R>& wi, const V3<R>& wo, R& pdf)
+    template <class R> MCRT_D V3<R> matDiffuseReflection(const Material<R>& m, uint32_t flags, const V3<R>& wi, const V3<R>& wo, R& pdf)
     {
         if (wi.z < R(0)) { pdf = R(0); return V3<R>(R(0)); }
         pdf = wi.z * Consts<R>::INV_PI;
         V3<R> lambert = m.reflectance * Consts<R>::INV_PI;
-        if (!(m.flags & MAT_ROUGH)) return lambert;
+        if (!(flags & MAT_ROUGH)) return lambert;
         R cos_delta_phi = gclamp((wi.x * wo.x + wi.y * wo.y) /
                                  msqrt((pow2(wi.x) + pow2(wi.y)) * (pow2(wo.x) + pow2(wo.y))), R(0), R(1));
         R D = msqrt((R(1) - pow2(wi.z)) * (R(1) - pow2(wo.z))) / gmax(wi.z, wo.z);
         return lambert * (m.A + m.B * cos_delta_phi * D);
     }
 
-    template <class R> MCRT_D V3<R> matSpecularReflection(const Material<R>& m, const V3<R>& wi, const V3<R>& wo, R& pdf)
+    template <class R> MCRT_D V3<R> matSpecularReflection(const Material<R>& m, uint32_t flags, const V3<R>& wi, const V3<R>& wo, R& pdf)
     {
         if (wi.z < R(0)) { pdf = R(0); return V3<R>(R(0)); }
-        if (m.flags & MAT_ROUGH_SPECULAR) return m.specular_reflectance * ggxReflection(wi, wo, m.ax, m.ay, pdf);
+        if (flags & MAT_ROUGH_SPECULAR) return m.specular_reflectance * ggxReflection(wi, wo, m.ax, m.ay, pdf);
         pdf = R(1);
         return m.specular_reflectance / mabs(wi.z);
     }
 
-    template <class R> MCRT_D V3<R> matSpecularTransmission(const Material<R>& m, const V3<R>& wi, const V3<R>& wo,
+    template <class R> MCRT_D V3<R> matSpecularTransmission(const Material<R>& m, uint32_t flags, const V3<R>& wi, const V3<R>& wo,
                                                             R n1, R n2, R& pdf, bool inside, bool flux)
     {
         if (wi.z > R(0)) { pdf = R(0); return V3<R>(R(0)); }
         V3<R> btdf = !inside ? m.transmittance : V3<R>(R(1));
-        if (m.flags & MAT_ROUGH_SPECULAR)
+        if (flags & MAT_ROUGH_SPECULAR)
         {
             btdf *= ggxTransmission(wi, wo, n1, n2, m.ax, m.ay, pdf);
             if (flux) btdf *= pow2(n2 / n1);
@@ -159,6 +159,11 @@ namespace mcrt
         uint32_t type;
         R t, n1, n2, T, Rf;
         const Material<R>* material;
+        // Feature set of the kernel instantiation (k_shade<.., FEATS>), a compile-time constant after
+        // inlining: scenes without GGX / Oren-Nayar / conductors run kernels from which that code is
+        // pruned, because (flags & fmask) & bit folds to 0 for the bits the mask lacks.
+        uint32_t fmask;
+        MCRT_D uint32_t flags() const { return material->flags & fmask; }
         uint32_t prim;
         V3<R> position, normal, out;
         Frame<R> shading_cs;
@@ -171,7 +176,7 @@ namespace mcrt
         {
             const Material<R>& m = *material;
             R cos_theta = wo.z;
-            if (m.flags & MAT_ROUGH_SPECULAR)
+            if (flags() & MAT_ROUGH_SPECULAR)
             {
                 if (wi.z > R(0))
                 {
@@ -185,24 +190,24 @@ namespace mcrt
                 }
             }
 
-            if (m.flags & (MAT_PERFECT_MIRROR | MAT_COMPLEX_IOR))
+            if (flags() & (MAT_PERFECT_MIRROR | MAT_COMPLEX_IOR))
             {
-                V3<R> brdf = matSpecularReflection(m, wi, wo, pdf);
-                if (m.flags & MAT_COMPLEX_IOR) brdf *= fresnelConductor(n1, m.ior_real, m.ior_imag, cos_theta);
+                V3<R> brdf = matSpecularReflection(m, flags(), wi, wo, pdf);
+                if (flags() & MAT_COMPLEX_IOR) brdf *= fresnelConductor(n1, m.ior_real, m.ior_imag, cos_theta);
                 return brdf;
             }
 
-            if (n2 < R(1)) return matDiffuseReflection(m, wi, wo, pdf);
+            if (n2 < R(1)) return matDiffuseReflection(m, flags(), wi, wo, pdf);
 
             R F = fresnelDielectric(n1, n2, cos_theta);
 
             R pdf_s, pdf_d;
-            V3<R> brdf_s = matSpecularReflection(m, wi, wo, pdf_s);
-            V3<R> brdf_d = matDiffuseReflection(m, wi, wo, pdf_d);
+            V3<R> brdf_s = matSpecularReflection(m, flags(), wi, wo, pdf_s);
+            V3<R> brdf_d = matDiffuseReflection(m, flags(), wi, wo, pdf_d);
 
             R pdf_t = pdf_s;
             V3<R> btdf = brdf_s;
-            if (F < R(1)) btdf = matSpecularTransmission(m, wi, wo, n1, n2, pdf_t, inside, flux);
+            if (F < R(1)) btdf = matSpecularTransmission(m, flags(), wi, wo, n1, n2, pdf_t, inside, flux);
 
             if (wi_dirac_delta)
             {
@@ -217,7 +222,7 @@ namespace mcrt
                     return btdf * T * (R(1) - F);
                 }
             }
-            else if (!(m.flags & MAT_ROUGH_SPECULAR))
+            else if (!(flags() & MAT_ROUGH_SPECULAR))
             {
                 pdf = pdf_d * (R(1) - Rf) * (R(1) - T);
                 return brdf_d * (R(1) - F) * (R(1) - T);
@@ -239,7 +244,7 @@ namespace mcrt
 
     // Interaction::Interaction + selectType. `ray_dir`/`ray_start` are the incoming ray.
     // normal_geo: Surface::normal(position); shading normal resolved by the caller's callback data.
-    template <class R>
+    template <uint32_t FEATS = 0xFFFFFFFFu, class R>
     MCRT_D void buildInteraction(Interaction<R>& ia, const DeviceScene<R>& sc, const Hit<R>& hit, const PathRay<R>& ray,
                                  R external_ior, const SamplerState& smp)
     {
@@ -250,6 +255,7 @@ namespace mcrt
         const PrimShade<R> ps = sc.shade[hit.prim];
         ia.material = &sc.materials[ps.material];
         const Material<R>& m = *ia.material;
+        ia.fmask = FEATS;
         ia.position = ray.start + ray.direction * hit.t;
 
         // Surface::normal(position)
@@ -276,7 +282,7 @@ namespace mcrt
 
         R cos_theta = dot(ray.direction, normal);
         ia.inside = cos_theta > R(0);
-        ia.n2 = (ia.inside && !(m.flags & MAT_OPAQUE)) ? external_ior : m.ior;
+        ia.n2 = (ia.inside && !(ia.flags() & MAT_OPAQUE)) ? external_ior : m.ior;
 
         V3<R> shading_normal = normal;
         if (ps.type == PRIM_TRIANGLE && ps.vn_index >= 0)
@@ -298,10 +304,10 @@ namespace mcrt
 
         ia.Rf = fresnelDielectric(ia.n1, ia.n2, dot(shading_normal, ia.out));
         ia.T = m.transparency;
-        if (m.flags & MAT_ROUGH_SPECULAR) ia.Rf = gclamp(ia.Rf, R(0.1), R(0.9));
+        if (ia.flags() & MAT_ROUGH_SPECULAR) ia.Rf = gclamp(ia.Rf, R(0.1), R(0.9));
 
         // selectType, interaction.cpp:156-183
-        if (m.flags & (MAT_PERFECT_MIRROR | MAT_COMPLEX_IOR))
+        if (ia.flags() & (MAT_PERFECT_MIRROR | MAT_COMPLEX_IOR))
         {
             ia.type = IA_REFLECT;
         }
@@ -317,7 +323,7 @@ namespace mcrt
             else if (ia.Rf + (R(1) - ia.Rf) * ia.T > p) ia.type = IA_REFRACT;
             else ia.type = IA_DIFFUSE;
         }
-        ia.dirac_delta = ia.type != IA_DIFFUSE && !(m.flags & MAT_ROUGH_SPECULAR);
+        ia.dirac_delta = ia.type != IA_DIFFUSE && !(ia.flags() & MAT_ROUGH_SPECULAR);
     }
 
     template <class R>
@@ -346,7 +352,7 @@ namespace mcrt
         V3<R> specular_normal;
         if (ia.type != IA_DIFFUSE)
         {
-            if (m.flags & MAT_ROUGH_SPECULAR)
+            if (ia.flags() & MAT_ROUGH_SPECULAR)
             {
                 R u[2];
                 samplerGet<R, DIM_BSDF, 2>(smp, u);

@@ -36,6 +36,9 @@
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 3
 #endif
+#ifndef MCRT_SHADE_MINBLOCKS_LITE   // k_shade without the GGX / Oren-Nayar / conductor code needs fewer registers
+#define MCRT_SHADE_MINBLOCKS_LITE 4
+#endif
 #ifndef MCRT_SORT_ORIGIN_BITS
 #define MCRT_SORT_ORIGIN_BITS 4
 #endif
@@ -224,7 +227,7 @@ namespace mcrt
     template <> struct Mode<double> { static constexpr bool parity = true; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F64; };
     template <> struct Mode<float> { static constexpr bool parity = false; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F32; };
 
-    template <class R>
+    template <bool TRIS_ONLY = false, class R>
     MCRT_D Hit<R> traceClosest(const DeviceScene<R>& sc, const V3<R>& o, const V3<R>& d, uint32_t skip_prim,
                                TraceCounters& cnt, uint32_t& overflow)
     {
@@ -232,11 +235,11 @@ namespace mcrt
         rq.o = o; rq.d = d; rq.inv_d = R(1) / d;
         if constexpr (Mode<R>::parity)
         {
-            return traverseReferenceOrder(sc, rq, cnt, overflow);
+            return traverseReferenceOrder<TRIS_ONLY>(sc, rq, cnt, overflow);
         }
         else
         {
-            return traverseWide(sc, rq, skip_prim, cnt, overflow);
+            return traverseWide<TRIS_ONLY>(sc, rq, skip_prim, cnt, overflow);
         }
     }
 
@@ -412,7 +415,7 @@ namespace mcrt
         c->n_knn = 0;
     }
 
-    template <class R>
+    template <class R, bool TRIS_ONLY>
     __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
@@ -429,7 +432,7 @@ namespace mcrt
             uint32_t skip = NO_PRIM;
             if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
             const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
-            Hit<R> h = traceClosest(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
+            Hit<R> h = traceClosest<TRIS_ONLY>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
             p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
             rays++;
             // tail diagnostic: how much of the warp's time (~ its slowest ray) the average ray uses
@@ -484,8 +487,13 @@ namespace mcrt
         return mix(V3<R>(R(1), R(0.5), R(0)), V3<R>(R(0), R(0.5), R(1)), fy);
     }
 
-    template <class R, int KIND, bool FILM>
-    __global__ void __launch_bounds__(128, MCRT_SHADE_MINBLOCKS) k_shade(WaveParams<R> p, int cur)
+    // FEATS: material features present in the scene (mask over Material::flags): SHADE_FEATS_LITE drops
+    // Oren-Nayar, GGX (evaluation, VNDF sampling) and the conductor Fresnel from the instantiation
+    constexpr uint32_t SHADE_FEATS_ALL = 0xFFFFFFFFu;
+    constexpr uint32_t SHADE_FEATS_LITE = ~(uint32_t)(MAT_ROUGH | MAT_ROUGH_SPECULAR | MAT_COMPLEX_IOR);
+
+    template <class R, int KIND, bool FILM, uint32_t FEATS>
+    __global__ void __launch_bounds__(128, FEATS == 0xFFFFFFFFu ? MCRT_SHADE_MINBLOCKS : MCRT_SHADE_MINBLOCKS_LITE) k_shade(WaveParams<R> p, int cur)
     {
         __shared__ SobolByteTables sobol_tab;
         sobol_tab.fill(p.sobol_bytes);
@@ -579,7 +587,7 @@ namespace mcrt
                     const R external_ior = iors[ext_idx];
 
                     Interaction<R> ia;
-                    buildInteraction(ia, sc, hit, ray, external_ior, smp);
+                    buildInteraction<FEATS>(ia, sc, hit, ray, external_ior, smp);
                     const Material<R>& m = *ia.material;
                     const PrimShade<R> ps = sc.shade[hit.prim];
 
@@ -798,7 +806,7 @@ namespace mcrt
         if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
-    template <class R, bool FILM>
+    template <class R, bool FILM, bool TRIS_ONLY>
     __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
@@ -811,7 +819,7 @@ namespace mcrt
             const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
-            Hit<R> h = traceClosest(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            Hit<R> h = traceClosest<TRIS_ONLY>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
             rays++;
             // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
             if (h.prim == sm.x)
@@ -898,7 +906,7 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.
-    template <class R, int SLOTS, bool FILM>
+    template <class R, int SLOTS, bool FILM, uint32_t FEATS>
     __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK, 4) k_knn(WaveParams<R> p)
     {
         extern __shared__ __align__(16) unsigned char knn_smem[];
@@ -923,6 +931,7 @@ namespace mcrt
             ia.type = IA_DIFFUSE;
             ia.n1 = qr.pos_n1.w; ia.n2 = qr.nrm_n2.w; ia.Rf = qr.out_rf.w; ia.T = qr.weight_t.w;
             ia.material = &p.scene.materials[qr.meta.x];
+            ia.fmask = FEATS;   // the k BSDF evaluations of the estimate (photon-mapper.cpp:343-391)
             ia.out = qr.out_rf.xyz();
             ia.shading_cs = Frame<R>(qr.nrm_n2.xyz());
             ia.inside = qr.meta.z & 1u;

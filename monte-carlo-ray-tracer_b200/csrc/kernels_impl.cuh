@@ -10,17 +10,24 @@ namespace mcrt
     }
     template <> void Launch<MCRT_REAL>::extend(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        k_extend<MCRT_REAL><<<grid, 256, 0, s>>>(p, cur);
+        // triangle-only scenes (every OBJ scene) run the traversal without sphere / quadric code
+        if (p.scene.tris_only) k_extend<MCRT_REAL, true><<<grid, 256, 0, s>>>(p, cur);
+        else k_extend<MCRT_REAL, false><<<grid, 256, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        if (p.filmp.is_default_box) k_shade<MCRT_REAL, 0, false><<<grid * 2, 128, 0, s>>>(p, cur);
-        else k_shade<MCRT_REAL, 0, true><<<grid * 2, 128, 0, s>>>(p, cur);
+        // scenes whose materials use no Oren-Nayar / GGX / conductor Fresnel run the instantiation without that code
+        const bool lite = (p.scene.material_flags_any & ~SHADE_FEATS_LITE) == 0;
+        if (!p.filmp.is_default_box) k_shade<MCRT_REAL, 0, true, SHADE_FEATS_ALL><<<grid * 2, 128, 0, s>>>(p, cur);
+        else if (lite) k_shade<MCRT_REAL, 0, false, SHADE_FEATS_LITE><<<grid * 2, 128, 0, s>>>(p, cur);
+        else k_shade<MCRT_REAL, 0, false, SHADE_FEATS_ALL><<<grid * 2, 128, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shadePhoton(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
-        if (p.filmp.is_default_box) k_shade<MCRT_REAL, 1, false><<<grid * 2, 128, 0, s>>>(p, cur);
-        else k_shade<MCRT_REAL, 1, true><<<grid * 2, 128, 0, s>>>(p, cur);
+        const bool lite = (p.scene.material_flags_any & ~SHADE_FEATS_LITE) == 0;
+        if (!p.filmp.is_default_box) k_shade<MCRT_REAL, 1, true, SHADE_FEATS_ALL><<<grid * 2, 128, 0, s>>>(p, cur);
+        else if (lite) k_shade<MCRT_REAL, 1, false, SHADE_FEATS_LITE><<<grid * 2, 128, 0, s>>>(p, cur);
+        else k_shade<MCRT_REAL, 1, false, SHADE_FEATS_ALL><<<grid * 2, 128, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::knn(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
@@ -31,22 +38,29 @@ namespace mcrt
         if (!p.filmp.is_default_box)
         {
             // filtered film: the rare configuration, one generic instantiation
-            k_knn<MCRT_REAL, 0, true><<<g, b, smem, s>>>(p);
+            k_knn<MCRT_REAL, 0, true, SHADE_FEATS_ALL><<<g, b, smem, s>>>(p);
             return;
         }
-        switch (knnSlotsFor(p.pm.k_nearest))
+        const bool lite = (p.scene.material_flags_any & ~SHADE_FEATS_LITE) == 0;
+        const int slots = knnSlotsFor(p.pm.k_nearest);
+        #define MCRT_KNN_LAUNCH(SL) \
+            do { if (lite) k_knn<MCRT_REAL, SL, false, SHADE_FEATS_LITE><<<g, b, smem, s>>>(p); \
+                 else k_knn<MCRT_REAL, SL, false, SHADE_FEATS_ALL><<<g, b, smem, s>>>(p); } while (0)
+        switch (slots)
         {
-            case 1: k_knn<MCRT_REAL, 1, false><<<g, b, smem, s>>>(p); break;
-            case 2: k_knn<MCRT_REAL, 2, false><<<g, b, smem, s>>>(p); break;
-            case 4: k_knn<MCRT_REAL, 4, false><<<g, b, smem, s>>>(p); break;
-            case 8: k_knn<MCRT_REAL, 8, false><<<g, b, smem, s>>>(p); break;
-            default: k_knn<MCRT_REAL, 0, false><<<g, b, smem, s>>>(p); break;
+            case 1: MCRT_KNN_LAUNCH(1); break;
+            case 2: MCRT_KNN_LAUNCH(2); break;
+            case 4: MCRT_KNN_LAUNCH(4); break;
+            case 8: MCRT_KNN_LAUNCH(8); break;
+            default: MCRT_KNN_LAUNCH(0); break;
         }
+        #undef MCRT_KNN_LAUNCH
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
-        if (p.filmp.is_default_box) k_shadow<MCRT_REAL, false><<<grid, 256, 0, s>>>(p);
-        else k_shadow<MCRT_REAL, true><<<grid, 256, 0, s>>>(p);
+        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, false><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.tris_only) k_shadow<MCRT_REAL, false, true><<<grid, 256, 0, s>>>(p);
+        else k_shadow<MCRT_REAL, false, false><<<grid, 256, 0, s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {
