@@ -355,8 +355,12 @@ namespace
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.materials, a.materials, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.lights, a.lights, bytes))) return rc;
         d.n_nodes = s.n_nodes; d.n_prims = s.n_prims; d.n_lights = s.n_lights;
-        d.tris_only = 1;
-        for (uint32_t i = 0; i < s.n_prims; i++) if (s.prim_type[i] != MCRT_PRIM_TRIANGLE) { d.tris_only = 0; break; }
+        d.prims_class = PRIMS_TRI;
+        for (uint32_t i = 0; i < s.n_prims; i++)
+        {
+            if (s.prim_type[i] == MCRT_PRIM_SPHERE && d.prims_class == PRIMS_TRI) d.prims_class = PRIMS_TRI_SPHERE;
+            else if (s.prim_type[i] != MCRT_PRIM_TRIANGLE && s.prim_type[i] != MCRT_PRIM_SPHERE) { d.prims_class = PRIMS_ALL; break; }
+        }
         d.material_flags_any = 0;   // selects the k_shade feature set (kernels_impl.cuh)
         for (const auto& m : a.materials) d.material_flags_any |= m.flags;
         d.scene_ior = (R)s.scene_ior;

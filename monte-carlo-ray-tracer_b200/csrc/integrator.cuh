@@ -33,6 +33,9 @@
 #ifndef MCRT_TRACE_MINBLOCKS_F32
 #define MCRT_TRACE_MINBLOCKS_F32 4
 #endif
+#ifndef MCRT_TRACE_MINBLOCKS_F64_PRUNED   // double traversal without quadric code needs ~100 registers instead of 128
+#define MCRT_TRACE_MINBLOCKS_F64_PRUNED 4
+#endif
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 3
 #endif
@@ -224,10 +227,10 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     template <class R> struct Mode;
-    template <> struct Mode<double> { static constexpr bool parity = true; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F64; };
-    template <> struct Mode<float> { static constexpr bool parity = false; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F32; };
+    template <> struct Mode<double> { static constexpr bool parity = true; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F64; static constexpr int trace_minblocks_pruned = MCRT_TRACE_MINBLOCKS_F64_PRUNED; };
+    template <> struct Mode<float> { static constexpr bool parity = false; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F32; static constexpr int trace_minblocks_pruned = MCRT_TRACE_MINBLOCKS_F32; };
 
-    template <bool TRIS_ONLY = false, class R>
+    template <int PRIMS = PRIMS_ALL, class R>
     MCRT_D Hit<R> traceClosest(const DeviceScene<R>& sc, const V3<R>& o, const V3<R>& d, uint32_t skip_prim,
                                TraceCounters& cnt, uint32_t& overflow)
     {
@@ -235,11 +238,11 @@ namespace mcrt
         rq.o = o; rq.d = d; rq.inv_d = R(1) / d;
         if constexpr (Mode<R>::parity)
         {
-            return traverseReferenceOrder<TRIS_ONLY>(sc, rq, cnt, overflow);
+            return traverseReferenceOrder<PRIMS>(sc, rq, cnt, overflow);
         }
         else
         {
-            return traverseWide<TRIS_ONLY>(sc, rq, skip_prim, cnt, overflow);
+            return traverseWide<PRIMS>(sc, rq, skip_prim, cnt, overflow);
         }
     }
 
@@ -415,8 +418,8 @@ namespace mcrt
         c->n_knn = 0;
     }
 
-    template <class R, bool TRIS_ONLY>
-    __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_extend(WaveParams<R> p, int cur)
+    template <class R, int PRIMS>
+    __global__ void __launch_bounds__(256, PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
@@ -432,7 +435,7 @@ namespace mcrt
             uint32_t skip = NO_PRIM;
             if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
             const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
-            Hit<R> h = traceClosest<TRIS_ONLY>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
             p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
             rays++;
             // tail diagnostic: how much of the warp's time (~ its slowest ray) the average ray uses
@@ -806,8 +809,8 @@ namespace mcrt
         if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
-    template <class R, bool FILM, bool TRIS_ONLY>
-    __global__ void __launch_bounds__(256, Mode<R>::trace_minblocks) k_shadow(WaveParams<R> p)
+    template <class R, bool FILM, int PRIMS>
+    __global__ void __launch_bounds__(256, PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
         TraceCounters cnt = { 0u, 0u };
@@ -819,7 +822,7 @@ namespace mcrt
             const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
-            Hit<R> h = traceClosest<TRIS_ONLY>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
             rays++;
             // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
             if (h.prim == sm.x)

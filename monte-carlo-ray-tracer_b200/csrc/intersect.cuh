@@ -148,14 +148,16 @@ namespace mcrt
         return false;
     }
 
+    enum { PRIMS_ALL = 0, PRIMS_TRI_SPHERE = 1, PRIMS_TRI = 2 };
+
     // One ordered primitive against the ray; strict `t < best.t` acceptance (bvh.cpp:100).
-    // TRIS_ONLY: instantiation for scenes made of triangles only (every OBJ scene): no type dispatch,
-    // no sphere / quadric code in the traversal kernels.
-    template <bool TRIS_ONLY = false, class R>
+    // PRIMS: instantiations for scenes made of triangles only (every OBJ scene: no type dispatch at all)
+    // or of triangles and spheres (no quadric code) - the pruned branches are unreachable for them.
+    template <int PRIMS = PRIMS_ALL, class R>
     MCRT_D void testPrim(const DeviceScene<R>& sc, uint32_t prim, const RayQ<R>& ray, Hit<R>& best)
     {
         const V4<R> g0 = sc.geom[3 * prim + 0];
-        const uint32_t type = TRIS_ONLY ? (uint32_t)PRIM_TRIANGLE : (uint32_t)g0.w;
+        const uint32_t type = PRIMS == PRIMS_TRI ? (uint32_t)PRIM_TRIANGLE : (uint32_t)g0.w;
         R t, u = R(0), v = R(0);
         bool hit;
         if (type == PRIM_TRIANGLE)
@@ -164,7 +166,7 @@ namespace mcrt
             const V4<R> g2 = sc.geom[3 * prim + 2];
             hit = intersectTriangle(g0, g1, g2, ray, t, u, v);
         }
-        else if (type == PRIM_SPHERE)
+        else if (PRIMS == PRIMS_TRI_SPHERE || type == PRIM_SPHERE)
         {
             const V4<R> g1 = sc.geom[3 * prim + 1];
             hit = intersectSphere(g0, g1, ray, t);
@@ -230,7 +232,7 @@ namespace mcrt
         }
     };
 
-    template <bool TRIS_ONLY = false, class R>
+    template <int PRIMS = PRIMS_ALL, class R>
     MCRT_D Hit<R> traverseReferenceOrder(const DeviceScene<R>& sc, const RayQ<R>& ray, TraceCounters& cnt, uint32_t& overflow)
     {
         Hit<R> best;
@@ -239,7 +241,7 @@ namespace mcrt
         if (sc.n_nodes == 0)
         {
             // Scene::intersect without a bvh object: every surface in order
-            for (uint32_t i = 0; i < sc.n_prims; i++) testPrim<TRIS_ONLY>(sc, i, ray, best);
+            for (uint32_t i = 0; i < sc.n_prims; i++) testPrim<PRIMS>(sc, i, ray, best);
             cnt.prim_tests += sc.n_prims;
             return best;
         }
@@ -281,7 +283,7 @@ namespace mcrt
             if (done) break;
             {
                 const uint32_t count = cur_b & ~WIDE_LEAF;
-                for (uint32_t i = cur_a; i < cur_a + count; i++) testPrim<TRIS_ONLY>(sc, i, ray, best);
+                for (uint32_t i = cur_a; i < cur_a + count; i++) testPrim<PRIMS>(sc, i, ray, best);
                 cnt.prim_tests += count;
             }
             if (heap.size == 0 || heap.t[0] >= best.t) break;
@@ -309,7 +311,7 @@ namespace mcrt
 
     // skip_prim: ordered-primitive id the ray starts on when that primitive is planar (a ray
     // leaving a triangle cannot hit it again; float has no room for the reference's 1e-9 offset).
-    template <bool TRIS_ONLY = false>
+    template <int PRIMS = PRIMS_ALL>
     MCRT_D Hit<float> traverseWide(const DeviceScene<float>& sc, const RayQ<float>& ray, uint32_t skip_prim,
                                    TraceCounters& cnt, uint32_t& overflow)
     {
@@ -320,7 +322,7 @@ namespace mcrt
         {
             for (uint32_t i = 0; i < sc.n_prims; i++)
             {
-                if (i != skip_prim) testPrim<TRIS_ONLY>(sc, i, ray, best);
+                if (i != skip_prim) testPrim<PRIMS>(sc, i, ray, best);
             }
             cnt.prim_tests += sc.n_prims;
             return best;
@@ -382,7 +384,7 @@ namespace mcrt
                 const uint32_t count = cur_b & ~WIDE_LEAF;
                 for (uint32_t i = cur_a; i < cur_a + count; i++)
                 {
-                    if (i != skip_prim) testPrim<TRIS_ONLY>(sc, i, ray, best);
+                    if (i != skip_prim) testPrim<PRIMS>(sc, i, ray, best);
                 }
                 cnt.prim_tests += count;
             }

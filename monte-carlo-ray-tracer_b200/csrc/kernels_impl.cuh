@@ -11,8 +11,9 @@ namespace mcrt
     template <> void Launch<MCRT_REAL>::extend(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
         // triangle-only scenes (every OBJ scene) run the traversal without sphere / quadric code
-        if (p.scene.tris_only) k_extend<MCRT_REAL, true><<<grid, 256, 0, s>>>(p, cur);
-        else k_extend<MCRT_REAL, false><<<grid, 256, 0, s>>>(p, cur);
+        if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI><<<grid, 256, 0, s>>>(p, cur);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE><<<grid, 256, 0, s>>>(p, cur);
+        else k_extend<MCRT_REAL, PRIMS_ALL><<<grid, 256, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
@@ -58,9 +59,10 @@ namespace mcrt
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
-        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, false><<<grid, 256, 0, s>>>(p);
-        else if (p.scene.tris_only) k_shadow<MCRT_REAL, false, true><<<grid, 256, 0, s>>>(p);
-        else k_shadow<MCRT_REAL, false, false><<<grid, 256, 0, s>>>(p);
+        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE><<<grid, 256, 0, s>>>(p);
+        else k_shadow<MCRT_REAL, false, PRIMS_ALL><<<grid, 256, 0, s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {

@@ -101,7 +101,7 @@ namespace mcrt
         const Light<R>* lights;
         uint32_t n_nodes, n_prims, n_lights, n_wide_root; // n_wide_root: children of the root
         uint32_t root_is_leaf, root_first_prim, root_prim_count;
-        uint32_t tris_only, _pad3[3]; // 1: every primitive is a triangle (selects the pruned traversal kernels)
+        uint32_t prims_class, _pad3[3]; // PRIMS_ALL / PRIMS_TRI_SPHERE / PRIMS_TRI: selects the pruned traversal kernels
         uint32_t material_flags_any;   // OR of Material::flags over the scene: selects the k_shade feature set
         R root_bmin[3], root_bmax[3];
         R scene_ior;
