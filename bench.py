@@ -297,7 +297,9 @@ def run_gpu_arm(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.precision, {}).get("k_extend_dram_bytes_per_launch")
+            per_ray = json.load(f).get(args.precision, {}).get("k_extend_dram_bytes_per_ray")
+            # one ncu --set full capture of a full-pool launch, scaled to this run's average launch
+            traffic = per_ray * ext_rays / max(1, ext_launches) if per_ray else None
     except Exception:
         pass
     roofline = {
