@@ -102,6 +102,23 @@ namespace mcrt_host
             }
     }
 
+    void GpuRenderer::emitPhotons(const Camera& camera, uint64_t emissions, double caustic_factor, uint32_t max_photons_per_octree_leaf,
+                                  uint32_t k_nearest_photons, bool direct_visualization)
+    {
+        mcrt_photon_emit_params p{};
+        p.emissions = emissions;
+        p.caustic_factor = caustic_factor;
+        p.max_photons_per_octree_leaf = max_photons_per_octree_leaf;
+        p.k_nearest_photons = k_nearest_photons;
+        p.direct_visualization = direct_visualization ? 1u : 0u;
+        p.global_seed = global_seed_;
+        const BoundingBox bb = camera.integrator->scene.BB();   // the octrees' root box (photon-mapper.cpp:181-183)
+        for (int c = 0; c < 3; c++) { p.scene_bounds[c] = bb.min[c]; p.scene_bounds[3 + c] = bb.max[c]; }
+        uint64_t n_caustic = 0, n_global = 0;
+        check(mcrt_photon_emit(ctx_, &p, precision_, &n_caustic, &n_global, &stats_), "mcrt_photon_emit");
+        integrator_kind_ = MCRT_INTEGRATOR_PHOTON;
+    }
+
     void GpuRenderer::saveImage(const Camera& camera)
     {
         const Image& img = camera.image;

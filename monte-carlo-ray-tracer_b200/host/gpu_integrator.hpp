@@ -49,6 +49,13 @@ namespace mcrt_host
         // camera.image(x, y), through the camera's own Film filter (mcrt_set_film).
         void sampleImage(Camera& camera);
 
+        // First pass of PhotonMapper::PhotonMapper (photon-mapper.cpp:24-277) on the GPU instead of the CPU:
+        // photon emission and both photon octrees (mcrt_photon_emit). The camera is built WITHOUT photon
+        // mapping (a PathTracer, so the reference runs no CPU pass); afterwards this renderer renders
+        // photon-mapped. Arguments = the scene JSON's "photon_map" object (photon-mapper.cpp:28-36).
+        void emitPhotons(const Camera& camera, uint64_t emissions, double caustic_factor, uint32_t max_photons_per_octree_leaf = 200,
+                         uint32_t k_nearest_photons = 50, bool direct_visualization = false);
+
         // Camera::saveImage / Image::save (image.cpp:37-51) with exposure, tone mapping, gain, gamma and
         // byte conversion on the GPU (mcrt_image_tonemap); writes camera.savename + ".tga".
         void saveImage(const Camera& camera);
