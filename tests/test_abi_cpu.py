@@ -79,3 +79,29 @@ def test_python_mirror_is_complete(mcrt):
         assert hasattr(mcrt.Integrator, name), name
     for name in ("prim_bounds", "reordered", "unbuilt", "with_bvh", "cameras", "photon_maps"):
         assert hasattr(mcrt.Scene, name), name
+
+
+def test_scene_reorder_round_trip(mcrt):
+    """Scene.unbuilt() / with_bvh(): taking a packed scene back to Scene::surfaces order and re-attaching
+    the tree it was built with must give back the packed arrays (the host-side half of mcrt_bvh_build)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    for cid in ("c2_hexagon_room_96", "quadric_64", "veach_mis_64"):
+        scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, cid + ".mcrtpack"))
+        flat = scene.unbuilt()
+        assert flat.n_nodes == 0 and np.array_equal(flat.extra["prim_original"], np.arange(flat.n_prims))
+        # boxes follow the primitives through the permutation
+        assert np.array_equal(flat.prim_bounds()[scene.extra["prim_original"]], scene.prim_bounds())
+        tree = {k: scene.a[k] for k in ("node_bounds", "node_first_prim", "node_prim_count", "node_next_sibling")}
+        tree["prim_order"] = scene.extra["prim_original"]
+        back = flat.with_bvh(tree)
+        for k in mcrt.Scene._ARRAYS:
+            assert np.array_equal(back.a[k], scene.a[k]), (cid, k)
+        # every leaf box contains the boxes of its primitives; the root box is Scene::BB()
+        b = scene.prim_bounds()
+        nb = scene.a["node_bounds"].reshape(-1, 6)
+        for n in np.nonzero(scene.a["node_prim_count"])[0]:
+            f, c = int(scene.a["node_first_prim"][n]), int(scene.a["node_prim_count"][n])
+            assert (b[f:f + c, :3] >= nb[n, :3]).all() and (b[f:f + c, 3:] <= nb[n, 3:]).all()
+        assert np.array_equal(nb[0], scene.extra["scene_bounds"])
