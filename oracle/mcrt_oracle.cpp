@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <vector>
 
 #include "mcrt_abi.h"
@@ -841,6 +842,271 @@ void oracle_render_film(void* h, const mcrt_camera* cam, const mcrt_film* film, 
             out[3 * i + k] = v < 0.0 ? 0.0 : v;
         }
 }
+
+// BVH::BVH (bvh.cpp:13-78): the three hierarchy builders restated recursively, exactly in the
+// reference's order of operations, over primitive boxes (Surface::Base::BB()) instead of surfaces.
+namespace
+{
+    struct Box
+    {
+        double mn[3] = { 1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308 };
+        double mx[3] = { -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308 };
+        void merge(const Box& b) { for (int i = 0; i < 3; i++) { if (mn[i] > b.mn[i]) mn[i] = b.mn[i]; if (mx[i] < b.mx[i]) mx[i] = b.mx[i]; } }
+        void mergePoint(const double* p) { for (int i = 0; i < 3; i++) { if (mn[i] > p[i]) mn[i] = p[i]; if (mx[i] < p[i]) mx[i] = p[i]; } }
+        bool valid() const { for (int i = 0; i < 3; i++) if (mn[i] > mx[i]) return false; return true; }
+        double area() const   // bounding-box.cpp:35-40
+        {
+            if (!valid()) return 0.0;
+            const double dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+            return 2.0 * (dx * dy + dx * dz + dy * dz);
+        }
+        void centroid(double* c) const { for (int i = 0; i < 3; i++) c[i] = (mx[i] + mn[i]) / 2.0; }
+    };
+
+    struct BuildNode
+    {
+        Box BB;
+        std::vector<uint32_t> surfaces;      // primitive indices (BuildNode::surfaces)
+        std::vector<std::unique_ptr<BuildNode>> children;
+        uint32_t df_idx = 0;
+    };
+
+    struct BvhBuilder
+    {
+        const double* bounds;      // [n][6]
+        int bins_per_axis;
+        uint32_t df_idx = 0;
+        static constexpr size_t leaf_surfaces = 8, max_leaf_surfaces = 0xFF;   // bvh.hpp:91-92
+        static constexpr double EPS = 1e-9;
+
+        Box boxOf(uint32_t s) const { Box b; for (int i = 0; i < 3; i++) { b.mn[i] = bounds[6 * (size_t)s + i]; b.mx[i] = bounds[6 * (size_t)s + 3 + i]; } return b; }
+
+        void arbitrarySplit(BuildNode* node, size_t N)   // bvh.cpp:458-474
+        {
+            auto& S = node->surfaces;
+            N = std::min(N, S.size());
+            for (size_t i = 0; i < N; i++) node->children.push_back(std::make_unique<BuildNode>());
+            for (size_t i = 0; i < S.size(); i++)
+            {
+                BuildNode* c = node->children[i % N].get();
+                c->surfaces.push_back(S[i]);
+                c->BB.merge(boxOf(S[i]));
+            }
+            S.clear();
+        }
+
+        void binary(BuildNode* node)   // recursiveBuildBinarySAH, bvh.cpp:165-283
+        {
+            node->df_idx = df_idx++;
+            auto& S = node->surfaces;
+            if (S.size() <= leaf_surfaces) return;
+            Box extent;
+            double c[3];
+            for (uint32_t s : S) { boxOf(s).centroid(c); extent.mergePoint(c); }
+            const double dims[3] = { extent.mx[0] - extent.mn[0], extent.mx[1] - extent.mn[1], extent.mx[2] - extent.mn[2] };
+            const int axis = dims[0] > dims[1] ? (dims[0] > dims[2] ? 0 : 2) : (dims[1] > dims[2] ? 1 : 2);
+            if (dims[axis] < EPS)
+            {
+                if (S.size() > max_leaf_surfaces) { arbitrarySplit(node, 2); for (auto& ch : node->children) binary(ch.get()); }
+                return;
+            }
+            auto getIdx = [&](const double* cc)
+            {
+                const double f = (cc[axis] - extent.mn[axis]) / dims[axis];
+                const int idx = (int)std::floor(f * bins_per_axis);
+                return std::min(idx, bins_per_axis - 1);
+            };
+            std::vector<std::pair<size_t, Box>> bins(bins_per_axis);
+            for (auto& b : bins) b.first = 0;
+            for (uint32_t s : S) { const Box b = boxOf(s); b.centroid(c); const int idx = getIdx(c); bins[idx].first++; bins[idx].second.merge(b); }
+            double min_cost = std::numeric_limits<double>::max();
+            size_t split_bin = 0;
+            for (size_t i = 0; i + 1 < (size_t)bins_per_axis; i++)
+            {
+                size_t A_count = 0, B_count = 0;
+                Box A, B;
+                for (size_t j = 0; j < i + 1; j++) { A_count += bins[j].first; A.merge(bins[j].second); }
+                for (size_t j = i + 1; j < (size_t)bins_per_axis; j++) { B_count += bins[j].first; B.merge(bins[j].second); }
+                const double cost = 1.0 + (A_count * A.area() + B_count * B.area()) / node->BB.area();
+                if (cost < min_cost) { split_bin = i; min_cost = cost; }
+            }
+            if (min_cost > S.size())
+            {
+                if (S.size() > max_leaf_surfaces) { arbitrarySplit(node, 2); for (auto& ch : node->children) binary(ch.get()); }
+                return;
+            }
+            auto A = std::make_unique<BuildNode>(), B = std::make_unique<BuildNode>();
+            for (uint32_t s : S)
+            {
+                const Box b = boxOf(s); b.centroid(c);
+                BuildNode* t = (size_t)getIdx(c) <= split_bin ? A.get() : B.get();
+                t->surfaces.push_back(s); t->BB.merge(b);
+            }
+            S.clear();
+            if (!A->surfaces.empty()) { node->children.push_back(std::move(A)); binary(node->children.back().get()); }
+            if (!B->surfaces.empty()) { node->children.push_back(std::move(B)); binary(node->children.back().get()); }
+        }
+
+        void quaternary(BuildNode* node)   // recursiveBuildQuaternarySAH, bvh.cpp:285-432
+        {
+            node->df_idx = df_idx++;
+            const int nb = bins_per_axis;
+            auto& S = node->surfaces;
+            if (S.size() <= leaf_surfaces) return;
+            Box extent;
+            double c[3];
+            for (uint32_t s : S) { boxOf(s).centroid(c); extent.mergePoint(c); }
+            const double dims[3] = { extent.mx[0] - extent.mn[0], extent.mx[1] - extent.mn[1], extent.mx[2] - extent.mn[2] };
+            int ax, ay;
+            if (dims[0] > dims[1]) { ax = 0; ay = dims[1] > dims[2] ? 1 : 2; }
+            else if (dims[0] > dims[2]) { ax = 0; ay = 1; }
+            else { ax = 1; ay = 2; }
+            if (dims[ax] < EPS || dims[ay] < EPS) { df_idx--; binary(node); return; }
+            auto getIdx = [&](const double* cc, int& ix, int& iy)
+            {
+                const double fx = (cc[ax] - extent.mn[ax]) / dims[ax], fy = (cc[ay] - extent.mn[ay]) / dims[ay];
+                ix = std::min((int)std::floor(fx * (double)nb), nb - 1);
+                iy = std::min((int)std::floor(fy * (double)nb), nb - 1);
+            };
+            std::vector<std::pair<size_t, Box>> bins((size_t)nb * nb);
+            for (auto& b : bins) b.first = 0;
+            for (uint32_t s : S) { const Box b = boxOf(s); b.centroid(c); int ix, iy; getIdx(c, ix, iy); bins[(size_t)ix * nb + iy].first++; bins[(size_t)ix * nb + iy].second.merge(b); }
+            double min_cost = std::numeric_limits<double>::max();
+            int split_x = 0, split_y = 0;
+            for (int i = 0; i < nb - 1; i++)
+                for (int j = 0; j < nb - 1; j++)
+                {
+                    Box BBs[4]; size_t counts[4] = { 0, 0, 0, 0 };
+                    for (int v = 0; v < 4; v++)
+                    {
+                        const int x0 = (v & 1) ? i + 1 : 0, x1 = (v & 1) ? nb : i + 1;
+                        const int y0 = (v & 2) ? j + 1 : 0, y1 = (v & 2) ? nb : j + 1;
+                        for (int x = x0; x < x1; x++) for (int y = y0; y < y1; y++) { counts[v] += bins[(size_t)x * nb + y].first; BBs[v].merge(bins[(size_t)x * nb + y].second); }
+                    }
+                    double cost = 0.0;
+                    for (int v = 0; v < 4; v++) cost += BBs[v].area() * counts[v];
+                    cost = 1.0 + cost / node->BB.area();
+                    if (cost < min_cost) { split_x = i; split_y = j; min_cost = cost; }
+                }
+            if (min_cost > S.size())
+            {
+                if (S.size() > max_leaf_surfaces) { arbitrarySplit(node, 4); for (auto& ch : node->children) quaternary(ch.get()); }
+                return;
+            }
+            std::unique_ptr<BuildNode> fresh[4];
+            for (uint32_t s : S)
+            {
+                const Box b = boxOf(s); b.centroid(c);
+                int ix, iy; getIdx(c, ix, iy);
+                const int child = (ix > split_x ? 1 : 0) | (iy > split_y ? 2 : 0);
+                if (!fresh[child]) fresh[child] = std::make_unique<BuildNode>();
+                fresh[child]->surfaces.push_back(s); fresh[child]->BB.merge(b);
+            }
+            S.clear();
+            for (auto& ch : fresh) if (ch) { node->children.push_back(std::move(ch)); quaternary(node->children.back().get()); }
+        }
+
+        // Octree<SurfaceCentroid> insertion (octree.cpp:34-81) + recursiveBuildFromOctree (bvh.cpp:130-163);
+        // `cell` is the octree node's box. A cell splits when it holds more than leaf_surfaces centroids.
+        void octree(BuildNode* node, const Box& cell)
+        {
+            node->df_idx = df_idx++;
+            auto S = std::move(node->surfaces);
+            node->surfaces.clear();
+            Box BB;
+            if (S.size() <= leaf_surfaces)
+            {
+                node->surfaces = S;
+                for (uint32_t s : S) BB.merge(boxOf(s));
+            }
+            else
+            {
+                double origin[3], half[3], c[3];
+                cell.centroid(origin);
+                for (int i = 0; i < 3; i++) half[i] = (cell.mx[i] - cell.mn[i]) / 2.0;
+                std::vector<uint32_t> part[8];
+                for (uint32_t s : S)
+                {
+                    boxOf(s).centroid(c);
+                    int o = 0;
+                    for (int i = 0; i < 3; i++) if (c[i] >= origin[i]) o |= (4 >> i);
+                    part[o].push_back(s);
+                }
+                for (int o = 0; o < 8; o++)
+                {
+                    if (part[o].empty()) continue;
+                    Box child_cell;
+                    for (int i = 0; i < 3; i++)
+                    {
+                        const double no = origin[i] + half[i] * ((o & (4 >> i)) ? 0.5 : -0.5), h = half[i] * 0.5;
+                        child_cell.mn[i] = no - h; child_cell.mx[i] = no + h;
+                    }
+                    node->children.push_back(std::make_unique<BuildNode>());
+                    node->children.back()->surfaces = std::move(part[o]);
+                    octree(node->children.back().get(), child_cell);
+                    BB.merge(node->children.back()->BB);
+                }
+            }
+            node->BB = BB;
+        }
+    };
+
+    struct BvhOut
+    {
+        std::vector<double> bounds;
+        std::vector<uint32_t> first, count, next, order;
+    };
+
+    void compactBvh(const BuildNode* node, uint32_t next_sibling, BvhOut& out)   // BVH::compact, bvh.cpp:434-456
+    {
+        const uint32_t i = node->df_idx;
+        for (int k = 0; k < 3; k++) { out.bounds[6 * (size_t)i + k] = node->BB.mn[k]; out.bounds[6 * (size_t)i + 3 + k] = node->BB.mx[k]; }
+        out.next[i] = next_sibling;
+        out.first[i] = (uint32_t)out.order.size();
+        out.count[i] = (uint32_t)node->surfaces.size();
+        for (uint32_t s : node->surfaces) out.order.push_back(s);
+        for (size_t k = 0; k < node->children.size(); k++)
+            compactBvh(node->children[k].get(), k + 1 < node->children.size() ? node->children[k + 1]->df_idx : 0u, out);
+    }
+}
+
+// prim_bounds [n][6], scene_bounds = Scene::BB(); type / bins as mcrt_bvh_build. *out points into
+// memory owned by *handle (oracle_bvh_free).
+void oracle_bvh_build(const double* prim_bounds, uint32_t n, const double* scene_bounds, int type, int bins_per_axis, void** handle,
+                      mcrt_bvh_desc* out)
+{
+    BvhBuilder b;
+    b.bounds = prim_bounds;
+    b.bins_per_axis = bins_per_axis > 0 ? bins_per_axis : (type == MCRT_BVH_BINARY_SAH ? 16 : 8);
+    BuildNode root;
+    for (int i = 0; i < 3; i++) { root.BB.mn[i] = scene_bounds[i]; root.BB.mx[i] = scene_bounds[3 + i]; }
+    root.surfaces.resize(n);
+    for (uint32_t i = 0; i < n; i++) root.surfaces[i] = i;
+    if (type == MCRT_BVH_QUATERNARY_SAH) b.quaternary(&root);
+    else if (type == MCRT_BVH_BINARY_SAH) b.binary(&root);
+    else
+    {
+        // bvh.cpp:44-47: cube around the scene box
+        double c[3], m = 0.0;
+        root.BB.centroid(c);
+        for (int i = 0; i < 3; i++) m = std::max(m, root.BB.mx[i] - root.BB.mn[i]);
+        const double half_max = m / 2.0;
+        Box cube;
+        for (int i = 0; i < 3; i++) { cube.mn[i] = c[i] - half_max; cube.mx[i] = c[i] + half_max; }
+        b.octree(&root, cube);
+    }
+    auto* o = new BvhOut();
+    const uint32_t n_nodes = b.df_idx;
+    o->bounds.resize(6 * (size_t)n_nodes); o->first.resize(n_nodes); o->count.resize(n_nodes); o->next.resize(n_nodes);
+    compactBvh(&root, 0u, *o);
+    std::memset(out, 0, sizeof(*out));
+    out->n_nodes = n_nodes; out->n_prims = n;
+    out->node_bounds = o->bounds.data(); out->node_first_prim = o->first.data(); out->node_prim_count = o->count.data();
+    out->node_next_sibling = o->next.data(); out->prim_order = o->order.data();
+    *handle = o;
+}
+
+void oracle_bvh_free(void* handle) { delete static_cast<BvhOut*>(handle); }
 
 // Octree<Photon> insertion + LinearOctree::compact (octree.cpp:34-81, linear-octree.cpp:201-244),
 // restated top-down. The reference inserts photons one by one; a node ends up internal exactly when

@@ -27,6 +27,8 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+        L.oracle_bvh_free.argtypes = [C.c_void_p]
         L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.oracle_octree_free.argtypes = [C.c_void_p]
         L.oracle_image_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -43,6 +45,23 @@ def sampler_stream(pixel, sample, n_shuffles, seed):
     pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
     out = np.zeros((len(pixel), 7), dtype=np.uint32)
     lib().oracle_sampler_stream(_p(pixel), _p(sample), len(pixel), n_shuffles, seed, _p(out))
+    return out
+
+
+def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis, desc_type):
+    """BVH::BVH restated (scalar, host). bvh_type: 0 octree, 1 binary_sah, 2 quaternary_sah; desc_type: the
+    product's BvhDesc ctypes struct (layout only). -> dict of node arrays + prim_order."""
+    prim_bounds = np.ascontiguousarray(prim_bounds, dtype=np.float64).reshape(-1, 6)
+    scene_bounds = np.ascontiguousarray(scene_bounds, dtype=np.float64).reshape(6)
+    h, d = C.c_void_p(), desc_type()
+    lib().oracle_bvh_build(_p(prim_bounds), len(prim_bounds), _p(scene_bounds), int(bvh_type), int(bins_per_axis), C.byref(h), C.addressof(d))
+
+    def arr(ptr, count, dtype):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype).copy() if count else np.zeros(0, dtype)
+    out = dict(node_bounds=arr(d.node_bounds, d.n_nodes * 6, np.float64).reshape(-1, 6), node_first_prim=arr(d.node_first_prim, d.n_nodes, np.uint32),
+               node_prim_count=arr(d.node_prim_count, d.n_nodes, np.uint32), node_next_sibling=arr(d.node_next_sibling, d.n_nodes, np.uint32),
+               prim_order=arr(d.prim_order, d.n_prims, np.uint32))
+    lib().oracle_bvh_free(h)
     return out
 
 

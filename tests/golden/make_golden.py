@@ -204,6 +204,61 @@ def make_obj_kat():
     print("obj_kat:", {k: v.shape for k, v in r.items() if hasattr(v, "shape")}, "negative throws:", threw)
 
 
+BVH_KAT_TYPES = [("binary_sah", 16), ("quaternary_sah", 8), ("binary_sah", 4), ("quaternary_sah", 3), ("octree", 0)]
+
+
+def make_bvh_kat():
+    """BVH::BVH of the reference on synthetic sphere sets that reach the builders' rare branches
+    (arbitrarySplit after a degenerate extent or a failed SAH cost test, the quaternary -> binary
+    fall-back) -> bvh_kat.npz. Spheres are the simplest surface whose box is exact (origin +- radius)."""
+    import json
+    import tempfile
+    rng = np.random.default_rng(99)
+    template = json.load(open("/root/reference/scenes/ior_test.json"))
+    material = template["surfaces"][0]["material"]
+
+    def blobs():
+        sets = {}
+        sets["random_400"] = (rng.uniform(-5, 5, (400, 3)), rng.uniform(0.05, 0.6, 400))
+        sets["coincident_600"] = (np.tile([[1.0, 2.0, 3.0]], (600, 1)), rng.uniform(0.1, 0.5, 600))
+        line = np.zeros((700, 3)); line[:, 0] = rng.uniform(-20, 20, 700); line[:, 1] = 0.5; line[:, 2] = -1.25
+        sets["line_700"] = (line, rng.uniform(0.05, 0.3, 700))
+        cl = np.concatenate([np.tile([[0.0, 0.0, 0.0]], (300, 1)), np.tile([[4.0, 0.5, 0.0]], (300, 1)),
+                             np.tile([[0.0, 3.0, -2.0]], (300, 1)), rng.uniform(-6, 6, (100, 3))])
+        sets["clusters_1000"] = (cl[rng.permutation(len(cl))], rng.uniform(0.05, 0.4, 1000))
+        sets["sah_fail_500"] = (rng.uniform(-1e-3, 1e-3, (500, 3)), rng.uniform(8.0, 12.0, 500))
+        plane = np.zeros((900, 3)); plane[:, 0] = rng.uniform(-3, 3, 900); plane[:, 2] = rng.uniform(-3, 3, 900); plane[:, 1] = 2.0
+        sets["plane_900"] = (plane, rng.uniform(0.02, 0.2, 900))
+        return sets
+
+    out = {"types": json.dumps(BVH_KAT_TYPES)}
+    names = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (pos, rad) in blobs().items():
+            j = dict(template)
+            j.pop("bvh", None)
+            j["surfaces"] = [dict(type="sphere", material=material, radius=float(r), position=[float(x) for x in p])
+                             for p, r in zip(pos, rad)]
+            with open(os.path.join(tmp, name + ".json"), "w") as f:
+                json.dump(j, f)
+            s = ref.RefScene(name + ".json", dict(width=8, height=8, sqrtspp=1), scenes=tmp)
+            bounds, scene_bounds = s.prim_bounds()
+            assert np.array_equal(bounds[:, :3], pos - rad[:, None]) and np.array_equal(bounds[:, 3:], pos + rad[:, None])
+            out[f"{name}/prim_bounds"] = bounds; out[f"{name}/scene_bounds"] = scene_bounds
+            names.append(name)
+            for t, b in BVH_KAT_TYPES:
+                if t == "octree" and name != "random_400":
+                    continue   # > 8 coincident centroids: the reference's octree recursion does not terminate
+                r = s.build_bvh(t, b)
+                for k in ("node_bounds", "node_first_prim", "node_prim_count", "node_next_sibling", "prim_order"):
+                    out[f"{name}/{t}:{b}/{k}"] = r[k]
+                inner = r["node_prim_count"] == 0
+                print(f"bvh_kat {name} {t}:{b}: {len(inner)} nodes, max leaf {r['node_prim_count'].max()}")
+            s.close()
+    out["sets"] = json.dumps(names)
+    np.savez_compressed(os.path.join(HERE, "bvh_kat.npz"), **out)
+
+
 def make_sampler_kat(rng):
     ref.set_seed(SEED)
     n = 8192
@@ -282,3 +337,5 @@ if __name__ == "__main__":
         make_image_kat()
     if not only or "obj_kat" in only:
         make_obj_kat()
+    if not only or "bvh_kat" in only:
+        make_bvh_kat()

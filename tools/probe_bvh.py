@@ -36,8 +36,27 @@ def compare(got, ref, label):
     return ok
 
 
+def probe_kat(results):
+    """tests/golden/bvh_kat.npz: sphere sets that reach arbitrarySplit / the quaternary->binary fall-back."""
+    path = os.path.join(ROOT, "tests", "golden", "bvh_kat.npz")
+    z = np.load(path)
+    for name in json.loads(str(z["sets"])):
+        for t, b in json.loads(str(z["types"])):
+            key = f"{name}/{t}:{b}"
+            if f"{key}/node_first_prim" not in z.files:
+                continue
+            ref = {k: z[f"{key}/{k}"] for k in ("node_bounds", "node_first_prim", "node_prim_count", "node_next_sibling", "prim_order")}
+            got = mcrt.bvh_build(z[f"{name}/prim_bounds"], z[f"{name}/scene_bounds"], t, int(b))
+            ok = compare(got, ref, key)
+            print(f"kat {key}: {'IDENTICAL' if ok else 'DIFFERENT'} nodes {len(got['node_first_prim'])} rounds {got['rounds']}")
+            results["kat " + key] = dict(identical=bool(ok), nodes=int(len(got["node_first_prim"])), rounds=got["rounds"])
+
+
 if __name__ == "__main__":
     results = {}
+    if "kat" in sys.argv[1:]:
+        sys.argv.remove("kat")
+        probe_kat(results)
     for name in (sys.argv[1:] or ["spaceship", "lego_bulldozer"]):
         path = os.path.join(ROOT, "bench_data", f"bvh_{name}.npz")
         if not os.path.exists(path):
