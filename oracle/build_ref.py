@@ -73,8 +73,11 @@ def build(reference="/root/reference", force=False, with_data=()):
     own_units = [
         os.path.join(ROOT, "oracle", "ref_driver.cpp"),
         os.path.join(ROOT, "monte-carlo-ray-tracer_b200", "host", "exporter.cpp"),
+        os.path.join(ROOT, "monte-carlo-ray-tracer_b200", "host", "obj_loader.cpp"),
     ]
     own_deps = [seed_pin,
+                os.path.join(ROOT, "monte-carlo-ray-tracer_b200", "host", "obj_loader.hpp"),
+                os.path.join(ROOT, "monte-carlo-ray-tracer_b200", "host", "obj_adapter.hpp"),
                 os.path.join(ROOT, "include", "mcrt_abi.h"),
                 os.path.join(ROOT, "monte-carlo-ray-tracer_b200", "host", "exporter.hpp")]
 

@@ -49,6 +49,7 @@ def lib():
         L.ref_prim_bounds.argtypes = [C.c_void_p] * 3
         L.ref_obj_parse.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_obj_copy.argtypes = [C.c_void_p] * 5
+        L.ref_obj_adapter_check.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ref_vertex_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_image_save.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_fresnel_dielectric.restype = C.c_double
@@ -168,6 +169,10 @@ class RefScene:
         lib().ref_obj_copy(_p(out["vertices"]), _p(out["normals"]), _p(out["tri_v"]), _p(out["tri_vt"]), _p(out["tri_vn"]))
         out["seconds"] = sec.value
         return out
+
+    def obj_adapter_check(self, path, with_normals=True):
+        """host/obj_adapter.hpp (the drop-in bodies for Scene::parseOBJ / generateVertexNormals) vs the reference's."""
+        return lib().ref_obj_adapter_check(self.h, os.fsencode(path), int(with_normals))
 
     def vertex_normals(self, vertices, tri_v):
         """Scene::generateVertexNormals -> ([n, 3], seconds)."""

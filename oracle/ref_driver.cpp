@@ -29,6 +29,7 @@
 
 #include <nlohmann/json.hpp>
 
+#include "obj_adapter.hpp"
 #include "bvh/bvh.hpp"
 #include "camera/camera.hpp"
 #include "common/option.hpp"
@@ -465,6 +466,37 @@ void ref_obj_copy(double* v, double* n, uint64_t* tv, uint64_t* tvt, uint64_t* t
     for (size_t i = 0; i < g_obj.n.size(); i++) for (int c = 0; c < 3; c++) n[3 * i + c] = g_obj.n[i][c];
     auto copy = [](const std::vector<std::vector<size_t>>& src, uint64_t* dst) { for (size_t i = 0; i < src.size(); i++) for (int c = 0; c < 3; c++) dst[3 * i + c] = src[i][c]; };
     copy(g_obj.tv, tv); copy(g_obj.tvt, tvt); copy(g_obj.tvn, tvn);
+}
+
+// The drop-in bodies of host/obj_adapter.hpp (what a maintainer puts into Scene::parseOBJ /
+// generateVertexNormals) against the reference's own: 1 = every container equal.
+int ref_obj_adapter_check(void* handle, const char* path, int with_normals)
+{
+    Handle* h = static_cast<Handle*>(handle);
+    const Scene& scene = h->camera->integrator->scene;
+    ParsedObj a, b;
+    try
+    {
+        CoutSilencer quiet;
+        scene.parseOBJ(path, a.v, a.n, a.tv, a.tvt, a.tvn);
+        mcrt_host::parseOBJ(path, b.v, b.n, b.tv, b.tvt, b.tvn);
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+    if (!(a.v == b.v && a.n == b.n && a.tv == b.tv && a.tvt == b.tvt && a.tvn == b.tvn)) return 0;
+    if (with_normals)
+    {
+        std::vector<glm::dvec3> na, nb;
+        try { scene.generateVertexNormals(na, a.v, a.tv); mcrt_host::generateVertexNormals(nb, b.v, b.tv); }
+        catch (const std::exception&) { return -2; }
+        if (na.size() != nb.size()) return 0;
+        for (size_t i = 0; i < na.size(); i++)
+            for (int c = 0; c < 3; c++)
+                if (!(na[i][c] == nb[i][c] || (na[i][c] != na[i][c] && nb[i][c] != nb[i][c]))) return 0;
+    }
+    return 1;
 }
 
 // Scene::generateVertexNormals (scene.cpp:326-355)

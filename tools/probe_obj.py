@@ -34,6 +34,7 @@ if __name__ == "__main__":
             t0 = time.perf_counter(); n_got = mcrt.vertex_normals(g["vertices"], g["tri_v"]); dt = time.perf_counter() - t0
             msg += (f"; vertex normals {'IDENTICAL' if np.array_equal(n_ref, n_got, equal_nan=True) else 'DIFFERENT'}: "
                     f"reference {sec * 1e3:.0f} ms, parallel {dt * 1e3:.0f} ms")
+        msg += f"; drop-in bodies (host/obj_adapter.hpp) vs the reference's: {'EQUAL' if s.obj_adapter_check(f) == 1 else 'DIFFERENT'}"
         print(msg, flush=True)
         lines.append(msg)
     with open(os.path.join(ROOT, "profiles", "r1_obj_loader.txt"), "w") as f:
