@@ -43,9 +43,14 @@ WORKLOADS = {
     "c1": ("bench_data/c1_hexagon_room_diffuse.mcrtpack", "hexagon_room_diffuse.json",
            dict(width=256, height=256, sqrtspp=2, bvh_type="binary_sah", bins_per_axis=16),
            "hexagon_room_diffuse.json 256x256 4spp binary_sah"),
-    "c3": ("bench_data/c3_spaceship.mcrtpack.xz", "spaceship.json",
+    # OBJ scenes: packs written by `python tools/validate_big.py make` (git-ignored, 35-81 MB); the camera is
+    # resized to the BASELINE configuration
+    "c3": ("bench_data/v3_spaceship.mcrtpack.xz", "spaceship.json",
            dict(width=1920, height=1080, sqrtspp=32),
            "spaceship.json 1920x1080 1024spp quaternary_sah"),
+    "c5": ("bench_data/v5_lego_bulldozer.mcrtpack.xz", "lego_bulldozer.json",
+           dict(width=3840, height=2160, sqrtspp=64),
+           "lego_bulldozer.json 3840x2160 4096spp quaternary_sah"),
 }
 
 METRIC = "Mray/s (primary+shadow+bounce)"
@@ -186,8 +191,12 @@ def run_gpu_arm(args):
 
     m = importlib.import_module("monte-carlo-ray-tracer_b200")
     pack, _, _, label = WORKLOADS[args.workload]
+    if not os.path.exists(os.path.join(ROOT, pack)):
+        raise SystemExit(f"bench.py: {pack} is missing - generate it with `python tools/validate_big.py make` where /root/reference exists")
     scene = m.Scene.from_pack(os.path.join(ROOT, pack))
     cam = scene.cameras()[0]
+    ov = WORKLOADS[args.workload][2]
+    cam = cam.resized(ov["width"], ov["height"], ov["sqrtspp"])
     if args.sqrtspp:
         cam = cam.resized(cam.width, cam.height, args.sqrtspp)
     precision = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32

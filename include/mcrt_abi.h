@@ -167,7 +167,10 @@ typedef struct mcrt_stats {
     uint64_t shadow_box_tests, shadow_prim_tests; /* k_shadow's share of box_tests / prim_tests */
     /* k_extend warp-tail diagnostic: sum over rays of (box+prim tests) / sum over warps of
      * 32*max over the warp's rays = the lane utilisation lost to uneven ray lengths alone */
-    uint64_t extend_work_sum, extend_work_warpmax;
+    uint64_t extend_work_sum, extend_work_warpmax; /* builds with -DMCRT_TAIL_DIAGNOSTIC only, else 0 */
+    /* parity mode: closest-hit queries whose two nearest candidates lay within rounding distance of each
+     * other and were therefore re-traced in the reference's own visiting order (csrc/bvh4.cuh) */
+    uint64_t replayed_rays;
 } mcrt_stats;
 
 typedef struct mcrt_ctx mcrt_ctx;

@@ -152,7 +152,8 @@ class Stats(C.Structure):
                 ("gpu_ms_shade", C.c_double), ("gpu_ms_shadow", C.c_double), ("gpu_ms_knn", C.c_double),
                 ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
                 ("shadow_box_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
-                ("extend_work_sum", C.c_uint64), ("extend_work_warpmax", C.c_uint64)]
+                ("extend_work_sum", C.c_uint64), ("extend_work_warpmax", C.c_uint64),
+                ("replayed_rays", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("_")}

@@ -64,6 +64,8 @@ struct mcrt_ctx
     DeviceScene<double> scene64;
     DeviceScene<float> scene32;
     float scene_scale = 1.0f;
+    uint32_t n_bvh4_nodes = 0;
+    int exact_traversal = 0;   // 1: every ray takes the reference-order replay (traverseReferenceOrder)
 
     WaveBuffers<double> wave64;
     WaveBuffers<float> wave32;
@@ -342,6 +344,109 @@ namespace
         return MCRT_OK;
     }
 
+
+    // The reference's tree collapsed to <= 4 children per node for traverseFast (bvh4.cuh). Any tree over
+    // the same ordered primitives with exactly containing boxes serves: the boxes only decide which
+    // primitives get tested. Inner children are pulled up greedily by box area (largest first) while
+    // the node has room; nodes with more than 4 children (the reference's octree type has up to 8) get
+    // intermediate nodes over consecutive runs of children. Float boxes are rounded outwards.
+    int buildBvh4(mcrt_ctx* ctx, const mcrt_scene_desc& s, std::vector<Bvh4Node>& out)
+    {
+        out.clear();
+        if (s.n_nodes == 0) return MCRT_OK;
+        if (s.n_prims >= BVH4_MAX_PRIMS) return MCRT_OK;   // leaf references hold 23 bits: such scenes use the replay traversal
+        auto lower = [](double v) { float r = (float)v; if ((double)r > v) r = std::nextafter(r, -INFINITY); return r; };
+        auto upper = [](double v) { float r = (float)v; if ((double)r < v) r = std::nextafter(r, INFINITY); return r; };
+        struct Item { int64_t node; std::vector<Item> group; double box[6]; };   // node >= 0: reference node; -1: run of items
+        auto itemOfNode = [&](uint32_t n) { Item it; it.node = n; for (int k = 0; k < 6; k++) it.box[k] = s.node_bounds[6 * (size_t)n + k]; return it; };
+        auto area = [](const double* b) { const double x = b[3] - b[0], y = b[4] - b[1], z = b[5] - b[2]; return x * y + y * z + z * x; };
+        auto childrenOf = [&](uint32_t node, std::vector<Item>& kids)
+        {
+            uint32_t c = node + 1;
+            while (c != 0 && c < s.n_nodes) { kids.push_back(itemOfNode(c)); c = s.node_next_sibling[c]; }
+        };
+        auto isInner = [&](const Item& it) { return it.node < 0 || s.node_prim_count[it.node] == 0; };
+        auto expand = [&](const Item& it, std::vector<Item>& kids) { if (it.node < 0) kids = it.group; else { kids.clear(); childrenOf((uint32_t)it.node, kids); } };
+        auto shape = [&](std::vector<Item>& kids)
+        {
+            // pull grandchildren up while there is room
+            while (kids.size() < 4)
+            {
+                int pick = -1; double pick_area = -1.0; std::vector<Item> sub, best_sub;
+                for (size_t i = 0; i < kids.size(); i++)
+                {
+                    if (!isInner(kids[i])) continue;
+                    expand(kids[i], sub);
+                    if (sub.empty() || kids.size() - 1 + sub.size() > 4) continue;
+                    const double a = area(kids[i].box);
+                    if (a > pick_area) { pick_area = a; pick = (int)i; best_sub = sub; }
+                }
+                if (pick < 0) break;
+                kids.erase(kids.begin() + pick);
+                kids.insert(kids.begin() + pick, best_sub.begin(), best_sub.end());
+            }
+            // too many: intermediate nodes over consecutive runs
+            while (kids.size() > 4)
+            {
+                std::vector<Item> packed;
+                for (size_t i = 0; i < kids.size(); i += 4)
+                {
+                    const size_t e = std::min(kids.size(), i + 4);
+                    if (e - i == 1) { packed.push_back(kids[i]); continue; }
+                    Item g; g.node = -1; g.group.assign(kids.begin() + i, kids.begin() + e);
+                    for (int k = 0; k < 3; k++) { g.box[k] = 1e300; g.box[3 + k] = -1e300; }
+                    for (const Item& c : g.group) for (int k = 0; k < 3; k++) { g.box[k] = std::min(g.box[k], c.box[k]); g.box[3 + k] = std::max(g.box[3 + k], c.box[3 + k]); }
+                    packed.push_back(std::move(g));
+                }
+                kids.swap(packed);
+            }
+        };
+        auto leafRef = [&](uint32_t node, uint32_t& ref) -> bool
+        {
+            const uint32_t first = s.node_first_prim[node], count = s.node_prim_count[node];
+            if (count > 255u) return false;
+            ref = BVH4_LEAF | (first << 8) | count;
+            return true;
+        };
+        struct Pending { Item item; uint32_t parent, slot; };
+        std::vector<Pending> queue;   // breadth-first: the top of the tree is contiguous
+        auto emit = [&](std::vector<Item>& kids, uint32_t self) -> int
+        {
+            shape(kids);
+            Bvh4Node n;
+            std::memset(&n, 0, sizeof(n));
+            for (int c = 0; c < 4; c++) for (int k = 0; k < 3; k++) { n.lo[k][c] = 3.0e38f; n.hi[k][c] = -3.0e38f; }
+            for (size_t c = 0; c < kids.size(); c++)
+            {
+                for (int k = 0; k < 3; k++) { n.lo[k][c] = lower(kids[c].box[k]); n.hi[k][c] = upper(kids[c].box[3 + k]); }
+                if (!isInner(kids[c]))
+                {
+                    if (!leafRef((uint32_t)kids[c].node, n.child[c])) return 1;
+                }
+                else queue.push_back({ kids[c], self, (uint32_t)c });
+            }
+            out[self] = n;
+            return 0;
+        };
+        std::vector<Item> kids;
+        out.emplace_back();
+        if (s.node_prim_count[0]) kids.push_back(itemOfNode(0));   // the root is a leaf: one child
+        else childrenOf(0, kids);
+        bool too_big = emit(kids, 0) != 0;
+        for (size_t q = 0; q < queue.size() && !too_big; q++)
+        {
+            const Pending pn = queue[q];   // copy: emit() grows the queue
+            const uint32_t self = (uint32_t)out.size();
+            out.emplace_back();
+            out[pn.parent].child[pn.slot] = self;
+            expand(pn.item, kids);
+            too_big = emit(kids, self) != 0;
+        }
+        if (too_big) out.clear();   // a leaf with more than 255 primitives: the replay traversal handles the scene
+        (void)ctx;
+        return MCRT_OK;
+    }
+
     template <class R>
     int uploadArrays(mcrt_ctx* ctx, const mcrt_scene_desc& s, SceneArrays<R>& a, uint64_t& bytes)
     {
@@ -461,6 +566,7 @@ namespace
         st->shadow_prim_tests = c.shadow_prim_tests;
         st->extend_work_sum = c.work_sum;
         st->extend_work_warpmax = c.work_warpmax;
+        st->replayed_rays = c.replayed_rays;
     }
 
     // The wavefront loop shared by mcrt_render_rows(_dev) and mcrt_sample_rays.
@@ -509,6 +615,7 @@ namespace
         WaveParams<R> p;
         std::memset(&p, 0, sizeof(p));
         p.scene = sceneOf<R>(ctx);
+        if (ctx->exact_traversal) p.scene.bvh4 = nullptr;
         if (cam)
         {
             p.camera.eye = v3<R>(cam->eye); p.camera.forward = v3<R>(cam->forward);
@@ -552,8 +659,9 @@ namespace
             {
                 // source-primitive keys for scenes with enough primitives to index space finely
                 const uint32_t n_prims = sceneOf<R>(ctx).n_prims;
-                const bool use_prim = ctx->sort_prim_key < 0 ? n_prims >= 4096u : ctx->sort_prim_key != 0;
                 const double cells = (double)(1u << (3 * SORT_ORIGIN_BITS));
+                // fewer primitives than cells: the scale would not fit 32 bits, and origin cells are finer anyway
+                const bool use_prim = (ctx->sort_prim_key < 0 ? n_prims >= 4096u : ctx->sort_prim_key != 0) && (double)n_prims >= cells;
                 p.sort.prim_scale = use_prim ? (uint32_t)(cells * 4294967296.0 / (double)n_prims * 0.999999) : 0u;
             }
             for (int k = 0; k < 3; k++)
@@ -720,6 +828,13 @@ namespace
             ctx->error = "traversal stack/heap overflow: result would differ from the reference";
             return MCRT_ERR_UNSUPPORTED;
         }
+        if (c.ior_stack_overflows)
+        {
+            // RefractionHistory::iors is an unbounded vector in the reference (ray.cpp:74-98); the device
+            // stack holds IOR_STACK_CAPACITY nested media. Beyond that externalIOR would be wrong: refuse.
+            ctx->error = "more than 8 nested dielectric media on a path (refraction-history stack overflow): result would differ from the reference";
+            return MCRT_ERR_UNSUPPORTED;
+        }
         if (emitting && c.photon_overflow)
         {
             ctx->error = "photon arrays overflowed";
@@ -842,6 +957,7 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "sort_rays") { ctx->sort_rays = value != 0.0; }
     else if (k == "sort_shade") { ctx->sort_shade = value != 0.0; }
     else if (k == "sort_prim_key") { ctx->sort_prim_key = (int)value; }
+    else if (k == "exact_traversal") { ctx->exact_traversal = value != 0.0; }
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }
@@ -916,6 +1032,11 @@ int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d
         std::memset(&a.dev, 0, sizeof(a.dev));
         if ((rc = buildWide(ctx, s, a))) return rc;
         if ((rc = uploadArrays(ctx, s, a, bytes))) return rc;
+        std::vector<Bvh4Node> bvh4;
+        if ((rc = buildBvh4(ctx, s, bvh4))) return rc;
+        a.dev.bvh4 = nullptr;
+        if (!bvh4.empty() && (rc = devUpload(ctx, ctx->scene_allocs, &a.dev.bvh4, bvh4, bytes))) return rc;
+        ctx->n_bvh4_nodes = (uint32_t)bvh4.size();
         CK(cudaStreamSynchronize(ctx->stream)); // host vectors die at scope exit
         ctx->scene64 = a.dev;
     }
@@ -943,6 +1064,9 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, c
     if (!caustic_map || !global_map || k_nearest == 0) { ctx->error = "mcrt_photon_upload: invalid arguments"; return MCRT_ERR_INVALID; }
     if (k_nearest > 1024) { ctx->error = "k_nearest_photons > 1024 unsupported"; return MCRT_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(ctx->device));
+    // the maps mcrt_photon_emit built live in photon_allocs too: forget them before they are freed
+    ctx->built_valid = false;
+    for (int w = 0; w < 2; w++) { ctx->built_dev[w] = PhotonOctreeDevice(); ctx->built_host_current[w] = false; ctx->photon_map[w] = DevicePhotonMap(); }
     freeAll(ctx->photon_allocs);
     ctx->has_photons = false;
     uint64_t bytes = 0;
@@ -1004,6 +1128,7 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
     if (!params || params->emissions == 0 || !(params->caustic_factor > 0.0) || params->max_photons_per_octree_leaf == 0 ||
         params->k_nearest_photons == 0)
     { ctx->error = "mcrt_photon_emit: invalid parameters"; return MCRT_ERR_INVALID; }
+    if (params->k_nearest_photons > 1024) { ctx->error = "k_nearest_photons > 1024 unsupported"; return MCRT_ERR_UNSUPPORTED; }
     if (!ctx->has_scene) { ctx->error = "no scene uploaded"; return MCRT_ERR_NO_SCENE; }
     CK(cudaSetDevice(ctx->device));
     const DeviceScene<double>& sc = ctx->scene64;
@@ -1051,7 +1176,7 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
     }
     ctx->d_emit_offsets = d_off; ctx->d_emit_flux = d_flux;
     ctx->emit_non_caustic_reject = 1.0 / params->caustic_factor;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cleanup(); ctx->error = "mcrt_photon_emit: upload failed"; return MCRT_ERR_CUDA; }
 
     if (precision == MCRT_PRECISION_F64)
         rc = runWavefront<double>(ctx, nullptr, 0, 1, 0, 1, total, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
@@ -1083,7 +1208,6 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
         ctx->photon_build_ms += ctx->built_dev[w].gpu_ms;
     }
     cleanup();
-    if (params->k_nearest_photons > 1024) { ctx->error = "k_nearest_photons > 1024 unsupported"; return MCRT_ERR_UNSUPPORTED; }
     ctx->k_nearest = params->k_nearest_photons;
     ctx->direct_visualization = params->direct_visualization;
     ctx->has_photons = true;
@@ -1354,7 +1478,12 @@ int mcrt_trace_closest(mcrt_ctx* ctx, const mcrt_ray* rays, size_t n, int precis
     cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), s);
     const int grid = ctx->sm_count * ctx->blocks_per_sm;
     cudaEventRecord(ctx->ev_start, s);
-    if (precision == MCRT_PRECISION_F64) Launch<double>::traceUser(ctx->scene64, d_rays, n, d_tuv, d_prim, ctx->d_counters, grid, s);
+    if (precision == MCRT_PRECISION_F64)
+    {
+        DeviceScene<double> sc = ctx->scene64;
+        if (ctx->exact_traversal) sc.bvh4 = nullptr;
+        Launch<double>::traceUser(sc, d_rays, n, d_tuv, d_prim, ctx->d_counters, grid, s);
+    }
     else if (precision == MCRT_PRECISION_F32) Launch<float>::traceUser(ctx->scene32, d_rays, n, d_tuv, d_prim, ctx->d_counters, grid, s);
     else { cleanup(); ctx->error = "unknown precision"; return MCRT_ERR_INVALID; }
     cudaEventRecord(ctx->ev_stop, s);

@@ -21,6 +21,7 @@
 
 #include "bsdf.cuh"
 #include "intersect.cuh"
+#include "bvh4.cuh"
 #include "photon.cuh"
 #include "film.cuh"
 
@@ -35,6 +36,12 @@
 #endif
 #ifndef MCRT_TRACE_MINBLOCKS_F64_PRUNED   // double traversal without quadric code needs ~100 registers instead of 128
 #define MCRT_TRACE_MINBLOCKS_F64_PRUNED 4
+#endif
+#ifndef MCRT_TRACE_MINBLOCKS_FAST          // order-free search (bvh4.cuh)
+#define MCRT_TRACE_MINBLOCKS_FAST 3
+#endif
+#ifndef MCRT_DYNAMIC_FETCH                  // k_extend / k_shadow take rays per lane as lanes finish (traceManyFast)
+#define MCRT_DYNAMIC_FETCH 1
 #endif
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 3
@@ -61,6 +68,8 @@ namespace mcrt
         unsigned long long paths, extension_rays, shadow_rays, box_tests, prim_tests, knn_queries;
         unsigned long long shadow_box_tests, shadow_prim_tests; // the k_shadow share of box/prim tests
         unsigned long long ior_stack_overflows;
+        unsigned long long replayed_rays;   // rays re-traced in the reference's order (ambiguous closest hit)
+        uint32_t fetch_extend, fetch_shadow; // dynamic-fetch cursors of k_extend / k_shadow (traceManyFast), reset by k_advance
         uint32_t traversal_overflow, max_depth;
         uint32_t n_knn, _pad;
         // diagnostics of k_extend: sum over rays of (box+prim tests) and sum over warps of 32*max
@@ -230,15 +239,39 @@ namespace mcrt
     template <> struct Mode<double> { static constexpr bool parity = true; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F64; static constexpr int trace_minblocks_pruned = MCRT_TRACE_MINBLOCKS_F64_PRUNED; };
     template <> struct Mode<float> { static constexpr bool parity = false; static constexpr int trace_minblocks = MCRT_TRACE_MINBLOCKS_F32; static constexpr int trace_minblocks_pruned = MCRT_TRACE_MINBLOCKS_F32; };
 
-    template <int PRIMS = PRIMS_ALL, class R>
+    // FAST (parity mode only): order-free search over the 4-wide BVH with the reference-order replay as
+    // fallback (bvh4.cuh); the launchers pick it whenever the scene has that BVH
+    template <int PRIMS = PRIMS_ALL, bool FAST = false, class R>
     MCRT_D Hit<R> traceClosest(const DeviceScene<R>& sc, const V3<R>& o, const V3<R>& d, uint32_t skip_prim,
                                TraceCounters& cnt, uint32_t& overflow)
     {
         RayQ<R> rq;
-        rq.o = o; rq.d = d; rq.inv_d = R(1) / d;
+        rq.o = o; rq.d = d;
+        if constexpr (!(Mode<R>::parity && FAST)) rq.inv_d = R(1) / d;
         if constexpr (Mode<R>::parity)
         {
-            return traverseReferenceOrder<PRIMS>(sc, rq, cnt, overflow);
+            if constexpr (FAST)
+            {
+                // order-free search; the rare ray whose answer could depend on the visiting order is
+                // replayed in the reference's order (bvh4.cuh)
+                bool ambiguous;
+                Hit<R> h = traverseFast<PRIMS>(sc, rq, cnt, overflow, ambiguous);
+                if (ambiguous)
+                {
+                    const DeviceScene<R> sc_copy = sc;   // the out-of-line call takes addresses: keep those copies off the hot path
+                    RayQ<R> rq_copy = rq;
+                    rq_copy.inv_d = R(1) / d;            // only the replay's float64 slab test needs it
+                    Hit<R> h2;
+                    traceReferenceOrderOutOfLine<PRIMS>(&sc_copy, &rq_copy, &h2, &cnt.box_tests, &cnt.prim_tests, &overflow);
+                    h = h2;
+                    cnt.replayed++;
+                }
+                return h;
+            }
+            else
+            {
+                return traverseReferenceOrder<PRIMS>(sc, rq, cnt, overflow);
+            }
         }
         else
         {
@@ -299,14 +332,17 @@ namespace mcrt
     {
         // block-level reduction through warp shuffles, then one atomic per warp
         unsigned long long b = cnt.box_tests, p = cnt.prim_tests, r = rays;
+        uint32_t a = cnt.replayed;
         for (int off = 16; off > 0; off >>= 1)
         {
             b += __shfl_down_sync(0xFFFFFFFFu, b, off);
             p += __shfl_down_sync(0xFFFFFFFFu, p, off);
             r += __shfl_down_sync(0xFFFFFFFFu, r, off);
+            a += __shfl_down_sync(0xFFFFFFFFu, a, off);
         }
         if ((threadIdx.x & 31u) == 0)
         {
+            if (a) atomicAdd(&c->replayed_rays, (unsigned long long)a);
             if (b) atomicAdd(&c->box_tests, b);
             if (p) atomicAdd(&c->prim_tests, p);
             if (shadow && b) atomicAdd(&c->shadow_box_tests, b);
@@ -416,17 +452,37 @@ namespace mcrt
         c->n_gen = 0;
         c->n_shadow = 0;
         c->n_knn = 0;
+        c->fetch_extend = 0;
+        c->fetch_shadow = 0;
     }
 
-    template <class R, int PRIMS>
-    __global__ void __launch_bounds__(256, PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned) k_extend(WaveParams<R> p, int cur)
+    template <class R, int PRIMS, bool FAST>
+    __global__ void __launch_bounds__(256, FAST ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned)) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
-        TraceCounters cnt = { 0u, 0u };
+        TraceCounters cnt = { 0u, 0u, 0u };
         uint32_t overflow = 0;
-        unsigned long long rays = 0, work_sum = 0, work_max = 0;
+        unsigned long long rays = 0;
         const uint32_t* order = p.sort.path_order;
+        if constexpr (Mode<R>::parity && FAST && MCRT_DYNAMIC_FETCH)
+        {
+            traceManyFast<PRIMS>(p.scene, n, &p.counters->fetch_extend,
+                [&](uint32_t ii, RayQ<R>& r)
+                {
+                    const uint32_t i = order ? order[ii] : ii;
+                    const V4<R> ro = in.ray_o[i], rd = in.ray_d[i];
+                    r.o = ro.xyz(); r.d = rd.xyz();
+                    return i;
+                },
+                [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
+                {
+                    p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
+                    rays++;
+                }, cnt, overflow);
+            flushStats(p.counters, cnt, rays, false, overflow);
+            return;
+        }
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
             const uint32_t i = order ? order[ii] : ii;
@@ -434,21 +490,20 @@ namespace mcrt
             const V4<R> rd = in.ray_d[i];
             uint32_t skip = NO_PRIM;
             if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
+#ifdef MCRT_TAIL_DIAGNOSTIC
             const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
-            Hit<R> h = traceClosest<PRIMS>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
+#endif
+            Hit<R> h = traceClosest<PRIMS, FAST>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
             p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
             rays++;
-            // tail diagnostic: how much of the warp's time (~ its slowest ray) the average ray uses
+#ifdef MCRT_TAIL_DIAGNOSTIC
+            // tuning builds only: how much of the warp's time (~ its slowest ray) the average ray uses
             const uint32_t w = cnt.box_tests + cnt.prim_tests - w0;
             const unsigned am = __activemask();
-            work_sum += w;
-            if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) work_max += 32ull * __reduce_max_sync(am, w);
-            else __reduce_max_sync(am, w);
-        }
-        {
-            unsigned long long ws = work_sum, wm = work_max;
-            for (int off = 16; off > 0; off >>= 1) { ws += __shfl_down_sync(0xFFFFFFFFu, ws, off); wm += __shfl_down_sync(0xFFFFFFFFu, wm, off); }
-            if ((threadIdx.x & 31u) == 0) { atomicAdd(&p.counters->work_sum, ws); atomicAdd(&p.counters->work_warpmax, wm); }
+            const uint32_t wmax = __reduce_max_sync(am, w);
+            atomicAdd(&p.counters->work_sum, (unsigned long long)w);
+            if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) atomicAdd(&p.counters->work_warpmax, 32ull * wmax);
+#endif
         }
         flushStats(p.counters, cnt, rays, false, overflow);
     }
@@ -809,20 +864,45 @@ namespace mcrt
         if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
-    template <class R, bool FILM, int PRIMS>
-    __global__ void __launch_bounds__(256, PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned) k_shadow(WaveParams<R> p)
+    template <class R, bool FILM, int PRIMS, bool FAST>
+    __global__ void __launch_bounds__(256, FAST ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned)) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
-        TraceCounters cnt = { 0u, 0u };
+        TraceCounters cnt = { 0u, 0u, 0u };
         uint32_t overflow = 0;
         unsigned long long rays = 0;
         const uint32_t* order = p.sort.shadow_order;
+        if constexpr (Mode<R>::parity && FAST && MCRT_DYNAMIC_FETCH)
+        {
+            traceManyFast<PRIMS>(p.scene, n, &p.counters->fetch_shadow,
+                [&](uint32_t ii, RayQ<R>& r)
+                {
+                    const uint32_t i = order ? order[ii] : ii;
+                    const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
+                    r.o = so.xyz(); r.d = sd.xyz();
+                    return i;
+                },
+                [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
+                {
+                    rays++;
+                    const uint4 sm = p.shadow.meta[i];
+                    if (h.prim == sm.x)   // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
+                    {
+                        const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i], sk = p.shadow.k[i];
+                        R light_pdf = pow2(h.t) / sd.w;
+                        R mis_weight = powerHeuristic(light_pdf, so.w);
+                        depositRadiance<FILM>(p, sm.y, pixelOfFilmIndex(p, sm.y), sm.w, sk.xyz() * (mis_weight / (light_pdf * sk.w)));
+                    }
+                }, cnt, overflow);
+            flushStats(p.counters, cnt, rays, true, overflow);
+            return;
+        }
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
             const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
-            Hit<R> h = traceClosest<PRIMS>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS, FAST>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
             rays++;
             // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
             if (h.prim == sm.x)
@@ -1239,17 +1319,17 @@ namespace mcrt
 
     // ------------------------------------------------------------------------------------------
     // Batched Scene::intersect on caller rays (mcrt_trace_closest)
-    template <class R>
+    template <class R, bool FAST>
     __global__ void __launch_bounds__(256) k_trace_user(DeviceScene<R> sc, const double* rays6, size_t n, double* out_tuv,
                                                         uint32_t* out_prim, Counters* c)
     {
-        TraceCounters cnt = { 0u, 0u };
+        TraceCounters cnt = { 0u, 0u, 0u };
         uint32_t overflow = 0;
         unsigned long long rays = 0;
         for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         {
             const double* r = rays6 + 6 * i;
-            Hit<R> h = traceClosest(sc, V3<R>((R)r[0], (R)r[1], (R)r[2]), V3<R>((R)r[3], (R)r[4], (R)r[5]), NO_PRIM, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS_ALL, FAST>(sc, V3<R>((R)r[0], (R)r[1], (R)r[2]), V3<R>((R)r[3], (R)r[4], (R)r[5]), NO_PRIM, cnt, overflow);
             out_tuv[3 * i + 0] = (double)h.t; out_tuv[3 * i + 1] = (double)h.u; out_tuv[3 * i + 2] = (double)h.v;
             out_prim[i] = h.prim;
             rays++;

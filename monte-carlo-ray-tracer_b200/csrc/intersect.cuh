@@ -29,6 +29,7 @@ namespace mcrt
     {
         uint32_t box_tests;
         uint32_t prim_tests;
+        uint32_t replayed;   // rays the order-free search handed to the reference-order replay (bvh4.cuh)
     };
 
     // BoundingBox::intersect

@@ -33,6 +33,17 @@ namespace mcrt
     {
         const dim3 g(grid), b(32 * KNN_WARPS_PER_BLOCK);
         const size_t smem = knnSharedBytes(k);
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+            const int max_smem = (int)knnSharedBytes(1024);   // k > 768 exceeds the default 48 KB
+            cudaFuncSetAttribute(k_knn_user<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(k_knn_user<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(k_knn_user<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(k_knn_user<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(k_knn_user<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            attr_set = true;
+        }
         switch (knnSlotsFor(k))
         {
             case 1: k_knn_user<1><<<g, b, smem, s>>>(map, k, points, n, out_index, out_d2, out_count, overflow_flag); break;

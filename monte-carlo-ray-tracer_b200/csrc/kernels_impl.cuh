@@ -11,9 +11,19 @@ namespace mcrt
     template <> void Launch<MCRT_REAL>::extend(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
         // triangle-only scenes (every OBJ scene) run the traversal without sphere / quadric code
-        if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI><<<grid, 256, 0, s>>>(p, cur);
-        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE><<<grid, 256, 0, s>>>(p, cur);
-        else k_extend<MCRT_REAL, PRIMS_ALL><<<grid, 256, 0, s>>>(p, cur);
+        if constexpr (Mode<MCRT_REAL>::parity)
+        {
+            if (p.scene.bvh4)
+            {
+                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, true><<<grid, 256, 0, s>>>(p, cur);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, true><<<grid, 256, 0, s>>>(p, cur);
+                else k_extend<MCRT_REAL, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p, cur);
+                return;
+            }
+        }
+        if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, false><<<grid, 256, 0, s>>>(p, cur);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, false><<<grid, 256, 0, s>>>(p, cur);
+        else k_extend<MCRT_REAL, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
@@ -39,14 +49,20 @@ namespace mcrt
         if (!p.filmp.is_default_box)
         {
             // filtered film: the rare configuration, one generic instantiation
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(k_knn<MCRT_REAL, 0, true, SHADE_FEATS_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knnSharedBytes(1024)); attr_set = true; }
             k_knn<MCRT_REAL, 0, true, SHADE_FEATS_ALL><<<g, b, smem, s>>>(p);
             return;
         }
         const bool lite = (p.scene.material_flags_any & ~SHADE_FEATS_LITE) == 0;
         const int slots = knnSlotsFor(p.pm.k_nearest);
+        // k > 768 needs more than the default 48 KB of dynamic shared memory (knnSharedBytes)
+        #define MCRT_KNN_LAUNCH1(SL, FE) \
+            do { static bool attr_set = false; \
+                 if (!attr_set) { cudaFuncSetAttribute(k_knn<MCRT_REAL, SL, false, FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knnSharedBytes(1024)); attr_set = true; } \
+                 k_knn<MCRT_REAL, SL, false, FE><<<g, b, smem, s>>>(p); } while (0)
         #define MCRT_KNN_LAUNCH(SL) \
-            do { if (lite) k_knn<MCRT_REAL, SL, false, SHADE_FEATS_LITE><<<g, b, smem, s>>>(p); \
-                 else k_knn<MCRT_REAL, SL, false, SHADE_FEATS_ALL><<<g, b, smem, s>>>(p); } while (0)
+            do { if (lite) MCRT_KNN_LAUNCH1(SL, SHADE_FEATS_LITE); else MCRT_KNN_LAUNCH1(SL, SHADE_FEATS_ALL); } while (0)
         switch (slots)
         {
             case 1: MCRT_KNN_LAUNCH(1); break;
@@ -56,13 +72,25 @@ namespace mcrt
             default: MCRT_KNN_LAUNCH(0); break;
         }
         #undef MCRT_KNN_LAUNCH
+        #undef MCRT_KNN_LAUNCH1
     }
     template <> void Launch<MCRT_REAL>::shadow(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
     {
-        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL><<<grid, 256, 0, s>>>(p);
-        else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI><<<grid, 256, 0, s>>>(p);
-        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE><<<grid, 256, 0, s>>>(p);
-        else k_shadow<MCRT_REAL, false, PRIMS_ALL><<<grid, 256, 0, s>>>(p);
+        if constexpr (Mode<MCRT_REAL>::parity)
+        {
+            if (p.scene.bvh4)
+            {
+                if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, true><<<grid, 256, 0, s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, true><<<grid, 256, 0, s>>>(p);
+                else k_shadow<MCRT_REAL, false, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p);
+                return;
+            }
+        }
+        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, false><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, false><<<grid, 256, 0, s>>>(p);
+        else k_shadow<MCRT_REAL, false, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {
@@ -75,6 +103,10 @@ namespace mcrt
     template <> void Launch<MCRT_REAL>::traceUser(const DeviceScene<MCRT_REAL>& sc, const double* rays6, size_t n,
                                                   double* out_tuv, uint32_t* out_prim, Counters* c, int grid, cudaStream_t s)
     {
-        k_trace_user<MCRT_REAL><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c);
+        if constexpr (Mode<MCRT_REAL>::parity)
+        {
+            if (sc.bvh4) { k_trace_user<MCRT_REAL, true><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c); return; }
+        }
+        k_trace_user<MCRT_REAL, false><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c);
     }
 }

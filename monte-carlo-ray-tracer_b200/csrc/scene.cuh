@@ -90,8 +90,11 @@ namespace mcrt
         uint32_t type;
     };
 
+    struct Bvh4Node;   // bvh4.cuh
+
     template <class R> struct DeviceScene
     {
+        const Bvh4Node* bvh4;    // 4-wide float-box BVH of the order-free search (parity mode); null: replay traversal only
         const WideChild<R>* wide;
         const V4<R>* geom;
         const PrimShade<R>* shade;

@@ -758,6 +758,28 @@ void oracle_render_rows(void* h, const mcrt_camera* cam, uint32_t y0, uint32_t y
     if (rays) *rays = count;
 }
 
+// Camera::samplePixel's body for individual (pixel, sample) pairs: the camera ray and the radiance
+// Integrator::sampleRay returns for it (what oracle/ref.py's sample_pixels asks of the reference)
+void oracle_sample_pixels(void* h, const mcrt_camera* cam, const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t seed,
+                          double* out_rgb, double* out_rays6)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    Sampler smp(seed);
+    for (size_t i = 0; i < n; i++)
+    {
+        smp.initiate(pixel[i]);
+        smp.setIndex(sample[i]);
+        const Ray ray = cameraRay(*cam, s.d.scene_ior, pixel[i], smp);
+        if (out_rays6)
+        {
+            out_rays6[6 * i + 0] = ray.start.x; out_rays6[6 * i + 1] = ray.start.y; out_rays6[6 * i + 2] = ray.start.z;
+            out_rays6[6 * i + 3] = ray.direction.x; out_rays6[6 * i + 4] = ray.direction.y; out_rays6[6 * i + 5] = ray.direction.z;
+        }
+        const D3 r = sampleRay(s, ray, smp, nullptr);
+        out_rgb[3 * i + 0] = r.x; out_rgb[3 * i + 1] = r.y; out_rgb[3 * i + 2] = r.z;
+    }
+}
+
 // Film with a reconstruction filter (film.cpp:19-113, filter.hpp:8-66), whole frame. `film` is the
 // camera's "film" object after Film::Film resolved the default radius.
 namespace

@@ -27,6 +27,7 @@ def lib():
         L.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_sample_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
         L.oracle_bvh_free.argtypes = [C.c_void_p]
         L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -129,6 +130,13 @@ class PortScene:
         out = np.zeros((camera.height, camera.width, 3))
         lib().oracle_render_film(self.h, C.addressof(camera.rec), C.addressof(rec), sqrtspp, seed, _p(out))
         return out
+
+    def sample_pixels(self, camera, pixel, sample, seed):
+        """-> (rgb [n,3], camera rays [n,6]) for (pixel, sample) pairs"""
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32); sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        rgb = np.zeros((len(pixel), 3)); rays = np.zeros((len(pixel), 6))
+        lib().oracle_sample_pixels(self.h, C.addressof(camera.rec), _p(pixel), _p(sample), len(pixel), seed, _p(rgb), _p(rays))
+        return rgb, rays
 
     def render_rows(self, camera, y0, y1, sqrtspp, seed):
         out = np.zeros((y1 - y0, camera.width, 3))

@@ -48,12 +48,16 @@ CASES = {
     # CPU photon pass with 1 thread, shipped inside the pack
     "pm_hexagon_room_64": ("hexagon_room.json", dict(width=64, height=48, sqrtspp=2, emissions=4000,
                                                       num_render_threads=1), True),
+    # the OBJ scene written for this repository (tests/golden/make_mesh_scene.py): interpolated vertex
+    # normals (generated and from the file), the shading-normal fall-back, GGX / complex-IOR / glass on
+    # meshes, a 320-triangle mesh light (light CDF with 320 entries)
+    "smooth_mesh_64": ("smooth_mesh.json", dict(), False, os.path.join(HERE, "scenes")),
 }
 
 
-def make_case(cid, scene_file, overrides, photon_map, rng):
+def make_case(cid, scene_file, overrides, photon_map, rng, scenes=None):
     ref.set_seed(SEED)
-    s = ref.RefScene(scene_file, overrides, photon_map=photon_map)
+    s = ref.RefScene(scene_file, overrides, photon_map=photon_map, scenes=scenes)
     pack = os.path.join(HERE, cid + ".mcrtpack")
     s.export_pack(pack)
 
@@ -102,7 +106,8 @@ def make_case(cid, scene_file, overrides, photon_map, rng):
                         tr_rays=tr_rays, tr_t=tr_t, tr_prim=tr_prim, tr_uv=tr_uv, tr_interp=tr_interp,
                         total_rays=np.uint64(total_rays), shadow_rays=np.uint64(shadow_rays))
     print(f"{cid}: prims={s.n_prims} nodes={s.n_nodes} lights={s.n_lights} rays={total_rays} "
-          f"(shadow {shadow_rays}) mean={image.mean():.6f} miss={np.mean(~hit):.3f}")
+          f"(shadow {shadow_rays}) mean={image.mean():.6f} miss={np.mean(~hit):.3f} "
+          f"interpolated hits={int((tr_interp.astype(bool) & (tr_prim != 0xFFFFFFFF)).sum())}")
     s.close()
 
 
@@ -305,13 +310,31 @@ def make_bsdf_kat(rng):
     print("bsdf_kat: n =", n)
 
 
+def make_c2_band():
+    """BASELINE config 2 at its benchmark size (hexagon_room 1920x1080, 256 spp, quaternary SAH): rows
+    [538, 542) rendered by the reference (Camera::samplePixel over those buckets only) -> c2_band_kat.npz.
+    The GPU renders the same rows of the same frame through mcrt_render_rows(cam, 538, 542) from
+    bench_data/c2_hexagon_room.mcrtpack, the pack bench.py times."""
+    ref.set_seed(SEED)
+    ov = dict(width=1920, height=1080, sqrtspp=16, bvh_type="quaternary_sah")
+    s = ref.RefScene("hexagon_room.json", ov)
+    y0, y1 = 538, 542
+    band, sec, rays, sh = s.render(threads=8, y0=y0, y1=y1)
+    np.savez_compressed(os.path.join(HERE, "c2_band_kat.npz"), seed=np.uint32(SEED), y0=np.uint32(y0), y1=np.uint32(y1),
+                        width=np.uint32(1920), height=np.uint32(1080), sqrtspp=np.uint32(16), band=band,
+                        total_rays=np.uint64(rays), shadow_rays=np.uint64(sh))
+    print(f"c2_band_kat: rows {y0}..{y1} rays={rays} (shadow {sh}) mean={band.mean():.6f} in {sec:.1f} s")
+    s.close()
+
+
 def remake_packs(only):
     """Re-exports the scene packs only (pack format grew; the reference outputs in the .npz stay)."""
-    for cid, (scene_file, overrides, pm) in CASES.items():
+    for cid, case in CASES.items():
+        scene_file, overrides, pm = case[:3]
         if only and cid not in only:
             continue
         ref.set_seed(SEED)
-        s = ref.RefScene(scene_file, overrides, photon_map=pm)
+        s = ref.RefScene(scene_file, overrides, photon_map=pm, scenes=case[3] if len(case) > 3 else None)
         s.export_pack(os.path.join(HERE, cid + ".mcrtpack"))
         s.close()
         print("pack", cid)
@@ -323,14 +346,15 @@ if __name__ == "__main__":
         sys.exit(0)
     only = sys.argv[1:]
     rng = np.random.default_rng(20260923)
-    for cid, (scene_file, overrides, pm) in CASES.items():
+    for cid, case in CASES.items():
+        scene_file, overrides, pm = case[:3]
         if only and cid not in only:
             continue
-        make_case(cid, scene_file, overrides, pm, rng)
+        make_case(cid, scene_file, overrides, pm, rng, scenes=case[3] if len(case) > 3 else None)
+    if not only or "c2_band_kat" in only:
+        make_c2_band()
     if not only or "sampler_kat" in only:
         make_sampler_kat(rng)
-    if not only or "bsdf_kat" in only:
-        make_bsdf_kat(rng)
     if not only or "film_kat" in only:
         make_film_kat()
     if not only or "image_kat" in only:
