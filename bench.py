@@ -12,14 +12,19 @@ shadow / regenerate) until every path has terminated, film resolve. Rays = close
   e2e        same metric through the host-buffer C-ABI call: scene upload (H2D) + render + framebuffer
              D2H into pinned host memory inside the timed region (wall clock between synchronisations).
   roofline   the traversal kernel (k_extend): algorithmic bytes (48 B/ray + 32 B per
-             box test + 48 B per primitive test, counted by the kernel) / its CUDA-event time.
+             box test + 48 B per primitive test, counted by the kernel) / its CUDA-event time, PLUS what
+             this run measured in a non-timed ncu epilogue over the same kernels: DRAM bytes (traffic,
+             dram_gbs) and FP64 thread-instructions against the FP64 issue rate measured in the run.
+  secondary  the same measurements on BASELINE config 3's scene (spaceship, 457 k triangles) at 64 spp.
   cpu_baseline / --impl reference
-             the UNMODIFIED reference (oracle/_ref, all host threads) on a bounded sample of the same
-             workload: a block of rows of the same frame at the same 256 spp.
+             the UNMODIFIED reference (oracle/_ref, best of {hw, hw/2, ...} host threads) on a bounded
+             sample of the same workload: the SAME full frame at a REDUCED sample count (1 spp on the
+             driver's box for C2; rays/s does not depend on spp) - printed in `sample`.
 
-Multi-GPU: rows are sharded interleaved (rank r renders rows r, r+N, ...; bitwise the same pixels as
-the single-GPU image), the scene is replicated, one NCCL all-gather of the float64 framebuffer per
-step. Total work is fixed as N grows ("strong").
+Multi-GPU: rows are sharded interleaved (rank r renders rows r, r+N, ...; the same pixels as the
+single-GPU image), the scene is replicated; the film resolve of every rank stores its rows straight
+into the float3 frame of every rank (peer memory over NVLink, mcrt_render_rows_strided_peers), one
+barrier per step. Total work is fixed as N grows ("strong").
 """
 import argparse
 import importlib
@@ -175,6 +180,253 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+NCU_METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+               "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+               "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__thread_inst_executed.sum", "smsp__inst_executed.sum"]
+
+
+def child_render(args):
+    """One untimed render of the workload at a reduced sample count; prints its counters as JSON. Run under ncu
+    by profile_kernels() - nothing measured here is a bench value."""
+    m = importlib.import_module("monte-carlo-ray-tracer_b200")
+    pack, _, ov, _ = WORKLOADS[args.workload]
+    scene = m.Scene.from_pack(os.path.join(ROOT, pack))
+    cam = scene.cameras()[0].resized(ov["width"], ov["height"], args.sqrtspp or 2)
+    pt = m.PathTracer(scene, device=0, precision=m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32, global_seed=0x12345678)
+    pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))
+    import torch
+    out = torch.zeros((cam.height, cam.width, 3), dtype=torch.float64, device="cuda:0")
+    st = pt.render_rows_dev(cam, out.data_ptr())
+    print("CHILD_STATS " + json.dumps(st), flush=True)
+    pt.close()
+    return 0
+
+
+def profile_kernels(args, workload, sqrtspp):
+    """Non-timed epilogue: the same code path under `ncu` at a reduced sample count, every launch of the stage
+    kernels counted once: DRAM bytes, FP64 thread-instructions, active lanes per instruction, per kernel.
+    -> {kernel: {...}} with per-ray figures, or {"unavailable": why}."""
+    import csv
+    import io
+    import shutil
+    if not shutil.which("ncu"):
+        return {"unavailable": "ncu not on PATH"}
+    cmd = ["ncu", "--metrics", ",".join(NCU_METRICS), "--clock-control", "none", "-k", "regex:k_extend|k_shade|k_shadow|k_knn",
+           "--csv", sys.executable, os.path.abspath(__file__), "--child-render", "--workload", workload, "--sqrtspp", str(sqrtspp),
+           "--precision", args.precision] + (["--pool", str(args.pool)] if args.pool else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    stats = None
+    rows = []
+    for ln in r.stdout.splitlines():
+        if ln.startswith("CHILD_STATS "):
+            stats = json.loads(ln[len("CHILD_STATS "):])
+        elif ln.startswith('"'):
+            rows.append(ln)
+    if stats is None or len(rows) < 2:
+        return {"unavailable": "ncu produced no counters: " + (r.stderr or r.stdout)[-200:].replace("\n", " ")}
+    rd = list(csv.reader(io.StringIO("\n".join(rows))))
+    hdr = rd[0]
+    ik, im, iv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    agg = {}
+    for row in rd[1:]:
+        if len(row) <= iv:
+            continue
+        name = row[ik]
+        key = "k_shade_key" if "k_shade_key" in name else next((k for k in ("k_extend", "k_shadow", "k_shade", "k_knn") if k in name), None)
+        if key is None:
+            continue
+        try:
+            v = float(row[iv].replace(",", ""))
+        except ValueError:
+            continue
+        a = agg.setdefault(key, {"launches": 0})
+        a[row[im]] = a.get(row[im], 0.0) + v
+        if row[im] == "gpu__time_duration.sum":
+            a["launches"] += 1
+    units = {"k_extend": stats["extension_rays"], "k_shadow": stats["shadow_rays"], "k_shade": stats["extension_rays"], "k_knn": max(1, stats["knn_queries"])}
+    out = {"sample": f"{workload} at {sqrtspp * sqrtspp} spp under ncu (all launches of the stage kernels, each counted once)"}
+    for k, a in agg.items():
+        if k not in units or not units[k]:
+            continue
+        n = float(units[k])
+        fp64 = sum(a.get(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum", 0.0) for op in ("dadd", "dmul", "dfma"))
+        out[k] = {"launches": a["launches"], "dram_bytes_per_unit": (a.get("dram__bytes_read.sum", 0.0) + a.get("dram__bytes_write.sum", 0.0)) / n,
+                  "fp64_thread_inst_per_unit": fp64 / n,
+                  "lanes_per_inst": a.get("smsp__thread_inst_executed.sum", 0.0) / max(1.0, a.get("smsp__inst_executed.sum", 1.0)),
+                  "unit": "query" if k == "k_knn" else "ray"}
+    return out
+
+
+def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True):
+    """Times `steps` renders of `workload` on this job's GPUs. -> result dict on rank 0 (None elsewhere)."""
+    torch, dist, m, mdist = env["torch"], env["dist"], env["m"], env["mdist"]
+    rank, local_rank, world = env["rank"], env["local_rank"], env["world"]
+    pack, _, ov, label = WORKLOADS[workload]
+    if not os.path.exists(os.path.join(ROOT, pack)):
+        raise SystemExit(f"bench.py: {pack} is missing - generate it with `python tools/validate_big.py make` where /root/reference exists")
+    scene = m.Scene.from_pack(os.path.join(ROOT, pack))
+    cam = scene.cameras()[0].resized(ov["width"], ov["height"], sqrtspp_override or ov["sqrtspp"])
+    precision = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32
+    pt = m.PathTracer(scene, device=local_rank, precision=precision, global_seed=0x12345678)
+    pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))   # 16 Mi paths in flight (6.5 GB of HBM)
+    pt.set_option("stage_timing", 1)
+    W, H = cam.width, cam.height
+    dev = torch.device("cuda", local_rank)
+    # every rank holds the whole float3 frame; each rank's resolve kernel stores its rows into all of them (NVLink)
+    frames = mdist.PeerFrames(pt, rank, world, H, W, float32=True, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        st = frames.render(cam)       # returns after this rank's kernels (incl. the peer stores) have completed
+        frames.barrier()              # every rank's rows are in every frame
+        return st["gpu_ms_total"], st
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, stats = 0.0, []
+    for _ in range(steps):
+        ms, st = step()
+        dev_ms += ms
+        stats.append(st)
+    sync_all()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+
+    # ---- e2e: host buffers in, host buffers out. N=1: the plain C-ABI call mcrt_scene_upload + mcrt_render_rows
+    # (float64 frame to the host). N>1: scene upload + sharded render + rank 0 reads the assembled float3 frame.
+    e2e_steps = max(1, min(steps, 3))
+    host64 = torch.empty((H, W, 3), dtype=torch.float64).pin_memory() if world == 1 else None
+    host32 = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if world > 1 else None
+    frame_t = frames.tensor() if world > 1 else None
+
+    def e2e_step():
+        h2d = pt.upload_scene() + 144  # scene arrays + camera record
+        if world == 1:
+            pt.render_rows(cam, 0, H, out=host64.numpy())
+            return h2d, pt.last_stats
+        st = frames.render(cam)
+        frames.barrier()
+        if rank == 0:
+            host32.copy_(frame_t, non_blocking=False)
+        return h2d, st
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(e2e_steps):
+        h2d_bytes, st = e2e_step()
+        e2e_rays += st["extension_rays"] + st["shadow_rays"]
+    sync_all()
+    e2e_wall = time.perf_counter() - t0
+    d2h_bytes = H * W * 3 * (8 if world == 1 else 4)
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    SUM, MAX = (dist.ReduceOp.SUM, dist.ReduceOp.MAX) if world > 1 else (None, None)
+    rays_local = sum(s["extension_rays"] + s["shadow_rays"] for s in stats)
+    rays_total = allreduce(float(rays_local), SUM)
+    dev_ms_max = allreduce(dev_ms, MAX)
+    dev_ms_mean = allreduce(dev_ms, SUM) / world
+    wall_max = allreduce(wall, MAX)
+    e2e_rays_total = allreduce(float(e2e_rays), SUM)
+    e2e_wall_max = allreduce(e2e_wall, MAX)
+    launches = allreduce(float(sum(s["kernel_launches"] for s in stats)), SUM)
+    fp64_peak = pt.fp64_peak() if args.precision == "f64" else None
+
+    # ---- the traversal kernel (rank 0's launches)
+    ext_rays = sum(s["extension_rays"] for s in stats)
+    sh_rays = sum(s["shadow_rays"] for s in stats)
+    ext_box = sum(s["box_tests"] - s["shadow_box_tests"] for s in stats)
+    ext_prim = sum(s["prim_tests"] - s["shadow_prim_tests"] for s in stats)
+    ext_ms = sum(s["gpu_ms_extend"] for s in stats)
+    ext_launches = sum(s["extend_launches"] for s in stats)
+    sh_ms = sum(s["gpu_ms_shadow"] for s in stats)
+    shade_ms = sum(s["gpu_ms_shade"] for s in stats)
+    gen_ms = sum(s["gpu_ms_generate"] for s in stats)
+    replayed = sum(s["replayed_rays"] for s in stats)
+    pt.close()
+    frames_bytes = frames.nbytes
+    # (the frames stay mapped until the process ends: closing them needs another barrier and buys nothing here)
+
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    alg_bytes = traversal_bytes(ext_rays, ext_box, ext_prim)
+    achieved = alg_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+    scene_bytes = int(pt.h2d_bytes)
+    prof = profile_kernels(args, workload, 3 if W * H >= 1000000 else 8) if (profile and world == 1) else {"unavailable": "profiled at N=1 only"}
+    pe = prof.get("k_extend") if isinstance(prof, dict) else None
+    avg_launch_ms = ext_ms / max(1, ext_launches)
+    rays_per_launch = ext_rays / max(1, ext_launches)
+    roofline = {
+        "kernel": "k_extend<%s>%s" % ("double" if args.precision == "f64" else "float", " (order-free search, replay of ambiguous rays)" if args.precision == "f64" else ""),
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes": "SURVEY.md 8(d): 48 B/ray + 32 B per box test + 48 B per primitive test, counted by the kernel",
+        "algorithmic_bytes_per_launch": alg_bytes / max(1, ext_launches), "bytes_per_ray": alg_bytes / max(1, ext_rays),
+        "avg_launch_ms": avg_launch_ms, "launches": ext_launches,
+        # measured in this run (ncu epilogue over the same kernels at a reduced sample count), scaled by rays:
+        "traffic": pe["dram_bytes_per_unit"] * rays_per_launch if pe else None,
+        "dram_gbs": pe["dram_bytes_per_unit"] * ext_rays / (ext_ms * 1e-3) / 1e9 if pe and ext_ms > 0 else None,
+        "scene_bytes": scene_bytes,
+        "note": ("the scene (%d bytes) is served from L1/L2, so `frac` counts cache hits as HBM bytes: it measures box/primitive-test throughput, "
+                 "may exceed 1 and is not the binding roofline; dram_gbs is what crosses HBM, fp64 is the issue-rate bound" % scene_bytes)
+                if scene_bytes < 126e6 else "scene larger than L2",
+    }
+    if pe and ext_ms > 0:
+        roofline["dram_frac"] = roofline["dram_gbs"] / peak
+        roofline["lanes_per_inst"] = pe["lanes_per_inst"]
+        if fp64_peak:
+            rate = pe["fp64_thread_inst_per_unit"] * ext_rays / (ext_ms * 1e-3)
+            roofline["fp64"] = {"achieved": rate / 1e12, "peak": fp64_peak / 1e12, "unit": "T thread-inst/s (DADD+DMUL+DFMA)", "frac": rate / fp64_peak,
+                                "inst_per_ray": pe["fp64_thread_inst_per_unit"], "peak_source": "measured in this run (mcrt_fp64_peak: independent DFMA chains)"}
+    if isinstance(prof, dict) and "unavailable" in prof:
+        roofline["profile_unavailable"] = prof["unavailable"]
+    value = rays_total / (dev_ms_max * 1e-3) / 1e6
+    result = {
+        "metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.precision,
+        "data": "reference scene flattened by the reference's own loader / BVH builder (scene pack), fixed sampler seed",
+        "config": {"workload": label if not sqrtspp_override else f"{label} [at {sqrtspp_override ** 2} spp]",
+                   "paths_per_step": W * H * cam.sqrtspp ** 2, "rays_per_step": rays_total / steps,
+                   "parallelism": (f"rows interleaved over {world} GPUs, scene replicated; each rank's film resolve stores its rows into every rank's "
+                                   f"float3 frame over NVLink (CUDA IPC peer memory), one barrier per step") if world > 1 else "1 GPU",
+                   "l2": "per-step working set (16 Mi-path pool ~6.5 GB) exceeds the 126 MB L2; see roofline.note for the scene arrays",
+                   "mode": "parity (float64 primitive tests and shading in the reference's operation order, --fmad=false)" if args.precision == "f64" else "fast (float32)"},
+        "wall_ms_per_step": 1e3 * wall_max / steps,
+        "rank_imbalance": {"max_over_mean_gpu_ms": dev_ms_max / max(1e-9, dev_ms_mean)},
+        "e2e": {"value": e2e_rays_total / e2e_wall_max / 1e6, "unit": "Mray/s",
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "steps": e2e_steps, "timing": "wall clock between synchronisations, max over ranks"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "stage_ms_per_step": {"extend": ext_ms / steps, "shade(+class sort)": shade_ms / steps, "shadow": sh_ms / steps, "generate+advance+sort": gen_ms / steps},
+        "rays": {"extension_per_step": ext_rays / steps, "shadow_per_step": sh_rays / steps, "replayed_in_reference_order": replayed / steps,
+                 "box_tests_per_ray": (ext_box) / max(1, ext_rays), "prim_tests_per_ray": ext_prim / max(1, ext_rays)},
+        "kernels": {k: v for k, v in prof.items() if k != "k_extend"} if isinstance(prof, dict) else None,
+    }
+    return result
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -188,164 +440,21 @@ def run_gpu_arm(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = {"torch": torch, "dist": dist, "rank": rank, "local_rank": local_rank, "world": world,
+           "m": importlib.import_module("monte-carlo-ray-tracer_b200"),
+           "mdist": importlib.import_module("monte-carlo-ray-tracer_b200.distributed")}
 
-    m = importlib.import_module("monte-carlo-ray-tracer_b200")
-    pack, _, _, label = WORKLOADS[args.workload]
-    if not os.path.exists(os.path.join(ROOT, pack)):
-        raise SystemExit(f"bench.py: {pack} is missing - generate it with `python tools/validate_big.py make` where /root/reference exists")
-    scene = m.Scene.from_pack(os.path.join(ROOT, pack))
-    cam = scene.cameras()[0]
-    ov = WORKLOADS[args.workload][2]
-    cam = cam.resized(ov["width"], ov["height"], ov["sqrtspp"])
-    if args.sqrtspp:
-        cam = cam.resized(cam.width, cam.height, args.sqrtspp)
-    precision = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32
-    pt = m.PathTracer(scene, device=local_rank, precision=precision, global_seed=0x12345678)
-    pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))   # 16 Mi paths in flight (6.5 GB of HBM)
-    pt.set_option("stage_timing", 1)
-
-    mdist = importlib.import_module("monte-carlo-ray-tracer_b200.distributed")
-    W, H = cam.width, cam.height
-    _, _, n_rows = mdist.interleaved_rows(rank, world, H)
-    max_rows = mdist.max_rows(world, H)
-    dev = torch.device("cuda", local_rank)
-    local = torch.zeros((max_rows, W, 3), dtype=torch.float64, device=dev)
-    gathered = torch.zeros((world, max_rows, W, 3), dtype=torch.float64, device=dev) if world > 1 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def step():
-        """→ (device ms, stats). Framebuffer stays in HBM; full frame assembled on every rank."""
-        st = pt.render_rows_strided_dev(cam, local.data_ptr(), rank, world, n_rows)
-        ms = st["gpu_ms_total"]
-        if world > 1:
-            ev0.record()
-            frame = mdist.gather_frame(local, H, world, out=gathered)
-            ev1.record()
-            ev1.synchronize()
-            ms += ev0.elapsed_time(ev1)
-        else:
-            frame = local
-        return ms, st, frame
-
-    for _ in range(args.warmup):
-        step()
-
-    sampler = ClockSampler(local_rank)
-    sync_all()
-    sampler.start()
-    wall0 = time.perf_counter()
-    dev_ms, stats = 0.0, []
-    for _ in range(args.steps):
-        ms, st, frame = step()
-        dev_ms += ms
-        stats.append(st)
-    sync_all()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-
-    # ---- e2e: host-buffer path. N=1: the plain C-ABI call mcrt_scene_upload + mcrt_render_rows.
-    e2e_steps = max(1, min(args.steps, 2))
-    host_frame = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
-    host_np = host_frame.numpy()
-
-    def e2e_step():
-        h2d = pt.upload_scene() + 144  # scene arrays + camera record
-        if world == 1:
-            pt.render_rows(cam, 0, H, out=host_np)
-            st = pt.last_stats
-        else:
-            st = pt.render_rows_strided_dev(cam, local.data_ptr(), rank, world, n_rows)
-            frame = mdist.gather_frame(local, H, world, out=gathered)
-            host_frame.copy_(frame, non_blocking=False)
-        return h2d, st
-
-    e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_rays = 0
-    for _ in range(e2e_steps):
-        h2d_bytes, st = e2e_step()
-        e2e_rays += st["extension_rays"] + st["shadow_rays"]
-    sync_all()
-    e2e_wall = time.perf_counter() - t0
-
-    # ---- reduce over ranks: max time, sum rays
-    def allreduce(x, op):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
-        return float(t.item())
-
-    SUM, MAX = (dist.ReduceOp.SUM, dist.ReduceOp.MAX) if world > 1 else (None, None)
-    rays_local = sum(s["extension_rays"] + s["shadow_rays"] for s in stats)
-    rays_total = allreduce(float(rays_local), SUM)
-    dev_ms_max = allreduce(dev_ms, MAX)
-    wall_max = allreduce(wall, MAX)
-    e2e_rays_total = allreduce(float(e2e_rays), SUM)
-    e2e_wall_max = allreduce(e2e_wall, MAX)
-    launches = allreduce(float(sum(s["kernel_launches"] for s in stats)), SUM)
-
-    # ---- roofline of the traversal kernel (rank 0's launches)
-    ext_rays = sum(s["extension_rays"] for s in stats)
-    ext_box = sum(s["box_tests"] - s["shadow_box_tests"] for s in stats)
-    ext_prim = sum(s["prim_tests"] - s["shadow_prim_tests"] for s in stats)
-    ext_ms = sum(s["gpu_ms_extend"] for s in stats)
-    ext_launches = sum(s["extend_launches"] for s in stats)
-    sh_ms = sum(s["gpu_ms_shadow"] for s in stats)
-    shade_ms = sum(s["gpu_ms_shade"] for s in stats)
-    gen_ms = sum(s["gpu_ms_generate"] for s in stats)
-    peak, peak_src = measured_peaks()
-    achieved = traversal_bytes(ext_rays, ext_box, ext_prim) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            per_ray = json.load(f).get(args.precision, {}).get("k_extend_dram_bytes_per_ray")
-            # one ncu --set full capture of a full-pool launch, scaled to this run's average launch
-            traffic = per_ray * ext_rays / max(1, ext_launches) if per_ray else None
-    except Exception:
-        pass
-    roofline = {
-        "kernel": "k_extend<%s>" % ("double" if args.precision == "f64" else "float"),
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": traversal_bytes(ext_rays, ext_box, ext_prim) / max(1, ext_launches),
-        "avg_launch_ms": ext_ms / max(1, ext_launches), "launches": ext_launches,
-        "bytes_per_ray": traversal_bytes(ext_rays, ext_box, ext_prim) / max(1, ext_rays),
-        "stage_ms_per_step": {"extend": ext_ms / args.steps, "shade": shade_ms / args.steps,
-                              "shadow": sh_ms / args.steps, "generate+advance": gen_ms / args.steps},
-        "shade_kernel_achieved_gbs": (340.0 * sum(s["extension_rays"] for s in stats)) / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0,
-        "shadow_kernel_achieved": traversal_bytes(sum(s["shadow_rays"] for s in stats),
-                                                  sum(s["shadow_box_tests"] for s in stats),
-                                                  sum(s["shadow_prim_tests"] for s in stats)) / (sh_ms * 1e-3) / 1e9 if sh_ms > 0 else 0.0,
-    }
+    line = measure(env, args, args.workload, args.steps, args.warmup, args.sqrtspp, profile=not args.no_profile)
+    # secondary block: the 457 k-triangle spaceship (BASELINE config 3) at a sample count that keeps the default run short
+    secondary = None
+    sec_pack = os.path.join(ROOT, WORKLOADS["c3"][0])
+    if args.workload == "c2" and not args.no_secondary and not args.sqrtspp and os.path.exists(sec_pack):
+        secondary = measure(env, args, "c3", 3, 3, 8, profile=not args.no_profile)
 
     if rank == 0:
-        value = rays_total / (dev_ms_max * 1e-3) / 1e6
-        line = {
-            "metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": args.precision,
-            "data": "reference scene (vendored hexagon_room.json flattened by the reference's own loader/BVH builder), fixed sampler seed",
-            "config": {"workload": label, "paths_per_step": W * H * cam.sqrtspp ** 2,
-                       "rays_per_step": rays_total / args.steps,
-                       "parallelism": f"rows interleaved over {world} GPU(s), scene replicated, 1 NCCL all-gather of the f64 framebuffer/step" if world > 1 else "1 GPU",
-                       "l2": "per-step working set (16 Mi-path pool ~6.5 GB, film 50 MB) exceeds the 126 MB L2; the 3 KB scene is cache-resident by nature",
-                       "mode": "parity (float64, reference operation order, --fmad=false)" if args.precision == "f64" else "fast (float32)"},
-            "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "e2e": {"value": e2e_rays_total / e2e_wall_max / 1e6, "unit": "Mray/s",
-                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(H * W * 3 * 8),
-                    "steps": e2e_steps, "timing": "wall clock between synchronisations, max over ranks"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roofline,
-        }
+        if secondary is not None:
+            line["secondary"] = {k: secondary[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "e2e", "roofline",
+                                                          "stage_ms_per_step", "rays", "kernels", "rank_imbalance", "gpu_launches")}
         if world == 1 and not args.no_cpu_baseline:
             # The reference arm runs in a child process: the reference aborts on a scene whose assets are
             # missing (e.g. OBJ scenes on a box without /root/reference), and that must not take the
@@ -361,8 +470,8 @@ def run_gpu_arm(args):
                                         "sample": f"unavailable on this box: {type(e).__name__}: {str(e)[:200]}"}
         print(json.dumps(line), flush=True)
 
-    pt.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -378,10 +487,15 @@ def main():
     ap.add_argument("--sqrtspp", type=int, default=0, help="override samples (debug only; invalidates the config)")
     ap.add_argument("--pool", type=float, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the ncu epilogue (measured DRAM traffic / FP64 counts)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the spaceship block")
+    ap.add_argument("--child-render", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--baseline-seconds", type=float, default=0.0, help="reference arm: target seconds per step")
     args = ap.parse_args()
     if args.warmup < 3 and not args.sqrtspp:
         args.warmup = 3
+    if args.child_render:
+        return child_render(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

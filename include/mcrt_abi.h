@@ -335,6 +335,29 @@ int mcrt_render_rows_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint3
                                  uint32_t global_seed, int integrator_kind, int precision,
                                  double* out_rgb_dev, mcrt_stats* stats);
 
+/* Row-sharded render with the frame exchange fused into the film resolve (replaces the NCCL
+ * all-gather of the framebuffer): the rows y_first + k*y_step this rank renders are written straight into
+ * frames[0..n_frames) - the FULL-frame buffers [height][width][3] of every rank, float32 ("float3
+ * framebuffer") or float64 - at their final position. frames[] are device pointers valid on this device:
+ * the rank's own buffer from mcrt_frame_alloc and the peers' buffers mapped with mcrt_frame_open (CUDA IPC;
+ * the stores cross NVLink). The caller synchronises the ranks (barrier) before reading a frame and before
+ * the next render overwrites it. */
+int mcrt_render_rows_strided_peers(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first,
+                                   uint32_t y_step, uint32_t n_rows, uint32_t sqrtspp,
+                                   uint32_t global_seed, int integrator_kind, int precision,
+                                   void* const* frames, uint32_t n_frames, int frame_is_float32,
+                                   mcrt_stats* stats);
+/* A device buffer that other processes on the node can map: *dev_ptr (zero-filled) and its 64-byte CUDA IPC
+ * handle, to be sent to the peers by whatever channel the host uses (torch.distributed in this repository). */
+int mcrt_frame_alloc(mcrt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
+int mcrt_frame_open(mcrt_ctx* ctx, const unsigned char ipc_handle[64], void** dev_ptr);
+int mcrt_frame_close(mcrt_ctx* ctx, void* peer_ptr);
+int mcrt_frame_free(mcrt_ctx* ctx, void* dev_ptr);
+
+/* Measured FP64 issue rate of this GPU (independent DFMA chains on every SM), thread-instructions per second:
+ * the denominator of bench.py's FP64 roofline for the float64 kernels. */
+int mcrt_fp64_peak(mcrt_ctx* ctx, double* dfma_per_second);
+
 /* Batched Scene::intersect (scene.cpp:151-176): closest hit per ray. `medium_ior` is not
  * needed by the query. Host buffers. */
 int mcrt_trace_closest(mcrt_ctx* ctx, const mcrt_ray* rays, size_t n, int precision,

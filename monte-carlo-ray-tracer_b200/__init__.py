@@ -32,6 +32,8 @@ ABI_SYMBOLS = [
     "mcrt_sample_rays", "mcrt_sampler_stream", "mcrt_knn_search", "mcrt_set_option", "mcrt_set_film",
     "mcrt_obj_load", "mcrt_obj_free", "mcrt_obj_vertex_normals",
     "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
+    "mcrt_render_rows_strided_peers", "mcrt_frame_alloc", "mcrt_frame_open", "mcrt_frame_close", "mcrt_frame_free",
+    "mcrt_fp64_peak",
 ]
 
 
@@ -191,6 +193,13 @@ def lib():
         L.mcrt_render_rows_dev.argtypes = render_args
         L.mcrt_render_rows_strided_dev.argtypes = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32,
                                                    C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_render_rows_strided_peers.argtypes = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                     C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(Stats)]
+        L.mcrt_frame_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]
+        L.mcrt_frame_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mcrt_frame_close.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcrt_frame_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcrt_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.mcrt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
@@ -512,6 +521,42 @@ class Integrator:
         return self.last_stats
 
     # -- interleaved rows y_first + k*y_step (multi-GPU sharding), framebuffer in HBM
+    def render_rows_strided_peers(self, camera, frame_ptrs, y_first, y_step, n_rows, frame_is_float32=True, sqrtspp=None, precision=None):
+        """Rows y_first + k*y_step rendered and resolved straight into the full-frame buffers `frame_ptrs` (this
+        rank's and the peers', see distributed.PeerFrames): mcrt_render_rows_strided_peers."""
+        self.set_film(camera)
+        arr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
+        st = Stats()
+        self._check(lib().mcrt_render_rows_strided_peers(self.ctx, C.byref(camera.rec), y_first, y_step, n_rows,
+                                                         camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed, self.kind,
+                                                         self.precision if precision is None else precision, arr, len(frame_ptrs),
+                                                         1 if frame_is_float32 else 0, C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def frame_alloc(self, nbytes):
+        """-> (device pointer, 64-byte CUDA IPC handle) of a zero-filled buffer other ranks can map"""
+        ptr = C.c_void_p(); h = (C.c_ubyte * 64)()
+        self._check(lib().mcrt_frame_alloc(self.ctx, nbytes, C.byref(ptr), h))
+        return ptr.value, bytes(h)
+
+    def frame_open(self, handle):
+        ptr = C.c_void_p(); h = (C.c_ubyte * 64)(*handle)
+        self._check(lib().mcrt_frame_open(self.ctx, h, C.byref(ptr)))
+        return ptr.value
+
+    def frame_close(self, ptr):
+        self._check(lib().mcrt_frame_close(self.ctx, C.c_void_p(ptr)))
+
+    def frame_free(self, ptr):
+        self._check(lib().mcrt_frame_free(self.ctx, C.c_void_p(ptr)))
+
+    def fp64_peak(self):
+        """Measured DFMA thread-instructions per second of this GPU (mcrt_fp64_peak)."""
+        v = C.c_double()
+        self._check(lib().mcrt_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
     def render_rows_strided_dev(self, camera, out_dev_ptr, y_first, y_step, n_rows, sqrtspp=None, precision=None):
         self.set_film(camera)
         st = Stats()

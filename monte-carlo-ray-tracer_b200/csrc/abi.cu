@@ -65,6 +65,9 @@ struct mcrt_ctx
     DeviceScene<float> scene32;
     float scene_scale = 1.0f;
     uint32_t n_bvh4_nodes = 0;
+    uint32_t bvh4_max_leaf = 0xFFFFFFFFu;   // auto; 0: keep the reference's leaves; n: cut larger leaves into runs of n (option / MCRT_BVH4_MAX_LEAF)
+    int dynamic_fetch = -1;       // -1 auto (scenes with >= 2048 BVH4 nodes), 0 off, 1 on
+    PeerFrames peer_out{};   // n_frames != 0: the next resolve writes into these frames (mcrt_render_rows_strided_peers)
     int exact_traversal = 0;   // 1: every ray takes the reference-order replay (traverseReferenceOrder)
 
     WaveBuffers<double> wave64;
@@ -126,6 +129,7 @@ struct mcrt_ctx
     // options
     int sort_rays = 1;
     int sort_shade = 0;
+    int sort_shade_class = 1;   // k_shade walks paths grouped by the material class of their hit
     int sort_prim_key = -1;   // -1 auto (>= 4096 primitives), 0 origin-cell keys, 1 source-primitive keys
     uint32_t pool_paths = 1u << 23;   // measured on C2: 2 Mi 2269, 4 Mi 2378, 8 Mi 2463, 16 Mi 2503 Mray/s (coarser bins fill better)
     int blocks_per_sm = 8;
@@ -357,15 +361,60 @@ namespace
         if (s.n_prims >= BVH4_MAX_PRIMS) return MCRT_OK;   // leaf references hold 23 bits: such scenes use the replay traversal
         auto lower = [](double v) { float r = (float)v; if ((double)r > v) r = std::nextafter(r, -INFINITY); return r; };
         auto upper = [](double v) { float r = (float)v; if ((double)r < v) r = std::nextafter(r, INFINITY); return r; };
-        struct Item { int64_t node; std::vector<Item> group; double box[6]; };   // node >= 0: reference node; -1: run of items
-        auto itemOfNode = [&](uint32_t n) { Item it; it.node = n; for (int k = 0; k < 6; k++) it.box[k] = s.node_bounds[6 * (size_t)n + k]; return it; };
+        struct Item { int64_t node; std::vector<Item> group; double box[6]; uint32_t first, count; };   // node >= 0: reference node; -1: run of items; -2: part of a reference leaf
+        // leaves larger than max_leaf are cut into runs of consecutive primitives with their own boxes (lanes of a
+        // warp then spend similar time per leaf, and the tighter boxes cull more)
+        // measured on the B200 (profiles/r2_leaf_split.txt): cutting leaves to 2 primitives gains 5 % on the 44-primitive
+        // hexagon room (the reference's leaves hold up to 8 there), costs 2-10 % on the 457 k-triangle spaceship
+        const uint32_t max_leaf = ctx->bvh4_max_leaf == 0xFFFFFFFFu ? (s.n_prims < 4096u ? 2u : 0u) : ctx->bvh4_max_leaf;
+        auto primBox = [&](uint32_t prim, double* b)
+        {
+            const uint32_t type = s.prim_type[prim], idx = s.prim_index[prim];
+            if (type == MCRT_PRIM_TRIANGLE)
+            {
+                for (int k = 0; k < 3; k++)
+                {
+                    const double a0 = s.tri_v0[3 * (size_t)idx + k], a1 = s.tri_v1[3 * (size_t)idx + k], a2 = s.tri_v2[3 * (size_t)idx + k];
+                    b[k] = std::min(a0, std::min(a1, a2)); b[3 + k] = std::max(a0, std::max(a1, a2));
+                }
+            }
+            else if (type == MCRT_PRIM_SPHERE)
+            {
+                const double* sp = s.sphere_origin_radius + 4 * (size_t)idx;
+                for (int k = 0; k < 3; k++) { b[k] = sp[k] - sp[3]; b[3 + k] = sp[k] + sp[3]; }
+            }
+            else for (int k = 0; k < 6; k++) b[k] = s.quadric_bounds[6 * (size_t)idx + k];
+        };
+        auto itemOfNode = [&](uint32_t n)
+        {
+            Item it; it.node = n; it.first = s.node_first_prim[n]; it.count = s.node_prim_count[n];
+            for (int k = 0; k < 6; k++) it.box[k] = s.node_bounds[6 * (size_t)n + k];
+            if (max_leaf && it.count > max_leaf)
+            {
+                // a reference leaf with more primitives than max_leaf: a run of part-leaves (shape() groups them by four)
+                it.node = -1;
+                for (uint32_t f = it.first; f < it.first + it.count; f += max_leaf)
+                {
+                    Item part; part.node = -2; part.first = f; part.count = std::min(max_leaf, it.first + it.count - f);
+                    for (int k = 0; k < 3; k++) { part.box[k] = 1e300; part.box[3 + k] = -1e300; }
+                    for (uint32_t q = f; q < f + part.count; q++)
+                    {
+                        double b[6]; primBox(q, b);
+                        // never outside the reference's leaf box (sphere / quadric boxes are what the reference stores anyway)
+                        for (int k = 0; k < 3; k++) { part.box[k] = std::min(part.box[k], b[k]); part.box[3 + k] = std::max(part.box[3 + k], b[3 + k]); }
+                    }
+                    it.group.push_back(part);
+                }
+            }
+            return it;
+        };
         auto area = [](const double* b) { const double x = b[3] - b[0], y = b[4] - b[1], z = b[5] - b[2]; return x * y + y * z + z * x; };
         auto childrenOf = [&](uint32_t node, std::vector<Item>& kids)
         {
             uint32_t c = node + 1;
             while (c != 0 && c < s.n_nodes) { kids.push_back(itemOfNode(c)); c = s.node_next_sibling[c]; }
         };
-        auto isInner = [&](const Item& it) { return it.node < 0 || s.node_prim_count[it.node] == 0; };
+        auto isInner = [&](const Item& it) { return it.node == -1 || (it.node >= 0 && s.node_prim_count[it.node] == 0); };
         auto expand = [&](const Item& it, std::vector<Item>& kids) { if (it.node < 0) kids = it.group; else { kids.clear(); childrenOf((uint32_t)it.node, kids); } };
         auto shape = [&](std::vector<Item>& kids)
         {
@@ -401,9 +450,9 @@ namespace
                 kids.swap(packed);
             }
         };
-        auto leafRef = [&](uint32_t node, uint32_t& ref) -> bool
+        auto leafRef = [&](const Item& it, uint32_t& ref) -> bool
         {
-            const uint32_t first = s.node_first_prim[node], count = s.node_prim_count[node];
+            const uint32_t first = it.first, count = it.count;
             if (count > 255u) return false;
             ref = BVH4_LEAF | (first << 8) | count;
             return true;
@@ -421,7 +470,7 @@ namespace
                 for (int k = 0; k < 3; k++) { n.lo[k][c] = lower(kids[c].box[k]); n.hi[k][c] = upper(kids[c].box[3 + k]); }
                 if (!isInner(kids[c]))
                 {
-                    if (!leafRef((uint32_t)kids[c].node, n.child[c])) return 1;
+                    if (!leafRef(kids[c], n.child[c])) return 1;
                 }
                 else queue.push_back({ kids[c], self, (uint32_t)c });
             }
@@ -459,6 +508,20 @@ namespace
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.quadrics, a.quadrics, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.materials, a.materials, bytes))) return rc;
         if ((rc = devUpload(ctx, ctx->scene_allocs, &d.lights, a.lights, bytes))) return rc;
+        {
+            // shade classes: distinct (material flags, has vertex normals) combinations present in the scene
+            std::vector<uint32_t> combos;
+            std::vector<uint8_t> cls(s.n_prims ? s.n_prims : 1, 1);
+            for (uint32_t i = 0; i < s.n_prims; i++)
+            {
+                const uint32_t combo = (a.materials[a.shade[i].material].flags << 1) | (a.shade[i].vn_index >= 0 ? 1u : 0u);
+                size_t k = 0;
+                while (k < combos.size() && combos[k] != combo) k++;
+                if (k == combos.size()) combos.push_back(combo);
+                cls[i] = (uint8_t)(1u + (k < SHADE_CLASS_BINS - 1u ? k : SHADE_CLASS_BINS - 2u));
+            }
+            if ((rc = devUpload(ctx, ctx->scene_allocs, &d.shade_class, cls, bytes))) return rc;
+        }
         d.n_nodes = s.n_nodes; d.n_prims = s.n_prims; d.n_lights = s.n_lights;
         d.prims_class = PRIMS_TRI;
         for (uint32_t i = 0; i < s.n_prims; i++)
@@ -517,6 +580,10 @@ namespace
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_key, n))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_rank, n))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shadow_order, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shade_key, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shade_rank, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.shade_order, n))) return rc;
+        if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_shade, (size_t)SORT_BINS))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_path, (size_t)SORT_BINS))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.hist_shadow, (size_t)SORT_BINS))) return rc;
         if ((rc = devAlloc(ctx, ctx->sort_allocs, &r.bin_start, (size_t)SORT_BINS))) return rc;
@@ -616,6 +683,7 @@ namespace
         std::memset(&p, 0, sizeof(p));
         p.scene = sceneOf<R>(ctx);
         if (ctx->exact_traversal) p.scene.bvh4 = nullptr;
+        p.scene.dynamic_fetch = (ctx->dynamic_fetch < 0 ? ctx->n_bvh4_nodes >= 2048u : ctx->dynamic_fetch != 0) ? 1u : 0u;
         if (cam)
         {
             p.camera.eye = v3<R>(cam->eye); p.camera.forward = v3<R>(cam->forward);
@@ -656,6 +724,7 @@ namespace
             if ((rc = ensureSort(ctx))) return rc;
             p.sort = ctx->sort;
             p.sort.shade_sorted = ctx->sort_shade ? 1u : 0u;
+            if (!ctx->sort_shade_class || integrator == MCRT_INTERNAL_EMIT) p.sort.shade_order = nullptr;
             {
                 // source-primitive keys for scenes with enough primitives to index space finely
                 const uint32_t n_prims = sceneOf<R>(ctx).n_prims;
@@ -702,6 +771,7 @@ namespace
         {
             CK(cudaMemsetAsync(p.sort.hist_path, 0, SORT_BINS * sizeof(uint32_t), s));
             CK(cudaMemsetAsync(p.sort.hist_shadow, 0, SORT_BINS * sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(ctx->sort.hist_shade, 0, SORT_BINS * sizeof(uint32_t), s));
         }
         auto sortPaths = [&](int buffer)
         {
@@ -743,6 +813,14 @@ namespace
                 }
                 Launch<R>::extend(p, cur, grid, s);
                 if (ev) cudaEventRecord(ev[1], s);
+                if (p.sort.shade_order)
+                {
+                    // group the paths by the material class of what they hit (counted with the shade stage)
+                    Launch<R>::shadeKey(p, grid, s);
+                    launchSortScan(p.sort.hist_shade, p.sort, s);
+                    launchSortScatter(p.sort.shade_key, p.sort.shade_rank, p.sort, p.sort.shade_order, &ctx->d_counters->n_cur, grid, s);
+                    launches += 3;
+                }
                 if (emitting)
                 {
                     Launch<R>::emitShade(p, cur, grid, s);
@@ -795,6 +873,7 @@ namespace
         if (!emitting)
         {
             if (filtered) launchResolveFilmWeighted(ctx->d_film, ctx->d_film_wsum, out_dev, film_pixels, grid, s);
+            else if (ctx->peer_out.n_frames) launchResolveFilmPeers(ctx->d_film, ctx->peer_out, film_pixels * 3, film_weight, grid, s);
             else launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
             launches += 1;
         }
@@ -891,6 +970,7 @@ int mcrt_init(int device, mcrt_ctx** out_ctx)
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MCRT_ERR_CUDA;
     mcrt_ctx* ctx = new mcrt_ctx();
+    if (const char* e = std::getenv("MCRT_BVH4_MAX_LEAF")) ctx->bvh4_max_leaf = (uint32_t)std::atoi(e);   // tuning experiments
     ctx->device = device;
     auto fail = [&](int rc) { mcrt_destroy(ctx); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(MCRT_ERR_CUDA);
@@ -956,8 +1036,11 @@ int mcrt_set_option(mcrt_ctx* ctx, const char* key, double value)
     else if (k == "stage_timing") { ctx->stage_timing = value != 0.0; }
     else if (k == "sort_rays") { ctx->sort_rays = value != 0.0; }
     else if (k == "sort_shade") { ctx->sort_shade = value != 0.0; }
+    else if (k == "sort_shade_class") { ctx->sort_shade_class = value != 0.0; }
     else if (k == "sort_prim_key") { ctx->sort_prim_key = (int)value; }
     else if (k == "exact_traversal") { ctx->exact_traversal = value != 0.0; }
+    else if (k == "dynamic_fetch") { ctx->dynamic_fetch = (int)value; }
+    else if (k == "bvh4_max_leaf") { if (value < 0 || value > 255) return MCRT_ERR_INVALID; ctx->bvh4_max_leaf = (uint32_t)value; }   // takes effect at the next mcrt_scene_upload
     else { ctx->error = "unknown option " + k; return MCRT_ERR_INVALID; }
     return MCRT_OK;
 }
@@ -1405,6 +1488,92 @@ int mcrt_render_rows_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint3
     if (!out_rgb_dev) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     return renderDispatch(ctx, camera, y_first, y_step, n_rows, sqrtspp, global_seed, integrator_kind, precision, out_rgb_dev, stats);
+}
+
+int mcrt_render_rows_strided_peers(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step,
+                                   uint32_t n_rows, uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
+                                   int precision, void* const* frames, uint32_t n_frames, int frame_is_float32, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!frames || n_frames == 0 || n_frames > (uint32_t)MAX_FRAME_PEERS || !camera) { ctx->error = "mcrt_render_rows_strided_peers: 1..16 frames"; return MCRT_ERR_INVALID; }
+    if (!ctx->film_default) { ctx->error = "a filtered film splats across rows: not available for row-sharded renders"; return MCRT_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(ctx->device));
+    PeerFrames pf{};
+    for (uint32_t q = 0; q < n_frames; q++) { if (!frames[q]) { ctx->error = "null frame"; return MCRT_ERR_INVALID; } pf.frame[q] = frames[q]; }
+    pf.n_frames = n_frames; pf.as_float = frame_is_float32 ? 1u : 0u;
+    pf.y_first = y_first; pf.y_step = y_step; pf.row_values = camera->width * 3u;
+    ctx->peer_out = pf;
+    const int rc = renderDispatch(ctx, camera, y_first, y_step, n_rows, sqrtspp, global_seed, integrator_kind, precision,
+                                  static_cast<double*>(frames[0]), stats);
+    ctx->peer_out.n_frames = 0;
+    return rc;
+}
+
+int mcrt_frame_alloc(mcrt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64])
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!dev_ptr || !ipc_handle || bytes == 0) { ctx->error = "mcrt_frame_alloc: invalid arguments"; return MCRT_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); ctx->error = "cudaIpcGetMemHandle failed"; return MCRT_ERR_CUDA; }
+    CK(cudaMemset(p, 0, bytes));
+    std::memcpy(ipc_handle, &h, 64);
+    *dev_ptr = p;
+    return MCRT_OK;
+}
+
+int mcrt_frame_open(mcrt_ctx* ctx, const unsigned char ipc_handle[64], void** dev_ptr)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!dev_ptr || !ipc_handle) { ctx->error = "mcrt_frame_open: invalid arguments"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return MCRT_OK;
+}
+
+int mcrt_frame_close(mcrt_ctx* ctx, void* peer_ptr)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(peer_ptr));
+    return MCRT_OK;
+}
+
+int mcrt_frame_free(mcrt_ctx* ctx, void* dev_ptr)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dev_ptr));
+    return MCRT_OK;
+}
+
+int mcrt_fp64_peak(mcrt_ctx* ctx, double* dfma_per_second)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!dfma_per_second) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int grid = ctx->sm_count * 8, iterations = 2048;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++)   // first repetition warms up
+    {
+        CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+        launchFp64Peak(reinterpret_cast<double*>(ctx->d_counters), iterations, grid, ctx->stream);
+        CK(cudaEventRecord(ctx->ev_stop, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        const double rate = (double)grid * 256.0 * 8.0 * iterations / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    *dfma_per_second = best;
+    return MCRT_OK;
 }
 
 int mcrt_render_rows(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y0, uint32_t y1, uint32_t sqrtspp,

@@ -40,8 +40,8 @@
 #ifndef MCRT_TRACE_MINBLOCKS_FAST          // order-free search (bvh4.cuh)
 #define MCRT_TRACE_MINBLOCKS_FAST 3
 #endif
-#ifndef MCRT_DYNAMIC_FETCH                  // k_extend / k_shadow take rays per lane as lanes finish (traceManyFast)
-#define MCRT_DYNAMIC_FETCH 1
+#ifndef MCRT_TRACE_MINBLOCKS_DYN           // order-free search with dynamic fetch (measured on the spaceship: 64 registers beat 80)
+#define MCRT_TRACE_MINBLOCKS_DYN 4
 #endif
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 3
@@ -125,6 +125,12 @@ namespace mcrt
         uint32_t* block_offset;  // [2 * SORT_BINS / 1024]: segment offsets, then segment totals
         uint32_t* done_counter;  // last-CTA-done counter of k_sort_scan
         uint32_t shade_sorted;   // 1: k_shade also walks the queue in sorted order
+        // shade-coherence sort: k_shade walks the paths grouped by the material class of the primitive they hit
+        // (DeviceScene::shade_class), so that a warp runs one material branch instead of all of them
+        uint32_t* shade_key;     // per path slot: class of the hit (k_shade_key)
+        uint32_t* shade_rank;
+        uint32_t* shade_order;   // null: disabled
+        uint32_t* hist_shade;    // [SORT_BINS] (only SHADE_CLASS_BINS used; shares k_sort_scan)
         uint32_t prim_scale;     // != 0: the cell field of the key is the source primitive's position in
                                  // BVH order, (prim * prim_scale) >> 32 (large scenes: the BVH order is a
                                  // far finer spatial index than a 16^3 grid where the geometry is dense)
@@ -247,7 +253,7 @@ namespace mcrt
     {
         RayQ<R> rq;
         rq.o = o; rq.d = d;
-        if constexpr (!(Mode<R>::parity && FAST)) rq.inv_d = R(1) / d;
+        if constexpr (!(Mode<R>::parity && FAST) || PRIMS == PRIMS_ALL) rq.inv_d = R(1) / d;   // the order-free search needs it for quadrics only (clip-box test)
         if constexpr (Mode<R>::parity)
         {
             if constexpr (FAST)
@@ -456,8 +462,10 @@ namespace mcrt
         c->fetch_shadow = 0;
     }
 
-    template <class R, int PRIMS, bool FAST>
-    __global__ void __launch_bounds__(256, FAST ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned)) k_extend(WaveParams<R> p, int cur)
+    // FAST: 0 reference-order replay for every ray, 1 order-free search one ray per lane, 2 order-free search with
+    // dynamic fetch (traceManyFast; big scenes, where ray lengths within a warp differ most)
+    template <class R, int PRIMS, int FAST>
+    __global__ void __launch_bounds__(256, FAST == 2 ? MCRT_TRACE_MINBLOCKS_DYN : (FAST == 1 ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned))) k_extend(WaveParams<R> p, int cur)
     {
         const uint32_t n = p.counters->n_cur;
         const PathBuffer<R>& in = p.buf[cur];
@@ -465,7 +473,7 @@ namespace mcrt
         uint32_t overflow = 0;
         unsigned long long rays = 0;
         const uint32_t* order = p.sort.path_order;
-        if constexpr (Mode<R>::parity && FAST && MCRT_DYNAMIC_FETCH)
+        if constexpr (Mode<R>::parity && FAST == 2)
         {
             traceManyFast<PRIMS>(p.scene, n, &p.counters->fetch_extend,
                 [&](uint32_t ii, RayQ<R>& r)
@@ -473,6 +481,7 @@ namespace mcrt
                     const uint32_t i = order ? order[ii] : ii;
                     const V4<R> ro = in.ray_o[i], rd = in.ray_d[i];
                     r.o = ro.xyz(); r.d = rd.xyz();
+                    if constexpr (PRIMS == PRIMS_ALL) r.inv_d = R(1) / r.d;   // quadric clip-box test
                     return i;
                 },
                 [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
@@ -493,7 +502,7 @@ namespace mcrt
 #ifdef MCRT_TAIL_DIAGNOSTIC
             const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
 #endif
-            Hit<R> h = traceClosest<PRIMS, FAST>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS, FAST != 0>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
             p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
             rays++;
 #ifdef MCRT_TAIL_DIAGNOSTIC
@@ -565,7 +574,7 @@ namespace mcrt
         uint32_t stack_overflows = 0;
 
         const uint32_t n_rounded = (n + 31u) & ~31u; // keep warps converged for the ballots
-        const uint32_t* order = p.sort.shade_sorted ? p.sort.path_order : nullptr;
+        const uint32_t* order = p.sort.shade_order ? p.sort.shade_order : (p.sort.shade_sorted ? p.sort.path_order : nullptr);
         const bool sorting = p.sort.path_order != nullptr;
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n_rounded; ii += gridDim.x * blockDim.x)
         {
@@ -864,15 +873,15 @@ namespace mcrt
         if (stack_overflows) atomicAdd(&c->ior_stack_overflows, (unsigned long long)stack_overflows);
     }
 
-    template <class R, bool FILM, int PRIMS, bool FAST>
-    __global__ void __launch_bounds__(256, FAST ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned)) k_shadow(WaveParams<R> p)
+    template <class R, bool FILM, int PRIMS, int FAST>
+    __global__ void __launch_bounds__(256, FAST == 2 ? MCRT_TRACE_MINBLOCKS_DYN : (FAST == 1 ? MCRT_TRACE_MINBLOCKS_FAST : (PRIMS == PRIMS_ALL ? Mode<R>::trace_minblocks : Mode<R>::trace_minblocks_pruned))) k_shadow(WaveParams<R> p)
     {
         const uint32_t n = p.counters->n_shadow;
         TraceCounters cnt = { 0u, 0u, 0u };
         uint32_t overflow = 0;
         unsigned long long rays = 0;
         const uint32_t* order = p.sort.shadow_order;
-        if constexpr (Mode<R>::parity && FAST && MCRT_DYNAMIC_FETCH)
+        if constexpr (Mode<R>::parity && FAST == 2)
         {
             traceManyFast<PRIMS>(p.scene, n, &p.counters->fetch_shadow,
                 [&](uint32_t ii, RayQ<R>& r)
@@ -880,6 +889,7 @@ namespace mcrt
                     const uint32_t i = order ? order[ii] : ii;
                     const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
                     r.o = so.xyz(); r.d = sd.xyz();
+                    if constexpr (PRIMS == PRIMS_ALL) r.inv_d = R(1) / r.d;
                     return i;
                 },
                 [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
@@ -902,7 +912,7 @@ namespace mcrt
             const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
-            Hit<R> h = traceClosest<PRIMS, FAST>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            Hit<R> h = traceClosest<PRIMS, FAST != 0>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
             rays++;
             // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
             if (h.prim == sm.x)
@@ -917,6 +927,37 @@ namespace mcrt
     }
 
 
+
+    // ------------------------------------------------------------------------------------------
+    // Shade-coherence key: class of the primitive each live path hit (misses: class 0), ranks from a
+    // per-CTA shared-memory histogram + one global atomic per class per CTA chunk.
+    constexpr uint32_t SHADE_CLASS_BINS = 64;
+
+    template <class R>
+    __global__ void __launch_bounds__(256) k_shade_key(WaveParams<R> p)
+    {
+        __shared__ uint32_t s_hist[SHADE_CLASS_BINS], s_base[SHADE_CLASS_BINS];
+        const uint32_t n = p.counters->n_cur;
+        const uint32_t chunks = (n + 255u) / 256u;
+        for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x)
+        {
+            if (threadIdx.x < SHADE_CLASS_BINS) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t i = chunk * 256u + threadIdx.x;
+            uint32_t key = 0, local = 0;
+            if (i < n)
+            {
+                const R w = p.hits[i].w;
+                if (!(w < R(0))) key = p.scene.shade_class[(uint32_t)w];
+                local = atomicAdd(&s_hist[key], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < SHADE_CLASS_BINS && s_hist[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&p.sort.hist_shade[threadIdx.x], s_hist[threadIdx.x]);
+            __syncthreads();
+            if (i < n) { p.sort.shade_key[i] = key; p.sort.shade_rank[i] = s_base[key] + local; }
+            __syncthreads();
+        }
+    }
 
     // ------------------------------------------------------------------------------------------
     // Counting-sort helpers. k_sort_scan: exclusive prefix sum of the SORT_BINS-entry histogram into
@@ -1347,6 +1388,52 @@ namespace mcrt
             const double v = w == 0.0 ? 0.0 : film[i] / w;
             out[i] = (v < 0.0) ? 0.0 : v;
         }
+    }
+
+    // Film resolve fused with the frame exchange of a row-sharded multi-GPU render: this rank's rows
+    // (y_first + k * y_step) go straight into the full-frame buffer of EVERY rank - peer memory mapped
+    // through CUDA IPC, stores travel over NVLink - at their final position, as the float3 framebuffer
+    // (or float64). No staging buffer, no all-gather, no re-interleaving copy.
+    constexpr int MAX_FRAME_PEERS = 16;
+    struct PeerFrames
+    {
+        void* frame[MAX_FRAME_PEERS];
+        uint32_t n_frames, as_float;
+        uint32_t y_first, y_step, row_values;   // row_values = width * 3
+    };
+
+    static __global__ void __launch_bounds__(256) k_resolve_film_peers(const double* film, PeerFrames pf, size_t n_values, double weight)
+    {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x)
+        {
+            double v = film[i] / weight;
+            v = (v < 0.0) ? 0.0 : v;
+            const size_t row = i / pf.row_values, col = i - row * pf.row_values;
+            const size_t at = ((size_t)pf.y_first + row * pf.y_step) * pf.row_values + col;
+            if (pf.as_float)
+            {
+                const float f = (float)v;
+                for (uint32_t q = 0; q < pf.n_frames; q++) static_cast<float*>(pf.frame[q])[at] = f;
+            }
+            else
+            {
+                for (uint32_t q = 0; q < pf.n_frames; q++) static_cast<double*>(pf.frame[q])[at] = v;
+            }
+        }
+    }
+
+    // FP64 issue-rate probe for bench.py's roofline: 8 independent DFMA chains per thread
+    static __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iterations)
+    {
+        double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+        const double m = 1.0000001, c = 1e-9;
+        for (int i = 0; i < iterations; i++)
+        {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+        const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+        if (r == 12345.678) sink[0] = r;   // never true: keeps the chains alive
     }
 
     static __global__ void k_resolve_film(const double* film, double* out, size_t n_values, double weight)

@@ -28,6 +28,16 @@ namespace mcrt
         k_resolve_film<<<grid, 256, 0, s>>>(film, out, n_values, weight);
     }
 
+    void launchResolveFilmPeers(const double* film, const PeerFrames& pf, size_t n_values, double weight, int grid, cudaStream_t s)
+    {
+        k_resolve_film_peers<<<grid, 256, 0, s>>>(film, pf, n_values, weight);
+    }
+
+    void launchFp64Peak(double* sink, int iterations, int grid, cudaStream_t s)
+    {
+        k_fp64_peak<<<grid, 256, 0, s>>>(sink, iterations);
+    }
+
     void launchKnnUser(const DevicePhotonMap& map, uint32_t k, const double* points, size_t n, uint32_t* out_index,
                        double* out_d2, uint32_t* out_count, uint32_t* overflow_flag, int grid, cudaStream_t s)
     {

@@ -13,17 +13,24 @@ namespace mcrt
         // triangle-only scenes (every OBJ scene) run the traversal without sphere / quadric code
         if constexpr (Mode<MCRT_REAL>::parity)
         {
+            if (p.scene.bvh4 && p.scene.dynamic_fetch)
+            {
+                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 2><<<grid, 256, 0, s>>>(p, cur);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 2><<<grid, 256, 0, s>>>(p, cur);
+                else k_extend<MCRT_REAL, PRIMS_ALL, 2><<<grid, 256, 0, s>>>(p, cur);
+                return;
+            }
             if (p.scene.bvh4)
             {
-                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, true><<<grid, 256, 0, s>>>(p, cur);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, true><<<grid, 256, 0, s>>>(p, cur);
-                else k_extend<MCRT_REAL, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p, cur);
+                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 1><<<grid, 256, 0, s>>>(p, cur);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 1><<<grid, 256, 0, s>>>(p, cur);
+                else k_extend<MCRT_REAL, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p, cur);
                 return;
             }
         }
-        if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, false><<<grid, 256, 0, s>>>(p, cur);
-        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, false><<<grid, 256, 0, s>>>(p, cur);
-        else k_extend<MCRT_REAL, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p, cur);
+        if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 0><<<grid, 256, 0, s>>>(p, cur);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 0><<<grid, 256, 0, s>>>(p, cur);
+        else k_extend<MCRT_REAL, PRIMS_ALL, 0><<<grid, 256, 0, s>>>(p, cur);
     }
     template <> void Launch<MCRT_REAL>::shade(const WaveParams<MCRT_REAL>& p, int cur, int grid, cudaStream_t s)
     {
@@ -78,19 +85,30 @@ namespace mcrt
     {
         if constexpr (Mode<MCRT_REAL>::parity)
         {
+            if (p.scene.bvh4 && p.scene.dynamic_fetch && p.filmp.is_default_box)
+            {
+                if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 2><<<grid, 256, 0, s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 2><<<grid, 256, 0, s>>>(p);
+                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 2><<<grid, 256, 0, s>>>(p);
+                return;
+            }
             if (p.scene.bvh4)
             {
-                if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p);
-                else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, true><<<grid, 256, 0, s>>>(p);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, true><<<grid, 256, 0, s>>>(p);
-                else k_shadow<MCRT_REAL, false, PRIMS_ALL, true><<<grid, 256, 0, s>>>(p);
+                if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 1><<<grid, 256, 0, s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 1><<<grid, 256, 0, s>>>(p);
+                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p);
                 return;
             }
         }
-        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p);
-        else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, false><<<grid, 256, 0, s>>>(p);
-        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, false><<<grid, 256, 0, s>>>(p);
-        else k_shadow<MCRT_REAL, false, PRIMS_ALL, false><<<grid, 256, 0, s>>>(p);
+        if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, 0><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 0><<<grid, 256, 0, s>>>(p);
+        else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 0><<<grid, 256, 0, s>>>(p);
+        else k_shadow<MCRT_REAL, false, PRIMS_ALL, 0><<<grid, 256, 0, s>>>(p);
+    }
+    template <> void Launch<MCRT_REAL>::shadeKey(const WaveParams<MCRT_REAL>& p, int grid, cudaStream_t s)
+    {
+        k_shade_key<MCRT_REAL><<<grid, 256, 0, s>>>(p);
     }
     template <> void Launch<MCRT_REAL>::emitGenerate(const WaveParams<MCRT_REAL>& p, int next, int grid, cudaStream_t s)
     {

@@ -102,9 +102,13 @@ namespace mcrt
         const Quadric<R>* quadrics;
         const Material<R>* materials;
         const Light<R>* lights;
+        const uint8_t* shade_class;   // per ordered primitive: 1 + index of its material's flag combination (+ vertex normals) among
+                                      // those present in the scene (< 64); the shade-coherence sort groups paths by it
         uint32_t n_nodes, n_prims, n_lights, n_wide_root; // n_wide_root: children of the root
         uint32_t root_is_leaf, root_first_prim, root_prim_count;
-        uint32_t prims_class, _pad3[3]; // PRIMS_ALL / PRIMS_TRI_SPHERE / PRIMS_TRI: selects the pruned traversal kernels
+        uint32_t prims_class;     // PRIMS_ALL / PRIMS_TRI_SPHERE / PRIMS_TRI: selects the pruned traversal kernels
+        uint32_t dynamic_fetch;   // k_extend / k_shadow take rays per lane as lanes finish (bvh4.cuh traceManyFast)
+        uint32_t _pad3[2];
         uint32_t material_flags_any;   // OR of Material::flags over the scene: selects the k_shade feature set
         R root_bmin[3], root_bmax[3];
         R scene_ior;

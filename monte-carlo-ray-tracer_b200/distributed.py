@@ -1,6 +1,9 @@
 """Multi-GPU plumbing for the row-sharded render: one process per GPU, scene
-replicated, rows interleaved over ranks, one all-gather of the float64 framebuffer per frame.
-Pure torch.distributed (NCCL on GPUs, gloo in the CPU tests) - nothing here touches the kernels."""
+replicated, rows interleaved over ranks. The frame exchange is fused into the film resolve: every
+rank owns a full-frame float3 buffer that its peers map through CUDA IPC (PeerFrames), and the resolve
+kernel of each rank stores its rows into all of them over NVLink (mcrt_render_rows_strided_peers).
+torch.distributed carries the 64-byte handles and the barriers (NCCL on GPUs, gloo in the CPU tests);
+gather_frame is the plain all-gather form kept for hosts without peer access."""
 import torch
 import torch.distributed as dist
 
@@ -24,3 +27,56 @@ def gather_frame(local, height, world, out=None):
     gathered = gathered.view(world * rows, W, C)   # concatenation layout (what gloo and NCCL both accept)
     dist.all_gather_into_tensor(gathered, local.contiguous())
     return gathered.view(world, rows, W, C).permute(1, 0, 2, 3).reshape(rows * world, W, C)[:height].contiguous()
+
+
+def exchange_handles(handle, world, device=None):
+    """All ranks' 64-byte IPC handles, in rank order (all_gather of a uint8 tensor)."""
+    assert len(handle) == 64
+    if world == 1:
+        return [bytes(handle)]
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+    out = torch.empty((world, 64), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out.view(-1), mine)
+    return [bytes(row.tolist()) for row in out.cpu()]
+
+
+class PeerFrames:
+    """One full-frame buffer [height, width, 3] per rank (float32 by default: the north star's float3
+    framebuffer), each mapped into every other rank. `ptrs` = device pointers usable on this rank, own
+    buffer first is NOT assumed: ptrs[r] is rank r's frame."""
+
+    def __init__(self, integrator, rank, world, height, width, float32=True, device=None):
+        self.integrator, self.rank, self.world = integrator, rank, world
+        self.height, self.width, self.float32 = height, width, float32
+        self.nbytes = height * width * 3 * (4 if float32 else 8)
+        self.own, handle = integrator.frame_alloc(self.nbytes)
+        handles = exchange_handles(handle, world, device)
+        self.ptrs = [self.own if r == rank else integrator.frame_open(handles[r]) for r in range(world)]
+
+    def tensor(self):
+        """The rank's own frame as a torch tensor (no copy)."""
+        import ctypes
+        dtype = torch.float32 if self.float32 else torch.float64
+        n = self.height * self.width * 3
+        iface = {"shape": (n,), "typestr": "<f4" if self.float32 else "<f8", "data": (self.own, False), "version": 2}
+        holder = type("FrameMem", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=torch.device("cuda", self.integrator.device)).view(self.height, self.width, 3)
+
+    def render(self, camera, sqrtspp=None):
+        """Renders this rank's interleaved rows into every rank's frame. Call barrier() before reading."""
+        y_first, y_step, n_rows = interleaved_rows(self.rank, self.world, self.height)
+        return self.integrator.render_rows_strided_peers(camera, self.ptrs, y_first, y_step, n_rows, self.float32, sqrtspp)
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.integrator.frame_close(p)
+        if self.world > 1:
+            dist.barrier()   # nobody frees a buffer a peer still maps
+        self.integrator.frame_free(self.own)
+        self.ptrs = []

@@ -11,6 +11,7 @@ ap.add_argument("pack"); ap.add_argument("--width", type=int); ap.add_argument("
 ap.add_argument("--sqrtspp", type=int); ap.add_argument("--rays", type=int, default=2_000_000)
 ap.add_argument("--reps", type=int, default=2); ap.add_argument("--pool", type=float, default=float(1 << 24))
 ap.add_argument("--skip-exact-render", action="store_true"); ap.add_argument("--tag", default="")
+ap.add_argument("--skip-trace", action="store_true"); ap.add_argument("--opt", action="append", default=[], help="key=value option")
 a = ap.parse_args()
 m = importlib.import_module("monte-carlo-ray-tracer_b200")
 scene = m.Scene.from_pack(a.pack)
@@ -18,9 +19,13 @@ cam = scene.cameras()[0]
 cam = cam.resized(a.width or cam.width, a.height or cam.height, a.sqrtspp or cam.sqrtspp)
 pt = m.PathTracer(scene, precision=m.PRECISION_F64)
 pt.set_option("pool_paths", a.pool); pt.set_option("stage_timing", 1)
+for kv in a.opt:
+    k_, v_ = kv.split("="); pt.set_option(k_, float(v_))
 out = {"pack": os.path.basename(a.pack), "tag": a.tag, "lib": os.environ.get("MCRT_LIB", "")}
 
 # ---- incoherent rays: segments between points on the surfaces the camera sees, plus the camera rays
+if a.skip_trace:
+    a.rays = 1000
 rng = np.random.default_rng(5)
 n = a.rays
 px = rng.integers(0, cam.width * cam.height, n // 4).astype(np.uint32)
