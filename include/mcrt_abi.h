@@ -230,6 +230,23 @@ typedef struct mcrt_photon_emit_params {
 int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision,
                      uint64_t* n_caustic, uint64_t* n_global, mcrt_stats* stats);
 
+/* The photon pass in pieces, for sharding it over GPUs (emission sharded by ranges of the
+ * reference's EmissionWork index space, photon-mapper.cpp:61-78, photons all-gathered, every rank builds the
+ * same octrees):
+ *   mcrt_photon_emit_total   size of the emission index space (sum over lights of their emission counts)
+ *   mcrt_photon_emit_range   emits work items [work_first, work_first + work_count); the photons stay in device
+ *                            buffers of the context - 8 floats per photon {flux.xyz, pos.xyz, phi, theta} - whose
+ *                            addresses are returned (valid until the next emission / mcrt_destroy)
+ *   mcrt_photon_build_dev    builds both octrees from device photon arrays (this rank's, or the concatenation
+ *                            of all ranks') and installs them like mcrt_photon_upload
+ * mcrt_photon_emit == total, range(0, total), build. */
+int mcrt_photon_emit_total(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, uint64_t* total_emissions);
+int mcrt_photon_emit_range(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision,
+                           uint64_t work_first, uint64_t work_count, const float** caustic_dev, uint64_t* n_caustic,
+                           const float** global_dev, uint64_t* n_global, mcrt_stats* stats);
+int mcrt_photon_build_dev(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, const float* caustic_dev,
+                          uint64_t n_caustic, const float* global_dev, uint64_t n_global, double* build_ms);
+
 /* Host view of the maps built by mcrt_photon_emit (which: 0 caustic, 1 global). The pointers stay
  * valid until the next mcrt_photon_emit / mcrt_destroy. */
 int mcrt_photon_download(mcrt_ctx* ctx, int which, mcrt_photon_map_desc* out);
@@ -347,6 +364,16 @@ int mcrt_render_rows_strided_peers(mcrt_ctx* ctx, const mcrt_camera* camera, uin
                                    uint32_t global_seed, int integrator_kind, int precision,
                                    void* const* frames, uint32_t n_frames, int frame_is_float32,
                                    mcrt_stats* stats);
+/* Reconstruction filters across row shards (film.cpp:61-79): with a filter set by mcrt_set_film a sample splats
+ * into neighbouring rows, so a rank that renders rows y_first + k*y_step accumulates into whole-frame buffers and
+ * returns them UNRESOLVED: rgb_sum_dev[height*width][3] and weight_sum_dev[height*width] (device, float64). The
+ * host adds them over the ranks (an all-reduce) and calls mcrt_film_resolve_dev, Film::Splat::get (film.cpp:106-113). */
+int mcrt_render_film_sums_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step,
+                                      uint32_t n_rows, uint32_t sqrtspp, uint32_t global_seed, int integrator_kind,
+                                      int precision, double* rgb_sum_dev, double* weight_sum_dev, mcrt_stats* stats);
+int mcrt_film_resolve_dev(mcrt_ctx* ctx, const double* rgb_sum_dev, const double* weight_sum_dev, uint64_t n_pixels,
+                          double* out_rgb_dev);
+
 /* A device buffer that other processes on the node can map: *dev_ptr (zero-filled) and its 64-byte CUDA IPC
  * handle, to be sent to the peers by whatever channel the host uses (torch.distributed in this repository). */
 int mcrt_frame_alloc(mcrt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);

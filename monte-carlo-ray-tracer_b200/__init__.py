@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "mcrt_obj_load", "mcrt_obj_free", "mcrt_obj_vertex_normals",
     "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
     "mcrt_render_rows_strided_peers", "mcrt_frame_alloc", "mcrt_frame_open", "mcrt_frame_close", "mcrt_frame_free",
-    "mcrt_fp64_peak",
+    "mcrt_render_film_sums_strided_dev", "mcrt_film_resolve_dev",
+    "mcrt_fp64_peak", "mcrt_photon_emit_total", "mcrt_photon_emit_range", "mcrt_photon_build_dev",
 ]
 
 
@@ -200,6 +201,14 @@ def lib():
         L.mcrt_frame_close.argtypes = [C.c_void_p, C.c_void_p]
         L.mcrt_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.mcrt_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.mcrt_render_film_sums_strided_dev.argtypes = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                        C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        L.mcrt_film_resolve_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.mcrt_photon_emit_total.argtypes = [C.c_void_p, C.POINTER(PhotonEmitParams), C.POINTER(C.c_uint64)]
+        L.mcrt_photon_emit_range.argtypes = [C.c_void_p, C.POINTER(PhotonEmitParams), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Stats)]
+        L.mcrt_photon_build_dev.argtypes = [C.c_void_p, C.POINTER(PhotonEmitParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_double)]
         L.mcrt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
@@ -534,6 +543,20 @@ class Integrator:
         self.last_stats = st.as_dict()
         return self.last_stats
 
+    def render_film_sums_strided_dev(self, camera, rgb_sum_ptr, weight_sum_ptr, y_first, y_step, n_rows, sqrtspp=None, precision=None):
+        """Row shard of a render through the camera's reconstruction filter: unresolved whole-frame sums (device)."""
+        self.set_film(camera)
+        st = Stats()
+        self._check(lib().mcrt_render_film_sums_strided_dev(self.ctx, C.byref(camera.rec), y_first, y_step, n_rows,
+                                                            camera.sqrtspp if sqrtspp is None else sqrtspp, self.global_seed, self.kind,
+                                                            self.precision if precision is None else precision,
+                                                            C.c_void_p(rgb_sum_ptr), C.c_void_p(weight_sum_ptr), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def film_resolve_dev(self, rgb_sum_ptr, weight_sum_ptr, n_pixels, out_ptr):
+        self._check(lib().mcrt_film_resolve_dev(self.ctx, C.c_void_p(rgb_sum_ptr), C.c_void_p(weight_sum_ptr), n_pixels, C.c_void_p(out_ptr)))
+
     def frame_alloc(self, nbytes):
         """-> (device pointer, 64-byte CUDA IPC handle) of a zero-filled buffer other ranks can map"""
         ptr = C.c_void_p(); h = (C.c_ubyte * 64)()
@@ -617,9 +640,7 @@ class PhotonMapper(Integrator):
         self._maps = maps
         self.upload_photons()
 
-    def emit(self, emissions, caustic_factor, max_photons_per_octree_leaf=200, k_nearest_photons=50,
-             direct_visualization=False, scene_bounds=None, precision=None):
-        """PhotonMapper::PhotonMapper's first pass on the GPU; replaces the uploaded maps."""
+    def _emit_params(self, emissions, caustic_factor, max_photons_per_octree_leaf, k_nearest_photons, direct_visualization, scene_bounds):
         p = PhotonEmitParams()
         p.emissions = int(emissions); p.caustic_factor = float(caustic_factor)
         p.max_photons_per_octree_leaf = int(max_photons_per_octree_leaf); p.k_nearest_photons = int(k_nearest_photons)
@@ -627,6 +648,44 @@ class PhotonMapper(Integrator):
         b = scene_bounds if scene_bounds is not None else self.scene.a["node_bounds"][:6]
         for i in range(6):
             p.scene_bounds[i] = float(b[i])
+        return p
+
+    def emit_sharded(self, rank, world, emissions, caustic_factor, max_photons_per_octree_leaf=200, k_nearest_photons=50,
+                     direct_visualization=False, scene_bounds=None, precision=None):
+        """The photon pass over `world` GPUs: this rank emits its range of the emission index space
+        (distributed.emission_range), the photon arrays are all-gathered (torch.distributed), and every rank builds the
+        same two octrees from the concatenation. -> (n_caustic, n_global) of the whole maps."""
+        import torch
+        from . import distributed as mdist
+        p = self._emit_params(emissions, caustic_factor, max_photons_per_octree_leaf, k_nearest_photons, direct_visualization, scene_bounds)
+        prec = self.precision if precision is None else precision
+        total = C.c_uint64()
+        self._check(lib().mcrt_photon_emit_total(self.ctx, C.byref(p), C.byref(total)))
+        first, count = mdist.emission_range(total.value, rank, world)
+        ptr = [C.c_void_p(), C.c_void_p()]; n = [C.c_uint64(), C.c_uint64()]; st = Stats()
+        self._check(lib().mcrt_photon_emit_range(self.ctx, C.byref(p), prec, first, count, C.byref(ptr[0]), C.byref(n[0]),
+                                                 C.byref(ptr[1]), C.byref(n[1]), C.byref(st)))
+        self.last_stats = st.as_dict()
+        dev = torch.device("cuda", self.device)
+        gathered = []
+        for w in range(2):
+            mine = mdist.device_view(ptr[w].value, n[w].value * 8, torch.float32, dev)
+            gathered.append(mdist.all_gather_photons(mine, world, dev))
+        ms = C.c_double()
+        self._check(lib().mcrt_photon_build_dev(self.ctx, C.byref(p), C.c_void_p(gathered[0].data_ptr()), gathered[0].numel() // 8,
+                                                C.c_void_p(gathered[1].data_ptr()), gathered[1].numel() // 8, C.byref(ms)))
+        torch.cuda.synchronize(dev)
+        self.last_stats["gpu_ms_knn"] = ms.value
+        self.k_nearest = int(k_nearest_photons)
+        self._host_maps = None
+        self._emitted = (int(k_nearest_photons), int(bool(direct_visualization)))
+        self.n_photons = (gathered[0].numel() // 8, gathered[1].numel() // 8)
+        return self.n_photons
+
+    def emit(self, emissions, caustic_factor, max_photons_per_octree_leaf=200, k_nearest_photons=50,
+             direct_visualization=False, scene_bounds=None, precision=None):
+        """PhotonMapper::PhotonMapper's first pass on the GPU; replaces the uploaded maps."""
+        p = self._emit_params(emissions, caustic_factor, max_photons_per_octree_leaf, k_nearest_photons, direct_visualization, scene_bounds)
         nc, ng, st = C.c_uint64(), C.c_uint64(), Stats()
         self._check(lib().mcrt_photon_emit(self.ctx, C.byref(p), self.precision if precision is None else precision,
                                            C.byref(nc), C.byref(ng), C.byref(st)))

@@ -67,6 +67,7 @@ struct mcrt_ctx
     uint32_t n_bvh4_nodes = 0;
     uint32_t bvh4_max_leaf = 0xFFFFFFFFu;   // auto; 0: keep the reference's leaves; n: cut larger leaves into runs of n (option / MCRT_BVH4_MAX_LEAF)
     int dynamic_fetch = -1;       // -1 auto (scenes with >= 2048 BVH4 nodes), 0 off, 1 on
+    double* film_raw_rgb = nullptr; double* film_raw_wsum = nullptr;   // != null: the next filtered render leaves its unresolved sums here (mcrt_render_film_sums_strided_dev)
     PeerFrames peer_out{};   // n_frames != 0: the next resolve writes into these frames (mcrt_render_rows_strided_peers)
     int exact_traversal = 0;   // 1: every ray takes the reference-order replay (traverseReferenceOrder)
 
@@ -113,11 +114,14 @@ struct mcrt_ctx
     const void* d_emit_flux = nullptr;
     float4* d_emit_photons[2] = { nullptr, nullptr };
     unsigned long long emit_capacity[2] = { 0, 0 };
+    std::vector<void*> emit_allocs;          // emission buffers (kept until the next emission / mcrt_destroy)
+    unsigned long long emit_stored[2] = { 0, 0 };
+    unsigned long long emit_work_first = 0;   // first emission index of the range being emitted (mcrt_photon_emit_range)
     double emit_non_caustic_reject = 1.0;
     void* knn_queue64 = nullptr; void* knn_queue32 = nullptr;
     uint32_t knn_capacity64 = 0, knn_capacity32 = 0;
 
-    std::vector<cudaEvent_t> stage_events; // 5 per wavefront iteration when stage_timing is on
+    std::vector<cudaEvent_t> stage_events; // 6 per wavefront iteration when stage_timing is on (the 6th: before k_knn)
     std::vector<uint8_t> prim_interpolates; // host copy: ordered prim has vertex normals
 
     // ray-coherence sort buffers (shared by both precisions)
@@ -762,6 +766,7 @@ namespace
         Counters init;
         std::memset(&init, 0, sizeof(init));
         init.total_work = total_work;
+        if (integrator == MCRT_INTERNAL_EMIT) { init.next_work = ctx->emit_work_first; init.total_work = ctx->emit_work_first + total_work; }
         ctx->h_counters[0] = init;
         CK(cudaMemcpyAsync(ctx->d_counters, &ctx->h_counters[0], sizeof(Counters), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ctx->d_film, 0, film_pixels * 3 * sizeof(double), s));
@@ -802,13 +807,13 @@ namespace
                 cudaEvent_t* ev = nullptr;
                 if (ctx->stage_timing)
                 {
-                    while (ctx->stage_events.size() < 5 * (iterations + 1))
+                    while (ctx->stage_events.size() < 6 * (iterations + 1))
                     {
                         cudaEvent_t e;
                         CK(cudaEventCreate(&e));
                         ctx->stage_events.push_back(e);
                     }
-                    ev = &ctx->stage_events[5 * iterations];
+                    ev = &ctx->stage_events[6 * iterations];
                     cudaEventRecord(ev[0], s);
                 }
                 Launch<R>::extend(p, cur, grid, s);
@@ -828,6 +833,7 @@ namespace
                 else if (integrator == MCRT_INTEGRATOR_PHOTON)
                 {
                     Launch<R>::shadePhoton(p, cur, grid, s);
+                    if (ev) cudaEventRecord(ev[5], s);
                     Launch<R>::knn(p, grid, s);
                     launches += 1;
                 }
@@ -872,7 +878,13 @@ namespace
 
         if (!emitting)
         {
-            if (filtered) launchResolveFilmWeighted(ctx->d_film, ctx->d_film_wsum, out_dev, film_pixels, grid, s);
+            if (filtered && ctx->film_raw_rgb)
+            {
+                // row-sharded filtered film: the caller sums these over ranks, then mcrt_film_resolve_dev
+                CK(cudaMemcpyAsync(ctx->film_raw_rgb, ctx->d_film, film_pixels * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                CK(cudaMemcpyAsync(ctx->film_raw_wsum, ctx->d_film_wsum, film_pixels * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            }
+            else if (filtered) launchResolveFilmWeighted(ctx->d_film, ctx->d_film_wsum, out_dev, film_pixels, grid, s);
             else if (ctx->peer_out.n_frames) launchResolveFilmPeers(ctx->d_film, ctx->peer_out, film_pixels * 3, film_weight, grid, s);
             else launchResolveFilm(ctx->d_film, out_dev, film_pixels * 3, film_weight, grid, s);
             launches += 1;
@@ -893,7 +905,8 @@ namespace
             {
                 for (uint64_t it = 0; it < iterations; it++)
                 {
-                    cudaEvent_t* ev = &ctx->stage_events[5 * it];
+                    cudaEvent_t* ev = &ctx->stage_events[6 * it];
+                    if (integrator == MCRT_INTEGRATOR_PHOTON) { float tk = 0; cudaEventElapsedTime(&tk, ev[5], ev[2]); stats->gpu_ms_knn += tk; }
                     float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
                     cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]);
                     cudaEventElapsedTime(&t23, ev[2], ev[3]); cudaEventElapsedTime(&t34, ev[3], ev[4]);
@@ -934,7 +947,7 @@ namespace
             ctx->error = "mcrt_render_rows: invalid camera / row range / sqrtspp";
             return MCRT_ERR_INVALID;
         }
-        if (!ctx->film_default && (y_first != 0 || y_step != 1 || n_rows != camera->height))
+        if (!ctx->film_default && !ctx->film_raw_rgb && (y_first != 0 || y_step != 1 || n_rows != camera->height))
         {
             ctx->error = "a reconstruction filter other than the default box splats across rows: render the whole frame in one call";
             return MCRT_ERR_UNSUPPORTED;
@@ -944,12 +957,14 @@ namespace
         const uint32_t n_pixels = (uint32_t)n_pixels64;
         const uint32_t spp = sqrtspp * sqrtspp;
         const uint64_t total = (uint64_t)n_pixels * spp;
+        // a filtered film accumulates at image positions (samples splat across rows): its buffers span the whole frame
+        const size_t film_pixels = ctx->film_default ? (size_t)n_pixels : (size_t)camera->width * camera->height;
         if (precision == MCRT_PRECISION_F64)
             return runWavefront<double>(ctx, camera, y_first, y_step, n_pixels, spp, total, global_seed, integrator_kind,
-                                        nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
+                                        nullptr, nullptr, nullptr, film_pixels, (double)spp, out_dev, stats);
         if (precision == MCRT_PRECISION_F32)
             return runWavefront<float>(ctx, camera, y_first, y_step, n_pixels, spp, total, global_seed, integrator_kind,
-                                       nullptr, nullptr, nullptr, n_pixels, (double)spp, out_dev, stats);
+                                       nullptr, nullptr, nullptr, film_pixels, (double)spp, out_dev, stats);
         ctx->error = "unknown precision";
         return MCRT_ERR_INVALID;
     }
@@ -1204,10 +1219,11 @@ int mcrt_photon_upload(mcrt_ctx* ctx, const mcrt_photon_map_desc* caustic_map, c
 }
 
 
-int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision, uint64_t* n_caustic,
-                     uint64_t* n_global, mcrt_stats* stats)
+// Emission index space of PhotonMapper::PhotonMapper (photon-mapper.cpp:38-78): work item w = emission j of light l,
+// offsets[l] <= w < offsets[l+1], emissions per light proportional to its flux. -> offsets, per-photon flux.
+static int emissionPlan(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, std::vector<unsigned long long>& offsets,
+                        std::vector<V4<double>>& flux64, std::vector<V4<float>>& flux32)
 {
-    if (!ctx) return MCRT_ERR_INVALID;
     if (!params || params->emissions == 0 || !(params->caustic_factor > 0.0) || params->max_photons_per_octree_leaf == 0 ||
         params->k_nearest_photons == 0)
     { ctx->error = "mcrt_photon_emit: invalid parameters"; return MCRT_ERR_INVALID; }
@@ -1216,16 +1232,13 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
     CK(cudaSetDevice(ctx->device));
     const DeviceScene<double>& sc = ctx->scene64;
     if (sc.n_lights == 0) { ctx->error = "scene has no emissive surfaces"; return MCRT_ERR_INVALID; }
-
-    // photon-mapper.cpp:38-72: emissions per light proportional to its flux
     std::vector<Light<double>> lights(sc.n_lights);
     CK(cudaMemcpy(lights.data(), sc.lights, sizeof(Light<double>) * sc.n_lights, cudaMemcpyDeviceToHost));
     const size_t photon_emissions = (size_t)((double)params->emissions * params->caustic_factor);
     double total_add_flux = 0.0;
     for (const auto& l : lights) { V3<double> f = l.emittance * l.area; total_add_flux += (0.0 + f.x + f.y + f.z); }
-    std::vector<unsigned long long> offsets(sc.n_lights + 1, 0);
-    std::vector<V4<double>> flux64(sc.n_lights);
-    std::vector<V4<float>> flux32(sc.n_lights);
+    offsets.assign(sc.n_lights + 1, 0);
+    flux64.resize(sc.n_lights); flux32.resize(sc.n_lights);
     for (uint32_t i = 0; i < sc.n_lights; i++)
     {
         const V3<double> light_flux = lights[i].emittance * lights[i].area;
@@ -1236,66 +1249,132 @@ int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int p
         flux64[i] = V4<double>(pf, 0.0);
         flux32[i] = V4<float>((float)pf.x, (float)pf.y, (float)pf.z, 0.0f);
     }
-    const uint64_t total = offsets[sc.n_lights];
-    if (total == 0) { ctx->error = "no emissions"; return MCRT_ERR_INVALID; }
+    if (offsets[sc.n_lights] == 0) { ctx->error = "no emissions"; return MCRT_ERR_INVALID; }
+    return MCRT_OK;
+}
 
-    std::vector<void*> tmp;
-    auto cleanup = [&]() { freeAll(tmp); ctx->d_emit_offsets = nullptr; ctx->d_emit_flux = nullptr; ctx->d_emit_photons[0] = ctx->d_emit_photons[1] = nullptr; };
+static void freeEmission(mcrt_ctx* ctx)
+{
+    freeAll(ctx->emit_allocs);
+    ctx->d_emit_offsets = nullptr; ctx->d_emit_flux = nullptr; ctx->d_emit_photons[0] = ctx->d_emit_photons[1] = nullptr;
+    ctx->emit_stored[0] = ctx->emit_stored[1] = 0;
+}
+
+int mcrt_photon_emit_total(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, uint64_t* total_emissions)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!total_emissions) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
+    std::vector<unsigned long long> offsets; std::vector<V4<double>> f64; std::vector<V4<float>> f32;
+    const int rc = emissionPlan(ctx, params, offsets, f64, f32);
+    if (rc) return rc;
+    *total_emissions = offsets.back();
+    return MCRT_OK;
+}
+
+int mcrt_photon_emit_range(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision, uint64_t work_first, uint64_t work_count,
+                           const float** caustic_dev, uint64_t* n_caustic, const float** global_dev, uint64_t* n_global, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    std::vector<unsigned long long> offsets; std::vector<V4<double>> flux64; std::vector<V4<float>> flux32;
+    int rc = emissionPlan(ctx, params, offsets, flux64, flux32);
+    if (rc) return rc;
+    const uint64_t total = offsets.back();
+    if (work_first > total || work_count > total - work_first) { ctx->error = "mcrt_photon_emit_range: range outside the emission index space"; return MCRT_ERR_INVALID; }
+    if (precision != MCRT_PRECISION_F64 && precision != MCRT_PRECISION_F32) { ctx->error = "unknown precision"; return MCRT_ERR_INVALID; }
+
+    freeEmission(ctx);
     uint64_t bytes = 0;
     const unsigned long long* d_off = nullptr;
-    int rc = devUpload(ctx, tmp, &d_off, offsets, bytes);
-    if (rc) { cleanup(); return rc; }
+    if ((rc = devUpload(ctx, ctx->emit_allocs, &d_off, offsets, bytes))) { freeEmission(ctx); return rc; }
     const void* d_flux = nullptr;
-    if (precision == MCRT_PRECISION_F64) { const V4<double>* q = nullptr; rc = devUpload(ctx, tmp, &q, flux64, bytes); d_flux = q; }
-    else if (precision == MCRT_PRECISION_F32) { const V4<float>* q = nullptr; rc = devUpload(ctx, tmp, &q, flux32, bytes); d_flux = q; }
-    else { cleanup(); ctx->error = "unknown precision"; return MCRT_ERR_INVALID; }
-    if (rc) { cleanup(); return rc; }
+    if (precision == MCRT_PRECISION_F64) { const V4<double>* q = nullptr; rc = devUpload(ctx, ctx->emit_allocs, &q, flux64, bytes); d_flux = q; }
+    else { const V4<float>* q = nullptr; rc = devUpload(ctx, ctx->emit_allocs, &q, flux32, bytes); d_flux = q; }
+    if (rc) { freeEmission(ctx); return rc; }
     // capacity: a path stores at most one photon per bounce; 4 photons per emission per map is far
     // above what any shipped scene produces (1.2 caustic per emission in water_caustics)
     for (int w = 0; w < 2; w++)
     {
-        ctx->emit_capacity[w] = 4ull * total + 1024;
-        if ((rc = devAlloc(ctx, tmp, &ctx->d_emit_photons[w], (size_t)ctx->emit_capacity[w] * 2))) { cleanup(); return rc; }
+        ctx->emit_capacity[w] = 4ull * work_count + 1024;
+        if ((rc = devAlloc(ctx, ctx->emit_allocs, &ctx->d_emit_photons[w], (size_t)ctx->emit_capacity[w] * 2))) { freeEmission(ctx); return rc; }
     }
     ctx->d_emit_offsets = d_off; ctx->d_emit_flux = d_flux;
     ctx->emit_non_caustic_reject = 1.0 / params->caustic_factor;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cleanup(); ctx->error = "mcrt_photon_emit: upload failed"; return MCRT_ERR_CUDA; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { freeEmission(ctx); ctx->error = "mcrt_photon_emit: upload failed"; return MCRT_ERR_CUDA; }
 
-    if (precision == MCRT_PRECISION_F64)
-        rc = runWavefront<double>(ctx, nullptr, 0, 1, 0, 1, total, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
-    else
-        rc = runWavefront<float>(ctx, nullptr, 0, 1, 0, 1, total, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
-    if (rc) { cleanup(); return rc; }
+    if (work_count)
+    {
+        ctx->emit_work_first = work_first;
+        if (precision == MCRT_PRECISION_F64)
+            rc = runWavefront<double>(ctx, nullptr, 0, 1, 0, 1, work_count, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
+        else
+            rc = runWavefront<float>(ctx, nullptr, 0, 1, 0, 1, work_count, params->global_seed, MCRT_INTERNAL_EMIT, nullptr, nullptr, nullptr, 1, 1.0, nullptr, stats);
+        ctx->emit_work_first = 0;
+        if (rc) { freeEmission(ctx); return rc; }
+        const Counters& c = ctx->h_counters[0];
+        ctx->emit_stored[0] = c.n_photons[0]; ctx->emit_stored[1] = c.n_photons[1];
+    }
+    else if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (caustic_dev) *caustic_dev = reinterpret_cast<const float*>(ctx->d_emit_photons[0]);
+    if (global_dev) *global_dev = reinterpret_cast<const float*>(ctx->d_emit_photons[1]);
+    if (n_caustic) *n_caustic = ctx->emit_stored[0];
+    if (n_global) *n_global = ctx->emit_stored[1];
+    return MCRT_OK;
+}
 
-    const Counters& c = ctx->h_counters[0];
-    const uint64_t n_stored[2] = { c.n_photons[0], c.n_photons[1] };
-    if (n_caustic) *n_caustic = n_stored[0];
-    if (n_global) *n_global = n_stored[1];
-    if (n_stored[0] >= 0xFFFFFFFFull || n_stored[1] >= 0xFFFFFFFFull) { cleanup(); ctx->error = "photon map with >= 2^32 photons unsupported"; return MCRT_ERR_UNSUPPORTED; }
-
-    // Octree<Photon> + LinearOctree::compact on the device, straight from the emission buffers into
+int mcrt_photon_build_dev(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, const float* caustic_dev, uint64_t n_caustic,
+                          const float* global_dev, uint64_t n_global, double* build_ms)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!params || params->max_photons_per_octree_leaf == 0 || params->k_nearest_photons == 0 || params->k_nearest_photons > 1024 ||
+        (n_caustic && !caustic_dev) || (n_global && !global_dev))
+    { ctx->error = "mcrt_photon_build_dev: invalid arguments"; return MCRT_ERR_INVALID; }
+    if (n_caustic >= 0xFFFFFFFFull || n_global >= 0xFFFFFFFFull) { ctx->error = "photon map with >= 2^32 photons unsupported"; return MCRT_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(ctx->device));
+    // Octree<Photon> + LinearOctree::compact on the device, straight from the photon arrays into
     // the layout k_knn walks: the photons never visit the host.
+    ctx->built_valid = false;
+    for (int w = 0; w < 2; w++) { ctx->built_dev[w] = PhotonOctreeDevice(); ctx->built_host_current[w] = false; ctx->photon_map[w] = DevicePhotonMap(); }
     freeAll(ctx->photon_allocs);
-    ctx->has_photons = false; ctx->built_valid = false;
+    ctx->has_photons = false;
     ctx->photon_build_ms = 0.0;
+    const float4* src[2] = { reinterpret_cast<const float4*>(caustic_dev), reinterpret_cast<const float4*>(global_dev) };
+    const uint64_t n[2] = { n_caustic, n_global };
     for (int w = 0; w < 2; w++)
     {
-        ctx->built_host_current[w] = false;
-        rc = buildPhotonOctreeOnDevice(ctx->d_emit_photons[w], (uint32_t)n_stored[w], params->scene_bounds, params->max_photons_per_octree_leaf,
-                                       ctx->sm_count, ctx->stream, ctx->photon_allocs, ctx->built_dev[w], ctx->error);
-        if (rc) { cleanup(); return rc; }
+        const int rc = buildPhotonOctreeOnDevice(src[w], (uint32_t)n[w], params->scene_bounds, params->max_photons_per_octree_leaf,
+                                                 ctx->sm_count, ctx->stream, ctx->photon_allocs, ctx->built_dev[w], ctx->error);
+        if (rc) return rc;
         ctx->photon_map[w].octants = ctx->built_dev[w].octants;
         ctx->photon_map[w].photons = ctx->built_dev[w].photons;
         ctx->photon_map[w].n_octants = ctx->built_dev[w].n_octants;
         ctx->photon_map[w].n_photons = ctx->built_dev[w].n_photons;
         ctx->photon_build_ms += ctx->built_dev[w].gpu_ms;
     }
-    cleanup();
     ctx->k_nearest = params->k_nearest_photons;
     ctx->direct_visualization = params->direct_visualization;
     ctx->has_photons = true;
     ctx->built_valid = true;
-    if (stats) stats->gpu_ms_knn = ctx->photon_build_ms;   // emission pass: this field reports the octree build
+    if (build_ms) *build_ms = ctx->photon_build_ms;
+    return MCRT_OK;
+}
+
+int mcrt_photon_emit(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, int precision, uint64_t* n_caustic,
+                     uint64_t* n_global, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    uint64_t total = 0;
+    int rc = mcrt_photon_emit_total(ctx, params, &total);
+    if (rc) return rc;
+    const float* raw[2] = { nullptr, nullptr };
+    uint64_t n[2] = { 0, 0 };
+    if ((rc = mcrt_photon_emit_range(ctx, params, precision, 0, total, &raw[0], &n[0], &raw[1], &n[1], stats))) return rc;
+    if (n_caustic) *n_caustic = n[0];
+    if (n_global) *n_global = n[1];
+    double build_ms = 0.0;
+    rc = mcrt_photon_build_dev(ctx, params, raw[0], n[0], raw[1], n[1], &build_ms);
+    freeEmission(ctx);
+    if (rc) return rc;
+    if (stats) stats->gpu_ms_knn = build_ms;   // emission pass: this field reports the octree build
     return MCRT_OK;
 }
 
@@ -1507,6 +1586,31 @@ int mcrt_render_rows_strided_peers(mcrt_ctx* ctx, const mcrt_camera* camera, uin
                                   static_cast<double*>(frames[0]), stats);
     ctx->peer_out.n_frames = 0;
     return rc;
+}
+
+int mcrt_render_film_sums_strided_dev(mcrt_ctx* ctx, const mcrt_camera* camera, uint32_t y_first, uint32_t y_step, uint32_t n_rows,
+                                      uint32_t sqrtspp, uint32_t global_seed, int integrator_kind, int precision,
+                                      double* rgb_sum_dev, double* weight_sum_dev, mcrt_stats* stats)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!rgb_sum_dev || !weight_sum_dev) { ctx->error = "null output"; return MCRT_ERR_INVALID; }
+    if (ctx->film_default) { ctx->error = "mcrt_render_film_sums_strided_dev is for reconstruction filters (mcrt_set_film); the default box film shards by rows directly"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->film_raw_rgb = rgb_sum_dev; ctx->film_raw_wsum = weight_sum_dev;
+    const int rc = renderDispatch(ctx, camera, y_first, y_step, n_rows, sqrtspp, global_seed, integrator_kind, precision, rgb_sum_dev, stats);
+    ctx->film_raw_rgb = nullptr; ctx->film_raw_wsum = nullptr;
+    return rc;
+}
+
+int mcrt_film_resolve_dev(mcrt_ctx* ctx, const double* rgb_sum_dev, const double* weight_sum_dev, uint64_t n_pixels, double* out_rgb_dev)
+{
+    if (!ctx) return MCRT_ERR_INVALID;
+    if (!rgb_sum_dev || !weight_sum_dev || !out_rgb_dev) { ctx->error = "null buffer"; return MCRT_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    launchResolveFilmWeighted(rgb_sum_dev, weight_sum_dev, out_rgb_dev, n_pixels, ctx->sm_count * ctx->blocks_per_sm, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return MCRT_OK;
 }
 
 int mcrt_frame_alloc(mcrt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64])

@@ -43,6 +43,9 @@
 #ifndef MCRT_TRACE_MINBLOCKS_DYN           // order-free search with dynamic fetch (measured on the spaceship: 64 registers beat 80)
 #define MCRT_TRACE_MINBLOCKS_DYN 4
 #endif
+#ifndef MCRT_KNN_MINBLOCKS                 // CTAs of 4 query warps per SM for k_knn
+#define MCRT_KNN_MINBLOCKS 8   // measured on water_caustics (B200): 4 -> 71, 6 -> 85, 8 -> 90 Mquery/s in-kernel (64 registers, spills and all)
+#endif
 #ifndef MCRT_SHADE_MINBLOCKS
 #define MCRT_SHADE_MINBLOCKS 3
 #endif
@@ -1031,7 +1034,7 @@ namespace mcrt
     // ------------------------------------------------------------------------------------------
     // k_knn: one warp per photon-map query emitted by k_shade<R,1>; search + radiance estimate.
     template <class R, int SLOTS, bool FILM, uint32_t FEATS>
-    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK, 4) k_knn(WaveParams<R> p)
+    __global__ void __launch_bounds__(32 * KNN_WARPS_PER_BLOCK, MCRT_KNN_MINBLOCKS) k_knn(WaveParams<R> p)
     {
         extern __shared__ __align__(16) unsigned char knn_smem[];
         const uint32_t n = min(p.counters->n_knn, p.pm.query_capacity);

@@ -80,3 +80,55 @@ class PeerFrames:
             dist.barrier()   # nobody frees a buffer a peer still maps
         self.integrator.frame_free(self.own)
         self.ptrs = []
+
+
+# ---- photon pass over several GPUs (photon-mapper.cpp:61-78)
+def emission_range(total, rank, world):
+    """Contiguous range of the emission index space [0, total) for `rank`: (first, count); remainder spread over the
+    first ranks. The index space is light-major (light 0's emissions, then light 1's, ...), so a range may span lights."""
+    base, rem = divmod(int(total), world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def device_view(ptr, n_elements, dtype, device):
+    """torch view (no copy) of `n_elements` of `dtype` at raw device address `ptr`."""
+    if n_elements == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device=device)
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1"}[dtype]
+    holder = type("DeviceMem", (), {"__cuda_array_interface__": {"shape": (int(n_elements),), "typestr": typestr, "data": (int(ptr), False), "version": 2}})()
+    return torch.as_tensor(holder, device=device)
+
+
+def all_gather_photons(mine, world, device=None):
+    """Concatenation, in rank order, of every rank's flat photon array (lengths differ per rank): one all-gather of the
+    lengths, one of the arrays padded to the longest."""
+    if world == 1:
+        return mine.contiguous()
+    n = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, n)
+    counts = counts.cpu().tolist()
+    longest = max(max(counts), 1)
+    padded = torch.zeros(longest, dtype=mine.dtype, device=device)
+    padded[:mine.numel()] = mine
+    out = torch.empty(world * longest, dtype=mine.dtype, device=device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * longest: r * longest + counts[r]] for r in range(world)]).contiguous()
+
+
+def render_filtered(integrator, camera, rank, world, device=None):
+    """A frame through the camera's reconstruction filter (mcrt_set_film) over `world` GPUs: every rank splats its
+    interleaved rows into whole-frame sums, the sums are all-reduced, every rank resolves. -> [H, W, 3] float64."""
+    H, W = camera.height, camera.width
+    rgb = torch.zeros((H, W, 3), dtype=torch.float64, device=device)
+    wsum = torch.zeros((H, W), dtype=torch.float64, device=device)
+    y_first, y_step, n_rows = interleaved_rows(rank, world, H)
+    integrator.render_film_sums_strided_dev(camera, rgb.data_ptr(), wsum.data_ptr(), y_first, y_step, n_rows)
+    if world > 1:
+        dist.all_reduce(rgb)
+        dist.all_reduce(wsum)
+    out = torch.empty_like(rgb)
+    torch.cuda.synchronize(device)
+    integrator.film_resolve_dev(rgb.data_ptr(), wsum.data_ptr(), H * W, out.data_ptr())
+    return out

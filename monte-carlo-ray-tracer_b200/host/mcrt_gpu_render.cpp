@@ -17,6 +17,8 @@
 #include "common/option.hpp"
 #include "scene/scene.hpp"
 
+#include "sampling/sampler.hpp"
+
 #include "gpu_integrator.hpp"
 
 int main(int argc, char* argv[])
@@ -28,6 +30,8 @@ int main(int argc, char* argv[])
     }
     try
     {
+        // the reference seeds its sampler from std::random_device (sampler.hpp:58); MCRT_SEED makes a run repeatable
+        if (const char* e = std::getenv("MCRT_SEED")) const_cast<uint32_t&>(Sampler::global_seed) = (uint32_t)std::strtoul(e, nullptr, 0);
         std::filesystem::path dir(argv[1]);
         Scene::path = dir;
         int camera_idx = argc > 3 ? std::atoi(argv[3]) : 0;

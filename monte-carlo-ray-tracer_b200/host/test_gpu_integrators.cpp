@@ -1,0 +1,91 @@
+// The substitution SURVEY.md 8(b) describes, executed: a reference Camera whose `integrator` (camera.cpp:22-29)
+// is a GpuPathTracer / GpuPhotonMapper, driven by the reference's own Camera::samplePixel - one
+// Integrator::sampleRay(Ray) call per sample - next to a second Camera with the reference's CPU integrator.
+// Prints the largest relative difference of Film::scan over the frame; exit code 0 iff within tolerance.
+// usage: test_gpu_integrators <scenes_dir> <scene.json> <photon_map 0|1> <width> <height> <sqrtspp> [emissions]
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include <nlohmann/json.hpp>
+
+#include "camera/camera.hpp"
+#include "common/option.hpp"
+#include "scene/scene.hpp"
+#include "sampling/sampler.hpp"
+
+#include "gpu_integrators.hpp"
+
+int main(int argc, char* argv[])
+{
+    if (argc < 7) { std::cerr << "usage: test_gpu_integrators <scenes_dir> <scene.json> <photon_map> <width> <height> <sqrtspp> [emissions]\n"; return 2; }
+    try
+    {
+        const std::filesystem::path dir(argv[1]);
+        Scene::path = dir;
+        const bool photon_map = std::atoi(argv[3]) != 0;
+        std::ifstream in(dir / argv[2]);
+        nlohmann::json j;
+        in >> j;
+        j["num_render_threads"] = 1;           // the CPU photon pass stores photons in emission order only with one thread
+        auto& cam_json = j.at("cameras").at(0);
+        cam_json["image"]["width"] = std::atoi(argv[4]);
+        cam_json["image"]["height"] = std::atoi(argv[5]);
+        cam_json["sqrtspp"] = std::atoi(argv[6]);
+        if (photon_map && argc > 7) j["photon_map"]["emissions"] = std::atof(argv[7]);
+
+        // the sampler sanity check of the adapter: (pixel, sample) read back from the thread_local state
+        for (uint32_t pixel : { 0u, 1u, 77777u, 0xFFFFFFFFu })
+            for (uint32_t sample : { 0u, 5u, 255u, 65535u })
+            {
+                Sampler::initiate(pixel); Sampler::setIndex(sample);
+                uint32_t p2, s2;
+                mcrt_host::currentSamplerPixelAndSample(p2, s2);
+                if (p2 != pixel || s2 != sample) { std::cerr << "sampler state not recovered: " << pixel << "," << sample << " -> " << p2 << "," << s2 << "\n"; return 1; }
+            }
+
+        Option option(dir / argv[2], "", 0, photon_map);
+        Camera reference(j, option);                         // PathTracer / PhotonMapper on the CPU
+        Camera substituted(j, Option(dir / argv[2], "", 0, false));
+        if (photon_map) substituted.integrator = std::make_shared<GpuPhotonMapper>(j);
+        else substituted.integrator = std::make_shared<GpuPathTracer>(j);
+
+        const size_t W = reference.image.width, H = reference.image.height;
+        double worst = 0.0, mean = 0.0;
+        for (size_t y = 0; y < H; y++)
+            for (size_t x = 0; x < W; x++)
+            {
+                reference.samplePixel(x, y);                 // reference loop body, CPU integrator
+                substituted.samplePixel(x, y);               // same loop body, GPU integrator behind Integrator::sampleRay
+                const glm::dvec3 a = reference.film.scan(x, y), b = substituted.film.scan(x, y);
+                for (int c = 0; c < 3; c++)
+                {
+                    worst = std::max(worst, std::abs(a[c] - b[c]) / std::max(1.0, std::abs(a[c])));
+                    mean += a[c];
+                }
+            }
+        mean /= double(3 * W * H);
+        const double tol = photon_map ? 1e-6 : 1e-9;
+        std::cout << (photon_map ? "GpuPhotonMapper" : "GpuPathTracer") << " behind Integrator::sampleRay: " << W << "x" << H << " x "
+                  << reference.sqrtspp * reference.sqrtspp << " spp, mean " << mean << ", worst relative difference " << worst
+                  << (worst <= tol ? " OK" : " MISMATCH") << std::endl;
+        // the batched form gives the same rows
+        auto* gpu = dynamic_cast<GpuPathTracer*>(substituted.integrator.get());
+        const std::vector<double> rows = gpu->sampleRows(substituted, 0, (uint32_t)H);
+        double worst_rows = 0.0;
+        for (size_t y = 0; y < H; y++)
+            for (size_t x = 0; x < W; x++)
+            {
+                const glm::dvec3 a = reference.film.scan(x, y);
+                for (int c = 0; c < 3; c++) worst_rows = std::max(worst_rows, std::abs(a[c] - rows[(y * W + x) * 3 + c]) / std::max(1.0, std::abs(a[c])));
+            }
+        std::cout << "sampleRows (batched): worst relative difference " << worst_rows << (worst_rows <= tol ? " OK" : " MISMATCH") << std::endl;
+        return worst <= tol && worst_rows <= tol ? 0 : 1;
+    }
+    catch (const std::exception& e)
+    {
+        std::cerr << "error: " << e.what() << std::endl;
+        return 1;
+    }
+}
