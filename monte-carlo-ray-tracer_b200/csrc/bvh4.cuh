@@ -108,7 +108,13 @@ namespace mcrt
 
     // The search as a resumable state: begin(), then step() until it returns false. One step = walk down
     // through inner nodes to the next leaf, test its primitives, pop the next pending subtree.
-    template <int PRIMS> struct FastSearch
+    // OCC (occlusion query of next-event estimation, integrator.cpp:68-86): the caller only needs to know
+    // whether `target` (the sampled light primitive) is the closest hit. The target is tested directly -
+    // same float64 test, same t as the reference computes for it - and the tree is searched only for
+    // something *in front* of it: the limit is known from the start and the search stops at the first
+    // occluder. A hit within delta of the target's t (either side) is a tie the reference's visiting order
+    // decides: such rays are replayed like ambiguous closest hits.
+    template <int PRIMS, bool OCC = false> struct FastSearch
     {
         Hit<double> best;
         double second_t;       // second-smallest hit distance seen (competitor of best.t)
@@ -117,6 +123,24 @@ namespace mcrt
         uint32_t cur;          // node index or leaf reference being visited
         FastRay fr;
         uint2 stack[FAST_STACK];   // (child reference, lower bound of its entry distance as float bits)
+        uint32_t target;       // OCC: the primitive whose visibility is asked
+        uint32_t verdict;      // OCC: 0 target visible so far, 1 occluded, 2 tie -> replay
+
+        // -> false: the ray does not hit the target at all (nothing to search)
+        MCRT_D bool beginOcclusion(const DeviceScene<double>& sc, const RayQ<double>& ray, uint32_t target_prim, TraceCounters& cnt)
+        {
+            best.u = 0.0; best.v = 0.0; best.interpolate = 0; best.prim = NO_PRIM; best.t = Consts<double>::MAXV;
+            second_t = Consts<double>::MAXV;
+            target = target_prim; verdict = 0u;
+            sp = 0; cur = 0;
+            double t, u, v;
+            cnt.prim_tests++;
+            if (!intersectPrim<PRIMS>(sc, target_prim, ray, t, u, v)) return false;
+            best.t = t; best.u = u; best.v = v; best.prim = target_prim;
+            limit = __double2float_ru(t + 2.0 * ambiguityDelta(t, (double)sc.scene_scale));
+            fr = makeFastRay(ray.o, ray.d);
+            return true;
+        }
 
         MCRT_D void begin(const RayQ<double>& ray)
         {
@@ -188,6 +212,17 @@ namespace mcrt
                 for (uint32_t i = first; i < first + count; i++)
                 {
                     double t, u, v;
+                    if constexpr (OCC)
+                    {
+                        if (i == target) continue;
+                        if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
+                        {
+                            const double delta = ambiguityDelta(best.t, (double)sc.scene_scale);
+                            if (t < best.t - delta) { verdict = 1u; cnt.prim_tests += i - first + 1; return false; }   // occluder: done
+                            if (t <= best.t + delta) { verdict = 2u; cnt.prim_tests += i - first + 1; return false; }  // tie: replay
+                        }
+                        continue;
+                    }
                     if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
                     {
                         if (t < best.t)
@@ -247,11 +282,13 @@ namespace mcrt
 #ifndef MCRT_FETCH_THRESHOLD
 #define MCRT_FETCH_THRESHOLD 22
 #endif
-    template <int PRIMS, class Load, class Done>
+    // OCC: load(ii, ray, target) also names the primitive whose visibility is asked; done() gets a hit whose
+    // prim is the target iff it is the closest hit
+    template <int PRIMS, bool OCC = false, class Load, class Done>
     MCRT_D void traceManyFast(const DeviceScene<double>& sc, uint32_t n, uint32_t* fetch_counter, Load load, Done done,
                               TraceCounters& cnt, uint32_t& overflow)
     {
-        FastSearch<PRIMS> fs;
+        FastSearch<PRIMS, OCC> fs;
         RayQ<double> ray;
         uint32_t item = 0;
         bool active = false;
@@ -270,9 +307,19 @@ namespace mcrt
                     const uint32_t ii = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
                     if (ii < n)
                     {
-                        item = load(ii, ray);
-                        fs.begin(ray);
-                        active = true;
+                        if constexpr (OCC)
+                        {
+                            uint32_t target;
+                            item = load(ii, ray, target);
+                            if (fs.beginOcclusion(sc, ray, target, cnt)) active = true;
+                            else { Hit<double> miss = fs.best; miss.prim = NO_PRIM; done(item, ray, miss); }   // the ray misses the light itself
+                        }
+                        else
+                        {
+                            item = load(ii, ray);
+                            fs.begin(ray);
+                            active = true;
+                        }
                     }
                 }
             }
@@ -282,7 +329,10 @@ namespace mcrt
                 if (!fs.step(sc, ray, cnt, overflow))
                 {
                     Hit<double> h = fs.best;
-                    if (fs.ambiguous(sc))
+                    bool replay;
+                    if constexpr (OCC) { replay = fs.verdict == 2u; if (fs.verdict == 1u) h.prim = NO_PRIM; }
+                    else replay = fs.ambiguous(sc);
+                    if (replay)
                     {
                         const DeviceScene<double> sc_copy = sc;
                         RayQ<double> rq_copy = ray;

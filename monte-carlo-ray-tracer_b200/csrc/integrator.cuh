@@ -288,6 +288,33 @@ namespace mcrt
         }
     }
 
+    // Occlusion query of next-event estimation for the order-free search (parity mode): the hit returned has
+    // prim == target iff the target is what Scene::intersect would return (bvh4.cuh, FastSearch<PRIMS, true>)
+    template <int PRIMS>
+    MCRT_D Hit<double> traceVisible(const DeviceScene<double>& sc, const V3<double>& o, const V3<double>& d, uint32_t target,
+                                    TraceCounters& cnt, uint32_t& overflow)
+    {
+        RayQ<double> rq;
+        rq.o = o; rq.d = d;
+        if constexpr (PRIMS == PRIMS_ALL) rq.inv_d = 1.0 / d;
+        FastSearch<PRIMS, true> fs;
+        if (!fs.beginOcclusion(sc, rq, target, cnt)) { Hit<double> miss = fs.best; miss.prim = NO_PRIM; return miss; }
+        while (fs.step(sc, rq, cnt, overflow)) { }
+        Hit<double> h = fs.best;
+        if (fs.verdict == 1u) h.prim = NO_PRIM;
+        else if (fs.verdict == 2u)
+        {
+            const DeviceScene<double> sc_copy = sc;
+            RayQ<double> rq_copy = rq;
+            rq_copy.inv_d = 1.0 / d;
+            Hit<double> h2;
+            traceReferenceOrderOutOfLine<PRIMS>(&sc_copy, &rq_copy, &h2, &cnt.box_tests, &cnt.prim_tests, &overflow);
+            h = h2;
+            cnt.replayed++;
+        }
+        return h;
+    }
+
     MCRT_D void filmAdd(double* film, uint32_t index, double r, double g, double b)
     {
         if (r != 0.0) atomicAdd(&film[3 * (size_t)index + 0], r);
@@ -886,13 +913,14 @@ namespace mcrt
         const uint32_t* order = p.sort.shadow_order;
         if constexpr (Mode<R>::parity && FAST == 2)
         {
-            traceManyFast<PRIMS>(p.scene, n, &p.counters->fetch_shadow,
-                [&](uint32_t ii, RayQ<R>& r)
+            traceManyFast<PRIMS, true>(p.scene, n, &p.counters->fetch_shadow,
+                [&](uint32_t ii, RayQ<R>& r, uint32_t& target)
                 {
                     const uint32_t i = order ? order[ii] : ii;
                     const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
                     r.o = so.xyz(); r.d = sd.xyz();
                     if constexpr (PRIMS == PRIMS_ALL) r.inv_d = R(1) / r.d;
+                    target = p.shadow.meta[i].x;
                     return i;
                 },
                 [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
@@ -915,7 +943,9 @@ namespace mcrt
             const uint32_t i = order ? order[ii] : ii;
             const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
             const uint4 sm = p.shadow.meta[i];
-            Hit<R> h = traceClosest<PRIMS, FAST != 0>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
+            Hit<R> h;
+            if constexpr (Mode<R>::parity && FAST != 0) h = traceVisible<PRIMS>(p.scene, so.xyz(), sd.xyz(), sm.x, cnt, overflow);
+            else h = traceClosest<PRIMS, false>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
             rays++;
             // integrator.cpp:70-86: visible iff the closest hit is that very light primitive
             if (h.prim == sm.x)

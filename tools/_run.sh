@@ -1,7 +1,12 @@
 mkdir -p gpurun_out
-nvidia-smi -L
-echo "== multi_gpu_check world=2"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py 2>&1 | tail -8
-echo "== bench N=2"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2_bench_c2_n2.json 2> gpurun_out/r2_bench_c2_n2.err
-tail -c 3000 gpurun_out/r2_bench_c2_n2.json; tail -5 gpurun_out/r2_bench_c2_n2.err
+rm -f gpurun_out/probe_fast.jsonl
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+C2="bench_data/c2_hexagon_room.mcrtpack --sqrtspp 8"
+V3="bench_data/v3_spaceship.mcrtpack.xz --width 1920 --height 1080 --sqrtspp 6"
+timeout 300 python tools/probe_fast.py $C2 --tag c2_occ 2>&1 | grep -E "render|fast vs"
+timeout 400 python tools/probe_fast.py $V3 --tag v3_occ 2>&1 | grep -E "render|fast vs"
+for v in _s5 _s6; do
+  export MCRT_LIB=$PWD/monte-carlo-ray-tracer_b200/libmcrt_b200$v.so
+  echo "== variant $v"
+  timeout 300 python tools/probe_fast.py $C2 --tag "c2$v" --skip-exact-render --skip-trace 2>&1 | grep -E "render"
+done
