@@ -53,6 +53,11 @@ WORKLOADS = {
     "c3": ("bench_data/v3_spaceship.mcrtpack.xz", "spaceship.json",
            dict(width=1920, height=1080, sqrtspp=32),
            "spaceship.json 1920x1080 1024spp quaternary_sah"),
+    # photon-mapped (PhotonMapper::sampleRay): the photon pass (1e6 emissions x caustic_factor 10, all on the GPU) runs
+    # once before the timed steps; sqrtspp 23 = 529 spp, the nearest square to the 512 spp of BASELINE config 4
+    "c4": ("bench_data/v4_water_caustics.mcrtpack.xz", "water_caustics.json",
+           dict(width=1024, height=1024, sqrtspp=23, photon_map=dict(emissions=1e6, caustic_factor=10.0, k_nearest_photons=50)),
+           "water_caustics.json 1024x1024 529spp photon_map 1e6 emissions k=50"),
     "c5": ("bench_data/v5_lego_bulldozer.mcrtpack.xz", "lego_bulldozer.json",
            dict(width=3840, height=2160, sqrtspp=64),
            "lego_bulldozer.json 3840x2160 4096spp quaternary_sah"),
@@ -132,7 +137,11 @@ def reference_sample(workload, seconds_target, threads=-1):
     from oracle import ref
     _, scene_json, overrides, _ = WORKLOADS[workload]
     ref.set_seed(0x12345678)
-    cal = ref.RefScene(scene_json, dict(overrides, sqrtspp=1))
+    photon = overrides.get("photon_map")
+    overrides = {k: v for k, v in overrides.items() if k != "photon_map"}
+    if photon:
+        overrides = dict(overrides, emissions=photon["emissions"])
+    cal = ref.RefScene(scene_json, dict(overrides, sqrtspp=1), photon_map=bool(photon))
     hw = ref.lib().ref_hardware_threads()
     # The reference takes its thread count from std::thread::hardware_concurrency (integrator.cpp:20-23).
     # On hosts where that exceeds the cores this container may use it oversubscribes badly, so the
@@ -146,7 +155,7 @@ def reference_sample(workload, seconds_target, threads=-1):
     cal.close()
     cores, rate, rays = best
     k = int(max(1, min(overrides["sqrtspp"], round((seconds_target * rate / max(rays, 1)) ** 0.5))))
-    s = ref.RefScene(scene_json, dict(overrides, sqrtspp=k))
+    s = ref.RefScene(scene_json, dict(overrides, sqrtspp=k), photon_map=bool(photon))
     s.best_threads = cores
     return s, cores, k
 
@@ -192,7 +201,14 @@ def child_render(args):
     pack, _, ov, _ = WORKLOADS[args.workload]
     scene = m.Scene.from_pack(os.path.join(ROOT, pack))
     cam = scene.cameras()[0].resized(ov["width"], ov["height"], args.sqrtspp or 2)
-    pt = m.PathTracer(scene, device=0, precision=m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32, global_seed=0x12345678)
+    prec = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32
+    if ov.get("photon_map"):
+        pe = scene.extra["photon_emit_params"]; ph = ov["photon_map"]
+        pt = m.PhotonMapper(scene, device=0, precision=prec, global_seed=0x12345678,
+                            emit=dict(emissions=int(ph["emissions"]), caustic_factor=ph["caustic_factor"], max_photons_per_octree_leaf=int(pe[2]),
+                                      k_nearest_photons=ph["k_nearest_photons"], scene_bounds=pe[3:9]))
+    else:
+        pt = m.PathTracer(scene, device=0, precision=prec, global_seed=0x12345678)
     pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))
     import torch
     out = torch.zeros((cam.height, cam.width, 3), dtype=torch.float64, device="cuda:0")
@@ -270,7 +286,21 @@ def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True
     scene = m.Scene.from_pack(os.path.join(ROOT, pack))
     cam = scene.cameras()[0].resized(ov["width"], ov["height"], sqrtspp_override or ov["sqrtspp"])
     precision = m.PRECISION_F64 if args.precision == "f64" else m.PRECISION_F32
-    pt = m.PathTracer(scene, device=local_rank, precision=precision, global_seed=0x12345678)
+    photon = ov.get("photon_map")
+    photon_pass = None
+    if photon:
+        pe = scene.extra["photon_emit_params"]
+        pt = m.PhotonMapper(scene, device=local_rank, precision=precision, global_seed=0x12345678)   # maps of the pack: replaced below
+        kw = dict(emissions=int(photon["emissions"]), caustic_factor=photon["caustic_factor"], max_photons_per_octree_leaf=int(pe[2]),
+                  k_nearest_photons=photon["k_nearest_photons"], scene_bounds=pe[3:9])
+        t0 = time.perf_counter()
+        n_c, n_g = pt.emit_sharded(rank, world, **kw) if world > 1 else pt.emit(**kw)
+        torch.cuda.synchronize()
+        photon_pass = {"emission_gpu_ms": pt.last_stats["gpu_ms_total"], "octree_build_gpu_ms": pt.last_stats["gpu_ms_knn"],
+                       "photon_rays": pt.last_stats["extension_rays"], "caustic_photons": int(n_c), "global_photons": int(n_g),
+                       "wall_s": time.perf_counter() - t0, "sharded_over": world}
+    else:
+        pt = m.PathTracer(scene, device=local_rank, precision=precision, global_seed=0x12345678)
     pt.set_option("pool_paths", args.pool if args.pool else float(1 << 24))   # 16 Mi paths in flight (6.5 GB of HBM)
     pt.set_option("stage_timing", 1)
     W, H = cam.width, cam.height
@@ -322,15 +352,16 @@ def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True
             host32.copy_(frame_t, non_blocking=False)
         return h2d, st
 
-    e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_rays = 0
-    for _ in range(e2e_steps):
-        h2d_bytes, st = e2e_step()
-        e2e_rays += st["extension_rays"] + st["shadow_rays"]
-    sync_all()
-    e2e_wall = time.perf_counter() - t0
+    h2d_bytes, e2e_rays, e2e_wall = 0, 0, 0.0
+    if not args.no_e2e:
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h2d_bytes, st = e2e_step()
+            e2e_rays += st["extension_rays"] + st["shadow_rays"]
+        sync_all()
+        e2e_wall = time.perf_counter() - t0
     d2h_bytes = H * W * 3 * (8 if world == 1 else 4)
 
     def allreduce(x, op):
@@ -362,6 +393,8 @@ def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True
     shade_ms = sum(s["gpu_ms_shade"] for s in stats)
     gen_ms = sum(s["gpu_ms_generate"] for s in stats)
     replayed = sum(s["replayed_rays"] for s in stats)
+    knn_queries = sum(s["knn_queries"] for s in stats)
+    knn_ms = sum(s["gpu_ms_knn"] for s in stats)
     pt.close()
     frames_bytes = frames.nbytes
     # (the frames stay mapped until the process ends: closing them needs another barrier and buys nothing here)
@@ -413,7 +446,7 @@ def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True
                    "mode": "parity (float64 primitive tests and shading in the reference's operation order, --fmad=false)" if args.precision == "f64" else "fast (float32)"},
         "wall_ms_per_step": 1e3 * wall_max / steps,
         "rank_imbalance": {"max_over_mean_gpu_ms": dev_ms_max / max(1e-9, dev_ms_mean)},
-        "e2e": {"value": e2e_rays_total / e2e_wall_max / 1e6, "unit": "Mray/s",
+        "e2e": {"value": (e2e_rays_total / e2e_wall_max / 1e6) if e2e_wall_max > 0 else None, "unit": "Mray/s",
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "steps": e2e_steps, "timing": "wall clock between synchronisations, max over ranks"},
         "gpu_launches": int(launches),
@@ -424,6 +457,11 @@ def measure(env, args, workload, steps, warmup, sqrtspp_override=0, profile=True
                  "box_tests_per_ray": (ext_box) / max(1, ext_rays), "prim_tests_per_ray": ext_prim / max(1, ext_rays)},
         "kernels": {k: v for k, v in prof.items() if k != "k_extend"} if isinstance(prof, dict) else None,
     }
+    if photon:
+        result["photon_pass"] = photon_pass
+        result["knn"] = {"queries_per_step": knn_queries / steps, "mquery_per_s_in_kernel": knn_queries / max(1e-9, knn_ms) / 1e3,
+                         "mquery_per_s_whole_step": knn_queries / (dev_ms * 1e-3) / 1e6, "k_knn_ms_per_step": knn_ms / steps,
+                         "algorithmic_bytes_per_query": 12400, "hbm_frac_algorithmic": 12400.0 * knn_queries / max(1e-9, knn_ms * 1e-3) / 1e9 / peak}
     return result
 
 
@@ -489,6 +527,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the ncu epilogue (measured DRAM traffic / FP64 counts)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the spaceship block")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (long single-purpose runs only)")
     ap.add_argument("--child-render", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--baseline-seconds", type=float, default=0.0, help="reference arm: target seconds per step")
     args = ap.parse_args()

@@ -768,6 +768,7 @@ namespace
         init.total_work = total_work;
         if (integrator == MCRT_INTERNAL_EMIT) { init.next_work = ctx->emit_work_first; init.total_work = ctx->emit_work_first + total_work; }
         ctx->h_counters[0] = init;
+        CK(cudaEventRecord(ctx->ev_start, s));   // the timed region includes the counter upload and the film / histogram memsets
         CK(cudaMemcpyAsync(ctx->d_counters, &ctx->h_counters[0], sizeof(Counters), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ctx->d_film, 0, film_pixels * 3 * sizeof(double), s));
         if (filtered) CK(cudaMemsetAsync(ctx->d_film_wsum, 0, film_pixels * sizeof(double), s));
@@ -785,7 +786,6 @@ namespace
                               &ctx->d_counters->n_cur, grid, s);
         };
 
-        CK(cudaEventRecord(ctx->ev_start, s));
         uint64_t launches = 0, iterations = 0;
 
         if (emitting) Launch<R>::emitGenerate(p, 0, grid, s);

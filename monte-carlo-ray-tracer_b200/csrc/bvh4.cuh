@@ -32,12 +32,21 @@
 #ifndef MCRT_FAST_STACK
 #define MCRT_FAST_STACK 40
 #endif
+#ifndef MCRT_FAST_SMEM_STACK          // entries of the search stack kept in shared memory (per thread); the rest is local memory.
+#define MCRT_FAST_SMEM_STACK 0       // Measured on the B200 (profiles/r2_stream_stack_ab.txt): 12 entries in shared memory are 4-5 % SLOWER than
+#endif                               // the all-local stack on the hexagon room, the spaceship and the bulldozer alike (the L1 keeps the hot top of the
+                                     // local stacks, and the shared-memory form adds address arithmetic and a branch per push / pop). Kept as a knob.
 
 namespace mcrt
 {
     constexpr uint32_t BVH4_LEAF = 0x80000000u;
     constexpr uint32_t BVH4_MAX_PRIMS = 1u << 23;     // leaf reference: 23 bits first primitive, 8 bits count
     constexpr int FAST_STACK = MCRT_FAST_STACK;
+    constexpr int FAST_SMEM_STACK = MCRT_FAST_SMEM_STACK;
+    constexpr int FAST_LOCAL_STACK = FAST_STACK - FAST_SMEM_STACK;
+    // dynamic shared memory of a kernel that runs the search: FAST_SMEM_STACK entries of 8 bytes per thread, entry e of
+    // thread t at [e * blockDim.x + t] (conflict-free); 0 by default (see above)
+    inline size_t fastStackSharedBytes(int block_threads) { return (size_t)FAST_SMEM_STACK * block_threads * sizeof(uint2); }
 
     // children c = 0..3: box [lo[k][c], hi[k][c]] on axis k; child[c] = 0 (empty), inner node index
     // (>= 1: the root is node 0 and nobody's child) or BVH4_LEAF | first_prim << 8 | count
@@ -122,7 +131,8 @@ namespace mcrt
         int sp;
         uint32_t cur;          // node index or leaf reference being visited
         FastRay fr;
-        uint2 stack[FAST_STACK];   // (child reference, lower bound of its entry distance as float bits)
+        uint2 lstack[FAST_LOCAL_STACK > 0 ? FAST_LOCAL_STACK : 1];   // (child reference, lower bound of its entry distance as float bits)
+        uint2* sstack;         // this thread's column of the shared-memory part of the stack
         uint32_t target;       // OCC: the primitive whose visibility is asked
         uint32_t verdict;      // OCC: 0 target visible so far, 1 occluded, 2 tie -> replay
 
@@ -133,6 +143,7 @@ namespace mcrt
             second_t = Consts<double>::MAXV;
             target = target_prim; verdict = 0u;
             sp = 0; cur = 0;
+            attach();
             double t, u, v;
             cnt.prim_tests++;
             if (!intersectPrim<PRIMS>(sc, target_prim, ray, t, u, v)) return false;
@@ -149,14 +160,30 @@ namespace mcrt
             limit = __int_as_float(0x7f800000);   // +inf until something is hit
             sp = 0;
             cur = 0;                              // node 0 = root
+            attach();
             fr = makeFastRay(ray.o, ray.d);
+        }
+
+        MCRT_D void attach()
+        {
+            extern __shared__ uint2 fast_stack_smem[];
+            sstack = fast_stack_smem + threadIdx.x;
+        }
+
+        MCRT_D void push(uint32_t ref, uint32_t tn_bits, uint32_t& overflow)
+        {
+            if (sp < FAST_SMEM_STACK) sstack[sp * blockDim.x] = make_uint2(ref, tn_bits);
+            else if (sp < FAST_STACK) lstack[sp - FAST_SMEM_STACK] = make_uint2(ref, tn_bits);
+            else { overflow = 1; return; }
+            sp++;
         }
 
         MCRT_D bool pop()
         {
             while (sp > 0)
             {
-                const uint2 e = stack[--sp];
+                --sp;
+                const uint2 e = sp < FAST_SMEM_STACK ? sstack[sp * blockDim.x] : lstack[sp - FAST_SMEM_STACK];
                 if (__uint_as_float(e.y) <= limit) { cur = e.x; return true; }
             }
             return false;
@@ -202,9 +229,9 @@ namespace mcrt
                     continue;
                 }
                 // far children first, so the nearest pending one is on top
-                if (key3 != 0xFFFFFFFFu) { if (sp < FAST_STACK) stack[sp++] = make_uint2(refOf(key3), key3 & ~3u); else overflow = 1; }
-                if (key2 != 0xFFFFFFFFu) { if (sp < FAST_STACK) stack[sp++] = make_uint2(refOf(key2), key2 & ~3u); else overflow = 1; }
-                if (key1 != 0xFFFFFFFFu) { if (sp < FAST_STACK) stack[sp++] = make_uint2(refOf(key1), key1 & ~3u); else overflow = 1; }
+                if (key3 != 0xFFFFFFFFu) push(refOf(key3), key3 & ~3u, overflow);
+                if (key2 != 0xFFFFFFFFu) push(refOf(key2), key2 & ~3u, overflow);
+                if (key1 != 0xFFFFFFFFu) push(refOf(key1), key1 & ~3u, overflow);
                 cur = refOf(key0);
             }
             {

@@ -464,11 +464,11 @@ namespace mcrt
                 cameraRay(p.camera, p.scene.scene_ior, pixel, smp, start, direction);
                 if constexpr (FILM) filmSplatSampleWeight(p.filmp, p.global_seed, pixel, sample);
             }
-            out.ray_o[slot] = V4<R>(start, p.scene.scene_ior);
-            out.ray_d[slot] = V4<R>(direction, R(1));
-            out.thr[slot] = V4<R>(R(1), R(1), R(1), R(0));
-            out.meta[slot] = make_uint4(pixel, sample, 0u, 0u);
-            out.meta2[slot] = make_uint4(NO_PRIM, 1u, film_index, NO_PRIM);
+            stStream(&out.ray_o[slot], V4<R>(start, p.scene.scene_ior));
+            stStream(&out.ray_d[slot], V4<R>(direction, R(1)));
+            stStream(&out.thr[slot], V4<R>(R(1), R(1), R(1), R(0)));
+            stStream(&out.meta[slot], make_uint4(pixel, sample, 0u, 0u));
+            stStream(&out.meta2[slot], make_uint4(NO_PRIM, 1u, film_index, NO_PRIM));
             if (p.sort.path_order) key = rayKey(p.sort, start, direction, NO_PRIM);
             }
             if (p.sort.path_order)
@@ -509,14 +509,14 @@ namespace mcrt
                 [&](uint32_t ii, RayQ<R>& r)
                 {
                     const uint32_t i = order ? order[ii] : ii;
-                    const V4<R> ro = in.ray_o[i], rd = in.ray_d[i];
+                    const V4<R> ro = ldStream(&in.ray_o[i]), rd = ldStream(&in.ray_d[i]);
                     r.o = ro.xyz(); r.d = rd.xyz();
                     if constexpr (PRIMS == PRIMS_ALL) r.inv_d = R(1) / r.d;   // quadric clip-box test
                     return i;
                 },
                 [&](uint32_t i, const RayQ<R>&, const Hit<R>& h)
                 {
-                    p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
+                    stStream(&p.hits[i], V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim)));
                     rays++;
                 }, cnt, overflow);
             flushStats(p.counters, cnt, rays, false, overflow);
@@ -525,15 +525,15 @@ namespace mcrt
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
             const uint32_t i = order ? order[ii] : ii;
-            const V4<R> ro = in.ray_o[i];
-            const V4<R> rd = in.ray_d[i];
+            const V4<R> ro = ldStream(&in.ray_o[i]);
+            const V4<R> rd = ldStream(&in.ray_d[i]);
             uint32_t skip = NO_PRIM;
             if constexpr (!Mode<R>::parity) skip = in.meta2[i].w;
 #ifdef MCRT_TAIL_DIAGNOSTIC
             const uint32_t w0 = cnt.box_tests + cnt.prim_tests;
 #endif
             Hit<R> h = traceClosest<PRIMS, FAST != 0>(p.scene, ro.xyz(), rd.xyz(), skip, cnt, overflow);
-            p.hits[i] = V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim));
+            stStream(&p.hits[i], V4<R>(h.t, h.u, h.v, h.prim == NO_PRIM ? R(-1) : R(h.prim)));
             rays++;
 #ifdef MCRT_TAIL_DIAGNOSTIC
             // tuning builds only: how much of the warp's time (~ its slowest ray) the average ray uses
@@ -627,8 +627,8 @@ namespace mcrt
 
             if (alive)
             {
-                const V4<R> ro = in.ray_o[i], rd = in.ray_d[i], th = in.thr[i], hv = p.hits[i];
-                meta = in.meta[i]; meta2 = in.meta2[i];
+                const V4<R> ro = ldStream(&in.ray_o[i]), rd = ldStream(&in.ray_d[i]), th = ldStream(&in.thr[i]), hv = ldStream(&p.hits[i]);
+                meta = ldStream(&in.meta[i]); meta2 = ldStream(&in.meta2[i]);
                 ray.start = ro.xyz(); ray.medium_ior = ro.w;
                 ray.direction = rd.xyz(); ray.refraction_scale = rd.w;
                 throughput = th.xyz(); ls_bsdf_pdf = th.w;
@@ -861,27 +861,27 @@ namespace mcrt
             }
             if (alive)
             {
-                out.ray_o[slot] = V4<R>(nray.start, nray.medium_ior);
-                out.ray_d[slot] = V4<R>(nray.direction, nray.refraction_scale);
-                out.thr[slot] = V4<R>(throughput, ls_bsdf_pdf);
+                stStream(&out.ray_o[slot], V4<R>(nray.start, nray.medium_ior));
+                stStream(&out.ray_d[slot], V4<R>(nray.direction, nray.refraction_scale));
+                stStream(&out.thr[slot], V4<R>(throughput, ls_bsdf_pdf));
                 if (ior_count > 1)
                 {
                     out.iors_a[slot] = V4<R>(iors[1], iors[2], iors[3], iors[4]);
                     if (ior_count > 5) out.iors_b[slot] = V4<R>(iors[5], iors[6], iors[7], R(0));
                 }
-                out.meta[slot] = make_uint4(meta.x, meta.y, (nray.depth & 0xFFFFu) | (nray.diffuse_depth << 16),
-                                            (uint32_t)nray.refraction_level);
-                out.meta2[slot] = make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
-                                             sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM);
+                stStream(&out.meta[slot], make_uint4(meta.x, meta.y, (nray.depth & 0xFFFFu) | (nray.diffuse_depth << 16),
+                                                     (uint32_t)nray.refraction_level));
+                stStream(&out.meta2[slot], make_uint4(ls_light, ior_count | (nray.dirac_delta ? 256u : 0u), meta2.z,
+                                                      sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM));
                 if (sorting) { p.sort.path_key[cur ^ 1][slot] = pkey; p.sort.path_rank[cur ^ 1][slot] = prank; }
             }
             if (want_shadow)
             {
-                p.shadow.o[sslot] = V4<R>(sh_o, sh_bsdf_pdf);
-                p.shadow.d[sslot] = V4<R>(sh_d, sh_area_cos);
-                p.shadow.k[sslot] = V4<R>(sh_k, sh_select);
-                p.shadow.meta[sslot] = make_uint4(sh_light, meta2.z,
-                                                  sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, meta.y);
+                stStream(&p.shadow.o[sslot], V4<R>(sh_o, sh_bsdf_pdf));
+                stStream(&p.shadow.d[sslot], V4<R>(sh_d, sh_area_cos));
+                stStream(&p.shadow.k[sslot], V4<R>(sh_k, sh_select));
+                stStream(&p.shadow.meta[sslot], make_uint4(sh_light, meta2.z,
+                                                           sc.shade[hit_prim].type == PRIM_TRIANGLE ? hit_prim : NO_PRIM, meta.y));
                 if (sorting) { p.sort.shadow_key[sslot] = skey; p.sort.shadow_rank[sslot] = srank; }
             }
 
@@ -917,7 +917,7 @@ namespace mcrt
                 [&](uint32_t ii, RayQ<R>& r, uint32_t& target)
                 {
                     const uint32_t i = order ? order[ii] : ii;
-                    const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
+                    const V4<R> so = ldStream(&p.shadow.o[i]), sd = ldStream(&p.shadow.d[i]);
                     r.o = so.xyz(); r.d = sd.xyz();
                     if constexpr (PRIMS == PRIMS_ALL) r.inv_d = R(1) / r.d;
                     target = p.shadow.meta[i].x;
@@ -941,8 +941,8 @@ namespace mcrt
         for (uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x; ii < n; ii += gridDim.x * blockDim.x)
         {
             const uint32_t i = order ? order[ii] : ii;
-            const V4<R> so = p.shadow.o[i], sd = p.shadow.d[i];
-            const uint4 sm = p.shadow.meta[i];
+            const V4<R> so = ldStream(&p.shadow.o[i]), sd = ldStream(&p.shadow.d[i]);
+            const uint4 sm = ldStream(&p.shadow.meta[i]);
             Hit<R> h;
             if constexpr (Mode<R>::parity && FAST != 0) h = traceVisible<PRIMS>(p.scene, so.xyz(), sd.xyz(), sm.x, cnt, overflow);
             else h = traceClosest<PRIMS, false>(p.scene, so.xyz(), sd.xyz(), sm.z, cnt, overflow);
@@ -1257,8 +1257,8 @@ namespace mcrt
 
             if (alive)
             {
-                const V4<R> ro = in.ray_o[i], rd = in.ray_d[i], th = in.thr[i], hv = p.hits[i];
-                meta = in.meta[i]; meta2 = in.meta2[i];
+                const V4<R> ro = ldStream(&in.ray_o[i]), rd = ldStream(&in.ray_d[i]), th = ldStream(&in.thr[i]), hv = ldStream(&p.hits[i]);
+                meta = ldStream(&in.meta[i]); meta2 = ldStream(&in.meta2[i]);
                 ray.start = ro.xyz(); ray.medium_ior = ro.w;
                 ray.direction = rd.xyz(); ray.refraction_scale = rd.w;
                 flux = th.xyz();

@@ -15,16 +15,16 @@ namespace mcrt
         {
             if (p.scene.bvh4 && p.scene.dynamic_fetch)
             {
-                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 2><<<grid, 256, 0, s>>>(p, cur);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 2><<<grid, 256, 0, s>>>(p, cur);
-                else k_extend<MCRT_REAL, PRIMS_ALL, 2><<<grid, 256, 0, s>>>(p, cur);
+                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
+                else k_extend<MCRT_REAL, PRIMS_ALL, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
                 return;
             }
             if (p.scene.bvh4)
             {
-                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 1><<<grid, 256, 0, s>>>(p, cur);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 1><<<grid, 256, 0, s>>>(p, cur);
-                else k_extend<MCRT_REAL, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p, cur);
+                if (p.scene.prims_class == PRIMS_TRI) k_extend<MCRT_REAL, PRIMS_TRI, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_extend<MCRT_REAL, PRIMS_TRI_SPHERE, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
+                else k_extend<MCRT_REAL, PRIMS_ALL, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p, cur);
                 return;
             }
         }
@@ -87,17 +87,17 @@ namespace mcrt
         {
             if (p.scene.bvh4 && p.scene.dynamic_fetch && p.filmp.is_default_box)
             {
-                if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 2><<<grid, 256, 0, s>>>(p);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 2><<<grid, 256, 0, s>>>(p);
-                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 2><<<grid, 256, 0, s>>>(p);
+                if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
+                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 2><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
                 return;
             }
             if (p.scene.bvh4)
             {
-                if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p);
-                else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 1><<<grid, 256, 0, s>>>(p);
-                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 1><<<grid, 256, 0, s>>>(p);
-                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 1><<<grid, 256, 0, s>>>(p);
+                if (!p.filmp.is_default_box) k_shadow<MCRT_REAL, true, PRIMS_ALL, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI) k_shadow<MCRT_REAL, false, PRIMS_TRI, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
+                else if (p.scene.prims_class == PRIMS_TRI_SPHERE) k_shadow<MCRT_REAL, false, PRIMS_TRI_SPHERE, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
+                else k_shadow<MCRT_REAL, false, PRIMS_ALL, 1><<<grid, 256, fastStackSharedBytes(256), s>>>(p);
                 return;
             }
         }
@@ -123,7 +123,7 @@ namespace mcrt
     {
         if constexpr (Mode<MCRT_REAL>::parity)
         {
-            if (sc.bvh4) { k_trace_user<MCRT_REAL, true><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c); return; }
+            if (sc.bvh4) { k_trace_user<MCRT_REAL, true><<<grid, 256, fastStackSharedBytes(256), s>>>(sc, rays6, n, out_tuv, out_prim, c); return; }
         }
         k_trace_user<MCRT_REAL, false><<<grid, 256, 0, s>>>(sc, rays6, n, out_tuv, out_prim, c);
     }

@@ -75,12 +75,15 @@ namespace mcrt
         return dx * dx + dy * dy + dz * dz;
     }
 
+    constexpr int KNN_HIST_BINS = 256;
+
     struct KnnShared
     {
         double* res_d2;       // [k_pad]
         uint32_t* res_idx;    // [k_pad]
         double* fr_d2;        // [KNN_FRONTIER]
         uint32_t* fr_node;    // [KNN_FRONTIER]
+        uint32_t* hist;       // [KNN_HIST_BINS] distance histogram of one leaf (radius estimate before the result set is full)
     };
 
     // warp maximum of non-negative doubles: their bit patterns order like the values, so two
@@ -138,6 +141,66 @@ namespace mcrt
             if (node->leaf || count <= (unsigned long long)k)
             {
                 const unsigned long long start = node->start, end = start + count;
+                if (n_found < k && count >= (unsigned long long)k && count <= 8ull * 32ull)
+                {
+                    // Radius estimate before the fill. Filling the result set with the first k photons of the leaf
+                    // and then replacing the farthest one photon at a time costs ~k ln(count/k) replacements of ~55
+                    // dependent warp instructions each (70 % of the kernel, ncu). Instead: one pass histograms the
+                    // photons' distances (256 bins between the nearest and the farthest point of the octant's box),
+                    // the bin where the running count reaches k gives an upper bound of the k-th distance - the same
+                    // kind of bound as the reference's farthest-corner rule (linear-octree.cpp:98-101), only tighter -
+                    // and the fill below then accepts k photons plus the few that share the last bin.
+                    const double lo = octantDistance2(*node, px, py, pz), hi = octantMaxDistance2(*node, px, py, pz);
+                    if (hi > lo)
+                    {
+                        const double scale = (double)(KNN_HIST_BINS - 1) / (hi - lo);
+                        for (uint32_t b = lane; b < (uint32_t)KNN_HIST_BINS; b += 32) sh.hist[b] = 0u;
+                        __syncwarp();
+                        for (unsigned long long idx = start + lane; idx < end; idx += 32)
+                        {
+                            const float4 a = __ldg(&map.photons[2 * idx]);
+                            const float4 b = __ldg(&map.photons[2 * idx + 1]);
+                            const double dx = px - (double)a.w, dy = py - (double)b.x, dz = pz - (double)b.y;
+                            const double d2 = dx * dx + dy * dy + dz * dz;
+                            if (d2 <= max_d2)
+                            {
+                                const double q = (d2 - lo) * scale;   // monotone in d2
+                                const uint32_t bin = q <= 0.0 ? 0u : (q >= (double)(KNN_HIST_BINS - 1) ? (uint32_t)(KNN_HIST_BINS - 1) : (uint32_t)q);
+                                atomicAdd(&sh.hist[bin], 1u);
+                            }
+                        }
+                        __syncwarp();
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int b = 0; b < KNN_HIST_BINS / 32; b++) mine += sh.hist[lane * (KNN_HIST_BINS / 32) + b];
+                        uint32_t incl = mine;
+                        for (int off = 1; off < 32; off <<= 1)
+                        {
+                            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                            if (lane >= (unsigned)off) incl += up;
+                        }
+                        const unsigned reach = __ballot_sync(0xFFFFFFFFu, incl >= k);
+                        if (reach)   // else: fewer than k photons of this leaf lie inside the current bound
+                        {
+                            const int owner = __ffs(reach) - 1;
+                            uint32_t bsel = 0;
+                            if ((int)lane == owner)
+                            {
+                                uint32_t running = incl - mine;
+                                for (int b = 0; b < KNN_HIST_BINS / 32; b++)
+                                {
+                                    running += sh.hist[lane * (KNN_HIST_BINS / 32) + b];
+                                    if (running >= k) { bsel = lane * (KNN_HIST_BINS / 32) + b; break; }
+                                }
+                            }
+                            bsel = __shfl_sync(0xFFFFFFFFu, bsel, owner);
+                            // every photon counted up to bin bsel has d2 < upper edge of that bin (the mapping is monotone)
+                            const double bound = (lo + (double)(bsel + 1u) / scale) * (1.0 + 1e-9);
+                            if (bound < max_d2) max_d2 = bound;
+                        }
+                        __syncwarp();
+                    }
+                }
                 for (unsigned long long base = start; base < end; base += 32)
                 {
                     const unsigned long long idx = base + lane;
@@ -325,20 +388,21 @@ namespace mcrt
     MCRT_D KnnShared knnSharedFor(unsigned char* smem, uint32_t k_pad)
     {
         const unsigned warp = threadIdx.x >> 5;
-        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12;
+        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12 + (size_t)KNN_HIST_BINS * 4;
         unsigned char* base = smem + warp * ((per_warp + 15) & ~(size_t)15);
         KnnShared sh;
         sh.res_d2 = reinterpret_cast<double*>(base);
         sh.fr_d2 = sh.res_d2 + k_pad;
         sh.res_idx = reinterpret_cast<uint32_t*>(sh.fr_d2 + KNN_FRONTIER);
         sh.fr_node = sh.res_idx + k_pad;
+        sh.hist = sh.fr_node + KNN_FRONTIER;
         return sh;
     }
 
     inline size_t knnSharedBytes(uint32_t k)
     {
         const uint32_t k_pad = (k + 31u) & ~31u;
-        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12;
+        const size_t per_warp = (size_t)k_pad * 12 + (size_t)KNN_FRONTIER * 12 + (size_t)KNN_HIST_BINS * 4;
         return KNN_WARPS_PER_BLOCK * ((per_warp + 15) & ~(size_t)15);
     }
 

@@ -25,7 +25,9 @@ namespace mcrt
         MCRT_HD R operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
     };
 
-    template <class R> struct alignas(16) V4
+    // 4 * sizeof(R) alignment: a float64 record is one 256-bit global access on sm_100 (LDG.E.256 / STG.E.256)
+    // instead of two 128-bit ones - the path state, hit and shadow records are all V4<double>
+    template <class R> struct alignas(4 * sizeof(R)) V4
     {
         R x, y, z, w;
         MCRT_HD V4() { }
@@ -33,6 +35,35 @@ namespace mcrt
         MCRT_HD V4(const V3<R>& v, R d) : x(v.x), y(v.y), z(v.z), w(d) { }
         MCRT_HD V3<R> xyz() const { return V3<R>(x, y, z); }
     };
+
+    // Streaming access to the wavefront queues (path state, hits, shadow records: written once, read once per
+    // bounce, 6.5 GB per pool): L2 evict-first, so that the 126 MB L2 keeps the scene arrays every ray reads
+    // (BVH nodes, float64 triangle records) instead of queue records nobody will touch again.
+#if defined(__CUDACC__) && defined(MCRT_NO_STREAM)   // A/B switch: plain accesses
+    template <class T> MCRT_D T ldStream(const T* p) { return *p; }
+    template <class T> MCRT_D void stStream(T* p, const T& v) { *p = v; }
+#elif defined(__CUDACC__)
+    MCRT_D V4<double> ldStream(const V4<double>* p)
+    {
+        V4<double> v;
+        asm volatile("ld.global.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+        return v;
+    }
+    MCRT_D void stStream(V4<double>* p, const V4<double>& v)
+    {
+        asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+    }
+    // 128-bit records: the cache-streaming forms (ld.global.cs / st.global.cs = evict-first); the L2::evict_first
+    // qualifier exists for the 256-bit instructions only
+    MCRT_D V4<float> ldStream(const V4<float>* p)
+    {
+        const float4 f = __ldcs(reinterpret_cast<const float4*>(p));
+        return V4<float>(f.x, f.y, f.z, f.w);
+    }
+    MCRT_D void stStream(V4<float>* p, const V4<float>& v) { __stcs(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w)); }
+    MCRT_D uint4 ldStream(const uint4* p) { return __ldcs(p); }
+    MCRT_D void stStream(uint4* p, const uint4& v) { __stcs(p, v); }
+#endif
 
     template <class R> MCRT_HD V3<R> operator+(const V3<R>& a, const V3<R>& b) { return V3<R>(a.x + b.x, a.y + b.y, a.z + b.z); }
     template <class R> MCRT_HD V3<R> operator-(const V3<R>& a, const V3<R>& b) { return V3<R>(a.x - b.x, a.y - b.y, a.z - b.z); }
