@@ -136,7 +136,7 @@ struct mcrt_ctx
     int sort_shade_class = 1;   // k_shade walks paths grouped by the material class of their hit
     int sort_prim_key = -1;   // -1 auto (>= 4096 primitives), 0 origin-cell keys, 1 source-primitive keys
     uint32_t pool_paths = 1u << 23;   // measured on C2: 2 Mi 2269, 4 Mi 2378, 8 Mi 2463, 16 Mi 2503 Mray/s (coarser bins fill better)
-    int blocks_per_sm = 8;
+    int blocks_per_sm = 16;   // grid = SMs x this for the grid-stride stage kernels; measured r2 (profiles/r2_knob_sweep.txt): 4 -> 8 -> 16 = 3388 -> 3758 -> 3819 Mray/s on C2
     double ray_eps_scale = 1e-5;
     int poll_interval = 4;
     int stage_timing = 0;
@@ -1355,6 +1355,7 @@ int mcrt_photon_build_dev(mcrt_ctx* ctx, const mcrt_photon_emit_params* params, 
     ctx->has_photons = true;
     ctx->built_valid = true;
     if (build_ms) *build_ms = ctx->photon_build_ms;
+    freeEmission(ctx);   // the raw emission buffers have been consumed (or superseded by the gathered arrays of a sharded pass)
     return MCRT_OK;
 }
 

@@ -22,6 +22,10 @@ int main(int argc, char* argv[])
     if (argc < 7) { std::cerr << "usage: test_gpu_integrators <scenes_dir> <scene.json> <photon_map> <width> <height> <sqrtspp> [emissions]\n"; return 2; }
     try
     {
+        // the reference seeds its sampler from std::random_device (sampler.hpp:58). MCRT_SEED pins it: a photon path that
+        // bounces chaotically inside a glass sphere amplifies the 1-ulp libm differences between host and device (DESIGN.md
+        // section 8), and whether a run contains such a photon depends on the seed
+        if (const char* e = std::getenv("MCRT_SEED")) const_cast<uint32_t&>(Sampler::global_seed) = (uint32_t)std::strtoul(e, nullptr, 0);
         const std::filesystem::path dir(argv[1]);
         Scene::path = dir;
         const bool photon_map = std::atoi(argv[3]) != 0;
