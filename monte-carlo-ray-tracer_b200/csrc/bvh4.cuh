@@ -319,16 +319,18 @@ namespace mcrt
         RayQ<double> ray;
         uint32_t item = 0;
         bool active = false;
+        bool more = true;        // warp-uniform: the queue may still hold rays
         const unsigned lane = threadIdx.x & 31u;
         while (true)
         {
             const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-            if (need)
+            if (need && more)
             {
                 uint32_t base = 0;
                 const int leader = __ffs(need) - 1;
                 if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                more = base < n;
                 if (!active)
                 {
                     const uint32_t ii = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
@@ -350,7 +352,11 @@ namespace mcrt
                     }
                 }
             }
-            if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
+            if (__ballot_sync(0xFFFFFFFFu, active) == 0u)
+            {
+                if (!more) break;
+                continue;        // every fetched ray was resolved at once (it misses its light): fetch again
+            }
             while (active)
             {
                 if (!fs.step(sc, ray, cnt, overflow))
