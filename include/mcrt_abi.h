@@ -381,6 +381,13 @@ int mcrt_frame_open(mcrt_ctx* ctx, const unsigned char ipc_handle[64], void** de
 int mcrt_frame_close(mcrt_ctx* ctx, void* peer_ptr);
 int mcrt_frame_free(mcrt_ctx* ctx, void* dev_ptr);
 
+/* Test hook (host only, no CUDA call): the 4-wide float-box BVH mcrt_scene_upload derives from the scene's tree for the
+ * order-free closest-hit search (csrc/bvh4.cuh). nodes128: n_nodes records of 128 bytes {float lo[3][4], hi[3][4];
+ * uint32 child[4], pad[4]}; child = 0 empty | inner node index | 0x80000000 | first_prim << 8 | count. max_leaf: 0 keeps the
+ * reference's leaves, n cuts larger leaves into runs of n, 0xFFFFFFFF = the upload's own rule. */
+int mcrt_bvh4_host(const mcrt_scene_desc* scene, uint32_t max_leaf, void** handle, const void** nodes128, uint32_t* n_nodes);
+void mcrt_bvh4_host_free(void* handle);
+
 /* Measured FP64 issue rate of this GPU (independent DFMA chains on every SM), thread-instructions per second:
  * the denominator of bench.py's FP64 roofline for the float64 kernels. */
 int mcrt_fp64_peak(mcrt_ctx* ctx, double* dfma_per_second);

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "mcrt_bvh_build", "mcrt_bvh_free", "mcrt_image_tonemap", "mcrt_image_tonemap_dev",
     "mcrt_render_rows_strided_peers", "mcrt_frame_alloc", "mcrt_frame_open", "mcrt_frame_close", "mcrt_frame_free",
     "mcrt_render_film_sums_strided_dev", "mcrt_film_resolve_dev",
+    "mcrt_bvh4_host", "mcrt_bvh4_host_free",
     "mcrt_fp64_peak", "mcrt_photon_emit_total", "mcrt_photon_emit_range", "mcrt_photon_build_dev",
 ]
 
@@ -201,6 +202,9 @@ def lib():
         L.mcrt_frame_close.argtypes = [C.c_void_p, C.c_void_p]
         L.mcrt_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.mcrt_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.mcrt_bvh4_host.argtypes = [C.POINTER(SceneDesc), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+        L.mcrt_bvh4_host_free.argtypes = [C.c_void_p]
+        L.mcrt_bvh4_host_free.restype = None
         L.mcrt_render_film_sums_strided_dev.argtypes = [C.c_void_p, C.POINTER(CameraRec), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                         C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         L.mcrt_film_resolve_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -839,6 +843,25 @@ def bvh_build(prim_bounds, scene_bounds, bvh_type, bins_per_axis=0, device=0):
         return out
     finally:
         lib().mcrt_destroy(ctx)
+
+
+BVH4_NODE_DTYPE = np.dtype([("lo", "<f4", (3, 4)), ("hi", "<f4", (3, 4)), ("child", "<u4", (4,)), ("pad", "<u4", (4,))])
+
+
+def bvh4_host(scene, max_leaf=0xFFFFFFFF):
+    """The 4-wide float-box BVH of the order-free search as mcrt_scene_upload builds it (host only) -> structured array."""
+    d = scene.desc()
+    h, p, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
+    rc = lib().mcrt_bvh4_host(C.byref(d), max_leaf, C.byref(h), C.byref(p), C.byref(n))
+    if rc:
+        raise McrtError(f"mcrt_bvh4_host failed with {rc}")
+    try:
+        if n.value == 0:
+            return np.zeros(0, BVH4_NODE_DTYPE)
+        buf = (C.c_uint8 * (128 * n.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=BVH4_NODE_DTYPE).copy()
+    finally:
+        lib().mcrt_bvh4_host_free(h)
 
 
 def shard_rows(height, rank, world_size):

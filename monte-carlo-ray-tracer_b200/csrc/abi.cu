@@ -358,7 +358,7 @@ namespace
     // primitives get tested. Inner children are pulled up greedily by box area (largest first) while
     // the node has room; nodes with more than 4 children (the reference's octree type has up to 8) get
     // intermediate nodes over consecutive runs of children. Float boxes are rounded outwards.
-    int buildBvh4(mcrt_ctx* ctx, const mcrt_scene_desc& s, std::vector<Bvh4Node>& out)
+    int buildBvh4(uint32_t max_leaf_option, const mcrt_scene_desc& s, std::vector<Bvh4Node>& out)
     {
         out.clear();
         if (s.n_nodes == 0) return MCRT_OK;
@@ -370,7 +370,7 @@ namespace
         // warp then spend similar time per leaf, and the tighter boxes cull more)
         // measured on the B200 (profiles/r2_leaf_split.txt): cutting leaves to 2 primitives gains 5 % on the 44-primitive
         // hexagon room (the reference's leaves hold up to 8 there), costs 2-10 % on the 457 k-triangle spaceship
-        const uint32_t max_leaf = ctx->bvh4_max_leaf == 0xFFFFFFFFu ? (s.n_prims < 4096u ? 2u : 0u) : ctx->bvh4_max_leaf;
+        const uint32_t max_leaf = max_leaf_option == 0xFFFFFFFFu ? (s.n_prims < 4096u ? 2u : 0u) : max_leaf_option;
         auto primBox = [&](uint32_t prim, double* b)
         {
             const uint32_t type = s.prim_type[prim], idx = s.prim_index[prim];
@@ -496,7 +496,6 @@ namespace
             too_big = emit(kids, self) != 0;
         }
         if (too_big) out.clear();   // a leaf with more than 255 primitives: the replay traversal handles the scene
-        (void)ctx;
         return MCRT_OK;
     }
 
@@ -1131,7 +1130,7 @@ int mcrt_scene_upload(mcrt_ctx* ctx, const mcrt_scene_desc* scene, uint64_t* h2d
         if ((rc = buildWide(ctx, s, a))) return rc;
         if ((rc = uploadArrays(ctx, s, a, bytes))) return rc;
         std::vector<Bvh4Node> bvh4;
-        if ((rc = buildBvh4(ctx, s, bvh4))) return rc;
+        if ((rc = buildBvh4(ctx->bvh4_max_leaf, s, bvh4))) return rc;
         a.dev.bvh4 = nullptr;
         if (!bvh4.empty() && (rc = devUpload(ctx, ctx->scene_allocs, &a.dev.bvh4, bvh4, bytes))) return rc;
         ctx->n_bvh4_nodes = (uint32_t)bvh4.size();
@@ -1612,6 +1611,21 @@ int mcrt_film_resolve_dev(mcrt_ctx* ctx, const double* rgb_sum_dev, const double
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return MCRT_OK;
+}
+
+int mcrt_bvh4_host(const mcrt_scene_desc* scene, uint32_t max_leaf, void** handle, const void** nodes128, uint32_t* n_nodes)
+{
+    if (!scene || !handle || !nodes128 || !n_nodes) return MCRT_ERR_INVALID;
+    auto* v = new std::vector<Bvh4Node>();
+    const int rc = buildBvh4(max_leaf, *scene, *v);
+    if (rc) { delete v; return rc; }
+    *handle = v; *nodes128 = v->data(); *n_nodes = (uint32_t)v->size();
+    return MCRT_OK;
+}
+
+void mcrt_bvh4_host_free(void* handle)
+{
+    delete static_cast<std::vector<Bvh4Node>*>(handle);
 }
 
 int mcrt_frame_alloc(mcrt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64])
