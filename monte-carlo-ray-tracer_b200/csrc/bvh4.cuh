@@ -32,6 +32,9 @@
 #ifndef MCRT_FAST_STACK
 #define MCRT_FAST_STACK 40
 #endif
+#ifndef MCRT_SPECULATIVE              // 1: a lane holding a leaf keeps walking inner nodes until its warp-mates hold one too
+#define MCRT_SPECULATIVE 0
+#endif
 #ifndef MCRT_FAST_SMEM_STACK          // entries of the search stack kept in shared memory (per thread); the rest is local memory.
 #define MCRT_FAST_SMEM_STACK 0       // Measured on the B200 (profiles/r2_stream_stack_ab.txt): 12 entries in shared memory are 4-5 % SLOWER than
 #endif                               // the all-local stack on the hexagon room, the spaceship and the bulldozer alike (the L1 keeps the hot top of the
@@ -189,84 +192,118 @@ namespace mcrt
             return false;
         }
 
-        MCRT_D bool step(const DeviceScene<double>& sc, const RayQ<double>& ray, TraceCounters& cnt, uint32_t& overflow)
+        // One inner node: tests its four child boxes, pushes the far hits, continues with the nearest (or with the next
+        // pending entry when nothing is hit). -> false: nothing left to visit.
+        MCRT_D bool visitNode(const DeviceScene<double>& sc, TraceCounters& cnt, uint32_t& overflow)
         {
-            const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.bvh4);
-            while (!(cur & BVH4_LEAF))
-            {
-                const float4* n = nodes + 8 * (size_t)cur;
-                // float4 rows of a node: lo.x lo.y lo.z hi.x hi.y hi.z; the near plane of axis k is lo for d_k >= 0
-                const float4 bnx = __ldg(n + 0 + fr.near_row[0]), bny = __ldg(n + 1 + fr.near_row[1]), bnz = __ldg(n + 2 + fr.near_row[2]);
-                const float4 bfx = __ldg(n + 3 - fr.near_row[0]), bfy = __ldg(n + 4 - fr.near_row[1]), bfz = __ldg(n + 5 - fr.near_row[2]);
-                const uint4 ch = __ldg(reinterpret_cast<const uint4*>(n + 6));
-                cnt.box_tests += 4;
+            const float4* __restrict__ n = reinterpret_cast<const float4*>(sc.bvh4) + 8 * (size_t)cur;
+            // float4 rows of a node: lo.x lo.y lo.z hi.x hi.y hi.z; the near plane of axis k is lo for d_k >= 0
+            const float4 bnx = __ldg(n + 0 + fr.near_row[0]), bny = __ldg(n + 1 + fr.near_row[1]), bnz = __ldg(n + 2 + fr.near_row[2]);
+            const float4 bfx = __ldg(n + 3 - fr.near_row[0]), bfy = __ldg(n + 4 - fr.near_row[1]), bfz = __ldg(n + 5 - fr.near_row[2]);
+            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(n + 6));
+            cnt.box_tests += 4;
 
-                #define MCRT_SLAB(C, REF, SLOT)                                                                   \
-                    uint32_t key##SLOT;                                                                           \
-                    {                                                                                             \
-                        const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.C, fr.idx, -fr.onx), __fmaf_rn(bny.C, fr.idy, -fr.ony)), \
-                                               fmaxf(__fmaf_rn(bnz.C, fr.idz, -fr.onz), 0.0f)) * 0.99999619f;    \
-                        const float tf = fminf(fminf(__fmaf_rn(bfx.C, fr.idx, -fr.ofx), __fmaf_rn(bfy.C, fr.idy, -fr.ofy)), \
-                                               __fmaf_rn(bfz.C, fr.idz, -fr.ofz)) * 1.00000381f;                  \
-                        const bool hit = (REF) != 0u && tn <= tf && tn <= limit;                                   \
-                        key##SLOT = hit ? ((__float_as_uint(tn) & 0x7FFFFFFCu) | SLOT##u) : 0xFFFFFFFFu;           \
-                    }
-                MCRT_SLAB(x, ch.x, 0)
-                MCRT_SLAB(y, ch.y, 1)
-                MCRT_SLAB(z, ch.z, 2)
-                MCRT_SLAB(w, ch.w, 3)
-                #undef MCRT_SLAB
-
-                // sort the four keys ascending (entry distance in the high 30 bits, slot in the low 2)
-                #define MCRT_CE(A, B) { const uint32_t lo_ = min(A, B); B = max(A, B); A = lo_; }
-                MCRT_CE(key0, key1) MCRT_CE(key2, key3) MCRT_CE(key0, key2) MCRT_CE(key1, key3) MCRT_CE(key1, key2)
-                #undef MCRT_CE
-                auto refOf = [&](uint32_t key) { const uint32_t s = key & 3u; return s == 0u ? ch.x : (s == 1u ? ch.y : (s == 2u ? ch.z : ch.w)); };
-
-                if (key0 == 0xFFFFFFFFu)
-                {
-                    if (!pop()) return false;     // nothing hit and nothing pending
-                    continue;
+            #define MCRT_SLAB(C, REF, SLOT)                                                                   \
+                uint32_t key##SLOT;                                                                           \
+                {                                                                                             \
+                    const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.C, fr.idx, -fr.onx), __fmaf_rn(bny.C, fr.idy, -fr.ony)), \
+                                           fmaxf(__fmaf_rn(bnz.C, fr.idz, -fr.onz), 0.0f)) * 0.99999619f;    \
+                    const float tf = fminf(fminf(__fmaf_rn(bfx.C, fr.idx, -fr.ofx), __fmaf_rn(bfy.C, fr.idy, -fr.ofy)), \
+                                           __fmaf_rn(bfz.C, fr.idz, -fr.ofz)) * 1.00000381f;                  \
+                    const bool hit = (REF) != 0u && tn <= tf && tn <= limit;                                   \
+                    key##SLOT = hit ? ((__float_as_uint(tn) & 0x7FFFFFFCu) | SLOT##u) : 0xFFFFFFFFu;           \
                 }
-                // far children first, so the nearest pending one is on top
-                if (key3 != 0xFFFFFFFFu) push(refOf(key3), key3 & ~3u, overflow);
-                if (key2 != 0xFFFFFFFFu) push(refOf(key2), key2 & ~3u, overflow);
-                if (key1 != 0xFFFFFFFFu) push(refOf(key1), key1 & ~3u, overflow);
-                cur = refOf(key0);
-            }
+            MCRT_SLAB(x, ch.x, 0)
+            MCRT_SLAB(y, ch.y, 1)
+            MCRT_SLAB(z, ch.z, 2)
+            MCRT_SLAB(w, ch.w, 3)
+            #undef MCRT_SLAB
+
+            // sort the four keys ascending (entry distance in the high 30 bits, slot in the low 2)
+            #define MCRT_CE(A, B) { const uint32_t lo_ = min(A, B); B = max(A, B); A = lo_; }
+            MCRT_CE(key0, key1) MCRT_CE(key2, key3) MCRT_CE(key0, key2) MCRT_CE(key1, key3) MCRT_CE(key1, key2)
+            #undef MCRT_CE
+            auto refOf = [&](uint32_t key) { const uint32_t s = key & 3u; return s == 0u ? ch.x : (s == 1u ? ch.y : (s == 2u ? ch.z : ch.w)); };
+
+            if (key0 == 0xFFFFFFFFu) return pop();     // nothing hit: next pending entry, if any
+            // far children first, so the nearest pending one is on top
+            if (key3 != 0xFFFFFFFFu) push(refOf(key3), key3 & ~3u, overflow);
+            if (key2 != 0xFFFFFFFFu) push(refOf(key2), key2 & ~3u, overflow);
+            if (key1 != 0xFFFFFFFFu) push(refOf(key1), key1 & ~3u, overflow);
+            cur = refOf(key0);
+            return true;
+        }
+
+        // The primitives of one leaf. -> false: the search is over (OCC only: an occluder or a tie was found).
+        MCRT_D bool testLeaf(uint32_t leaf, const DeviceScene<double>& sc, const RayQ<double>& ray, TraceCounters& cnt)
+        {
+            const uint32_t first = (leaf >> 8) & (BVH4_MAX_PRIMS - 1u), count = leaf & 0xFFu;
+            for (uint32_t i = first; i < first + count; i++)
             {
-                const uint32_t first = (cur >> 8) & (BVH4_MAX_PRIMS - 1u), count = cur & 0xFFu;
-                for (uint32_t i = first; i < first + count; i++)
+                double t, u, v;
+                if constexpr (OCC)
                 {
-                    double t, u, v;
-                    if constexpr (OCC)
-                    {
-                        if (i == target) continue;
-                        if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
-                        {
-                            const double delta = ambiguityDelta(best.t, (double)sc.scene_scale);
-                            if (t < best.t - delta) { verdict = 1u; cnt.prim_tests += i - first + 1; return false; }   // occluder: done
-                            if (t <= best.t + delta) { verdict = 2u; cnt.prim_tests += i - first + 1; return false; }  // tie: replay
-                        }
-                        continue;
-                    }
+                    if (i == target) continue;
                     if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
                     {
-                        if (t < best.t)
-                        {
-                            second_t = best.t;
-                            best.t = t; best.u = u; best.v = v; best.prim = i;
-                            limit = __double2float_ru(t + 2.0 * ambiguityDelta(t, (double)sc.scene_scale));
-                        }
-                        else if (t < second_t)
-                        {
-                            second_t = t;
-                        }
+                        const double delta = ambiguityDelta(best.t, (double)sc.scene_scale);
+                        if (t < best.t - delta) { verdict = 1u; cnt.prim_tests += i - first + 1; return false; }   // occluder: done
+                        if (t <= best.t + delta) { verdict = 2u; cnt.prim_tests += i - first + 1; return false; }  // tie: replay
+                    }
+                    continue;
+                }
+                if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
+                {
+                    if (t < best.t)
+                    {
+                        second_t = best.t;
+                        best.t = t; best.u = u; best.v = v; best.prim = i;
+                        limit = __double2float_ru(t + 2.0 * ambiguityDelta(t, (double)sc.scene_scale));
+                    }
+                    else if (t < second_t)
+                    {
+                        second_t = t;
                     }
                 }
-                cnt.prim_tests += count;
             }
+            cnt.prim_tests += count;
+            return true;
+        }
+
+        MCRT_D bool step(const DeviceScene<double>& sc, const RayQ<double>& ray, TraceCounters& cnt, uint32_t& overflow)
+        {
+#if MCRT_SPECULATIVE
+            // Speculative form (Aila & Laine): a lane that reaches a leaf stashes it and keeps walking inner nodes until every
+            // lane walking with it holds a leaf too; then all test their leaves together. Visits a superset of the nodes
+            // (the stashed leaf could have shortened the ray first), never a different answer.
+            uint32_t stashed = 0u;
+            bool have_cur = true;
+            while (true)
+            {
+                if (cur & BVH4_LEAF)
+                {
+                    if (stashed) break;                       // a second leaf: test the first one now
+                    stashed = cur;
+                    have_cur = pop();
+                    if (!have_cur) break;
+                }
+                else
+                {
+                    have_cur = visitNode(sc, cnt, overflow);
+                    if (!have_cur) break;
+                }
+                if (stashed && !__any_sync(__activemask(), stashed == 0u)) break;
+            }
+            if (stashed && !testLeaf(stashed, sc, ray, cnt)) return false;
+            return have_cur;
+#else
+            while (!(cur & BVH4_LEAF))
+            {
+                if (!visitNode(sc, cnt, overflow)) return false;
+            }
+            if (!testLeaf(cur, sc, ray, cnt)) return false;
             return pop();
+#endif
         }
 
         // another hit within delta of the closest: the answer may depend on the visiting order
