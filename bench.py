@@ -222,30 +222,42 @@ def profile_kernels(args, workload, sqrtspp):
     """Non-timed epilogue: the same code path under `ncu` at a reduced sample count, every launch of the stage
     kernels counted once: DRAM bytes, FP64 thread-instructions, active lanes per instruction, per kernel.
     -> {kernel: {...}} with per-ray figures, or {"unavailable": why}."""
-    import csv
-    import io
     import shutil
     if not shutil.which("ncu"):
         return {"unavailable": "ncu not on PATH"}
     cmd = ["ncu", "--metrics", ",".join(NCU_METRICS), "--clock-control", "none", "-k", "regex:k_extend|k_shade|k_shadow|k_knn",
-           "--csv", sys.executable, os.path.abspath(__file__), "--child-render", "--workload", workload, "--sqrtspp", str(sqrtspp),
+           "--print-units", "base", "--csv", sys.executable, os.path.abspath(__file__), "--child-render", "--workload", workload, "--sqrtspp", str(sqrtspp),
            "--precision", args.precision] + (["--pool", str(args.pool)] if args.pool else [])
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    out = parse_ncu_output(r.stdout)
+    if "unavailable" in out:
+        out["unavailable"] += " | " + (r.stderr or "")[-160:].replace("\n", " ")
+        return out
+    out["sample"] = f"{workload} at {sqrtspp * sqrtspp} spp under ncu (all launches of the stage kernels, each counted once)"
+    return out
+
+
+def parse_ncu_output(text):
+    """`ncu --csv` rows + the child's CHILD_STATS line -> per-kernel, per-unit figures (see profile_kernels)."""
+    import csv
+    import io
     stats = None
     rows = []
-    for ln in r.stdout.splitlines():
+    for ln in text.splitlines():
         if ln.startswith("CHILD_STATS "):
             stats = json.loads(ln[len("CHILD_STATS "):])
         elif ln.startswith('"'):
             rows.append(ln)
     if stats is None or len(rows) < 2:
-        return {"unavailable": "ncu produced no counters: " + (r.stderr or r.stdout)[-200:].replace("\n", " ")}
+        return {"unavailable": "ncu produced no counters: " + text[-200:].replace("\n", " ")}
     rd = list(csv.reader(io.StringIO("\n".join(rows))))
     hdr = rd[0]
     ik, im, iv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    iu = hdr.index("Metric Unit") if "Metric Unit" in hdr else None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     agg = {}
     for row in rd[1:]:
         if len(row) <= iv:
@@ -258,12 +270,14 @@ def profile_kernels(args, workload, sqrtspp):
             v = float(row[iv].replace(",", ""))
         except ValueError:
             continue
+        if iu is not None and row[im].startswith("dram__bytes"):
+            v *= scale.get(row[iu], 1.0)           # ncu prints byte counts in auto-scaled units unless told otherwise
         a = agg.setdefault(key, {"launches": 0})
         a[row[im]] = a.get(row[im], 0.0) + v
         if row[im] == "gpu__time_duration.sum":
             a["launches"] += 1
     units = {"k_extend": stats["extension_rays"], "k_shadow": stats["shadow_rays"], "k_shade": stats["extension_rays"], "k_knn": max(1, stats["knn_queries"])}
-    out = {"sample": f"{workload} at {sqrtspp * sqrtspp} spp under ncu (all launches of the stage kernels, each counted once)"}
+    out = {}
     for k, a in agg.items():
         if k not in units or not units[k]:
             continue
