@@ -721,6 +721,97 @@ void oracle_trace(void* h, const mcrt_ray* rays, size_t n, mcrt_hit* hits)
     }
 }
 
+// CPU restatement of the product's order-free closest-hit search (monte-carlo-ray-tracer_b200/csrc/bvh4.cuh: FastRay, FastSearch,
+// ambiguityDelta) over the 4-wide float-box BVH the product derives from the scene (passed in: mcrt_bvh4_host). Same float32 slab
+// arithmetic - fmaf and single multiplications are IEEE operations on both sides -, same margins, same pruning limit, the oracle's own
+// float64 primitive tests (which equal the reference's). flags[i]: 1 = the search declares the ray ambiguous (the product then replays it
+// in the reference's order), 0 = the search's answer is final. tests/test_fast_search_cpu.py: final answers == reference-order answers.
+namespace
+{
+    struct Node4 { float lo[3][4], hi[3][4]; uint32_t child[4], pad[4]; };
+
+    double ambiguityDelta(double t, double scale) { return 1e-6 * t + 1e-12 * scale; }
+
+    float roundUpToFloat(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }   // __double2float_ru
+
+    Isect searchFast(const Scene& s, const Node4* nodes, const Ray& r, double scene_scale, bool& ambiguous, uint64_t& box_tests, uint64_t& prim_tests)
+    {
+        auto inv = [](double v) { float f = (float)v; if (!(std::fabs(f) >= 1e-18f)) f = std::copysign(1e-18f, f); return 1.0f / f; };
+        const float id[3] = { inv(r.direction.x), inv(r.direction.y), inv(r.direction.z) };
+        const float od[3] = { (float)r.start.x * id[0], (float)r.start.y * id[1], (float)r.start.z * id[2] };
+        float on[3], of[3];
+        for (int k = 0; k < 3; k++) { const float m = std::fabs(od[k]) * 1.9073486e-6f; on[k] = od[k] + m; of[k] = od[k] - m; }
+        Isect best;
+        double second_t = std::numeric_limits<double>::max();
+        float limit = INFINITY;
+        struct Entry { uint32_t ref; float tn; };
+        std::vector<Entry> stack;
+        uint32_t cur = 0;
+        auto pop = [&]() { while (!stack.empty()) { Entry e = stack.back(); stack.pop_back(); if (e.tn <= limit) { cur = e.ref; return true; } } return false; };
+        while (true)
+        {
+            bool have = true;
+            while (!(cur & 0x80000000u))
+            {
+                const Node4& n = nodes[cur];
+                box_tests += 4;
+                uint32_t key[4];
+                for (int c = 0; c < 4; c++)
+                {
+                    float tn = 0.0f, tf = INFINITY;
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const float bn = id[k] < 0.0f ? n.hi[k][c] : n.lo[k][c], bf = id[k] < 0.0f ? n.lo[k][c] : n.hi[k][c];
+                        tn = std::fmax(tn, std::fmaf(bn, id[k], -on[k]));
+                        tf = std::fmin(tf, std::fmaf(bf, id[k], -of[k]));
+                    }
+                    tn *= 0.99999619f; tf *= 1.00000381f;
+                    const bool hit = n.child[c] != 0u && tn <= tf && tn <= limit;
+                    uint32_t bits; std::memcpy(&bits, &tn, 4);
+                    key[c] = hit ? ((bits & 0x7FFFFFFCu) | (uint32_t)c) : 0xFFFFFFFFu;
+                }
+                std::sort(key, key + 4);
+                if (key[0] == 0xFFFFFFFFu) { if (!pop()) { have = false; break; } continue; }
+                for (int j = 3; j >= 1; j--)
+                    if (key[j] != 0xFFFFFFFFu) { const uint32_t b = key[j] & ~3u; float tn; std::memcpy(&tn, &b, 4); stack.push_back({ n.child[key[j] & 3u], tn }); }
+                cur = n.child[key[0] & 3u];
+            }
+            if (!have) break;
+            const uint32_t first = (cur >> 8) & 0x7FFFFFu, count = cur & 0xFFu;
+            for (uint32_t i = first; i < first + count; i++)
+            {
+                Isect c;
+                prim_tests++;
+                if (hitPrim(s, i, r, c))
+                {
+                    if (c.t < best.t) { second_t = best.t; best = c; best.prim = i; limit = roundUpToFloat(c.t + 2.0 * ambiguityDelta(c.t, scene_scale)); }
+                    else if (c.t < second_t) second_t = c.t;
+                }
+            }
+            if (!pop()) break;
+        }
+        ambiguous = best.prim != 0xFFFFFFFFu && second_t <= best.t + ambiguityDelta(best.t, scene_scale);
+        return best;
+    }
+}
+
+void oracle_trace_fast(void* h, const void* nodes128, uint32_t n_nodes, double scene_scale, const mcrt_ray* rays, size_t n, mcrt_hit* hits,
+                       uint8_t* flags, uint64_t* box_tests, uint64_t* prim_tests)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    (void)n_nodes;
+    uint64_t bt = 0, pt = 0;
+    for (size_t i = 0; i < n; i++)
+    {
+        bool amb = false;
+        Isect is = searchFast(s, static_cast<const Node4*>(nodes128), makeRay(D3(rays[i].origin), D3(rays[i].direction), s.d.scene_ior), scene_scale, amb, bt, pt);
+        hits[i].t = is.t; hits[i].u = is.u; hits[i].v = is.v; hits[i].prim = is.prim; hits[i].interpolate = is.interpolate;
+        flags[i] = amb ? 1 : 0;
+    }
+    if (box_tests) *box_tests = bt;
+    if (prim_tests) *prim_tests = pt;
+}
+
 void oracle_sample_rays(void* h, const mcrt_ray* rays, const uint32_t* pixel, const uint32_t* sample, size_t n, uint32_t seed, double* out)
 {
     const Scene& s = *static_cast<Scene*>(h);

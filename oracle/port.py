@@ -28,6 +28,8 @@ def lib():
         L.oracle_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.oracle_render_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_sample_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.oracle_trace_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
         L.oracle_bvh_free.argtypes = [C.c_void_p]
         L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -130,6 +132,16 @@ class PortScene:
         out = np.zeros((camera.height, camera.width, 3))
         lib().oracle_render_film(self.h, C.addressof(camera.rec), C.addressof(rec), sqrtspp, seed, _p(out))
         return out
+
+    def trace_fast(self, nodes, scene_scale, rays):
+        """The product's order-free search restated on the CPU over `nodes` (mcrt.bvh4_host). -> (hits, ambiguous flags, box tests, primitive tests)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        nodes = np.ascontiguousarray(nodes)
+        hits = np.zeros(len(rays), dtype=self.pkg.HIT_DTYPE)
+        flags = np.zeros(len(rays), dtype=np.uint8)
+        bt, pt = C.c_uint64(), C.c_uint64()
+        lib().oracle_trace_fast(self.h, _p(nodes), len(nodes), float(scene_scale), _p(rays), len(rays), _p(hits), _p(flags), C.byref(bt), C.byref(pt))
+        return hits, flags.astype(bool), bt.value, pt.value
 
     def sample_pixels(self, camera, pixel, sample, seed):
         """-> (rgb [n,3], camera rays [n,6]) for (pixel, sample) pairs"""

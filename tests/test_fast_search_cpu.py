@@ -1,0 +1,120 @@
+"""CPU test of the algorithm behind the product's parity-mode closest hit (csrc/bvh4.cuh): an order-free search over a 4-wide
+float-box BVH whose answer is FINAL unless it flags the ray as ambiguous (two candidates within delta), in which case the product
+replays the ray in the reference's visiting order. oracle_trace_fast restates the search on the CPU - same float32 slab arithmetic,
+margins and pruning limit, over the very nodes the product builds (mcrt_bvh4_host) - and oracle_trace is the reference-order
+traversal pinned to the reference's golden hits (tests/test_oracle_cpu.py). The claim under test: every answer the search does not
+flag equals the reference-order answer bit for bit, flags are rare, and misses agree."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle import port
+
+CASES = [c for c in golden_cases() if c != "ior_test_nobvh_64" and not c.startswith("pm_")]
+
+
+@pytest.mark.parametrize("max_leaf", [0xFFFFFFFF, 0])
+@pytest.mark.parametrize("cid", CASES)
+def test_unflagged_answers_equal_reference_order(cid, max_leaf, mcrt):
+    scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, cid + ".mcrtpack"))
+    g = np.load(os.path.join(GOLDEN, cid + ".npz"))
+    ps = port.PortScene(scene)
+    try:
+        nodes = mcrt.bvh4_host(scene, max_leaf)
+        scale = float(np.float32(np.abs(scene.a["node_bounds"][:6]).max()))      # ctx->scene_scale (float) as mcrt_scene_upload computes it
+        rng = np.random.default_rng(3)
+        base = g["tr_rays"]
+        ref0 = ps.trace(base)
+        ok = ref0["prim"] != mcrt.NO_PRIM
+        pts = base[ok, :3] + base[ok, 3:] * ref0["t"][ok, None]
+        n = 20000
+        a = pts[rng.integers(0, len(pts), n)]
+        b = pts[rng.integers(0, len(pts), n)] + rng.normal(0, 1e-3, (n, 3))
+        d = b - a
+        nrm = np.linalg.norm(d, axis=1, keepdims=True)
+        keep = nrm[:, 0] > 1e-9
+        seg = np.concatenate([a[keep], d[keep] / nrm[keep]], axis=1)              # start exactly on surfaces, aim at surfaces
+        d2 = rng.normal(size=(n, 3)); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+        leave = np.concatenate([a + 1e-9 * d2, d2], axis=1)                        # leave surfaces in random directions
+        axis = np.zeros((600, 6)); axis[:, :3] = pts[rng.integers(0, len(pts), 600)] + rng.normal(0, 0.3, (600, 3))
+        axis[np.arange(600), 3 + np.arange(600) % 3] = np.where(np.arange(600) % 2, 1.0, -1.0)   # axis-parallel rays: 1/d = inf in the reference
+        rays = np.concatenate([base, seg, leave, axis], axis=0)
+        ref = ps.trace(rays)
+        fast, flagged, box, prim = ps.trace_fast(nodes, scale, rays)
+        final = ~flagged
+        for f in ("prim", "t", "u", "v", "interpolate"):
+            assert np.array_equal(fast[f][final], ref[f][final]), (cid, f, int((fast[f][final] != ref[f][final]).sum()))
+        assert flagged.mean() < 0.02, flagged.mean()
+        assert not flagged[ref["prim"] == mcrt.NO_PRIM].any()                      # a miss is never ambiguous
+        assert box > 0 and prim > 0
+    finally:
+        ps.close()
+
+
+def test_coincident_geometry_is_flagged(mcrt):
+    """Two copies of the same triangle: equal t, the winner depends on the visiting order - the search must hand such rays to the replay."""
+    scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, "c2_hexagon_room_96.mcrtpack"))
+    a = dict(scene.a); a.update(scene.extra); a["scene_ior"] = scene.ior
+    tri = int(np.nonzero(a["prim_type"] == 0)[0][0])           # an ordered primitive that is a triangle
+    idx = int(a["prim_index"][tri])
+    # overwrite another triangle's geometry with this one's (same node layout, boxes of the tree still contain... only if equal): use the
+    # neighbour in the same leaf when there is one, else skip
+    leaf = next((i for i in range(len(a["node_first_prim"])) if a["node_prim_count"][i] >= 2 and
+                 all(a["prim_type"][a["node_first_prim"][i] + k] == 0 for k in range(2))), None)
+    if leaf is None:
+        pytest.skip("no leaf with two triangles in the fixture")
+    p0, p1 = int(a["node_first_prim"][leaf]), int(a["node_first_prim"][leaf]) + 1
+    i0, i1 = int(a["prim_index"][p0]), int(a["prim_index"][p1])
+    for k in ("tri_v0", "tri_v1", "tri_v2", "tri_e1", "tri_e2", "tri_normal"):
+        arr = a[k].reshape(-1, 3).copy(); arr[i1] = arr[i0]; a[k] = arr.reshape(-1)
+    dup = mcrt.Scene(a)
+    ps = port.PortScene(dup)
+    try:
+        nodes = mcrt.bvh4_host(dup, 0)
+        v0 = dup.a["tri_v0"].reshape(-1, 3)[i0]; e1 = dup.a["tri_e1"].reshape(-1, 3)[i0]; e2 = dup.a["tri_e2"].reshape(-1, 3)[i0]
+        target = v0 + 0.3 * e1 + 0.3 * e2
+        nrm = np.cross(e1, e2); nrm /= np.linalg.norm(nrm)
+        rays = np.array([np.concatenate([target + 0.5 * nrm, -nrm]), np.concatenate([target - 0.5 * nrm, nrm])])
+        ref = ps.trace(rays)
+        fast, flagged, _, _ = ps.trace_fast(nodes, float(np.float32(np.abs(dup.a["node_bounds"][:6]).max())), rays)
+        hit_dup = np.isin(ref["prim"], (p0, p1))
+        assert hit_dup.any()
+        assert flagged[hit_dup].all()            # ties go to the replay, whichever copy the search saw first
+    finally:
+        ps.close()
+
+
+@pytest.mark.parametrize("cid", ["v3_spaceship", "v5_lego_bulldozer"])
+def test_big_scene_unflagged_answers_equal_reference_order(cid, mcrt):
+    """The same claim on the 457 k-triangle spaceship and the 2 M-triangle bulldozer (coincident faces in the model: ~1 % of rays that
+    start on its surfaces are flagged); profiles/r2_fast_search_cpu_check.txt is this check with 2 M rays per scene."""
+    from conftest import ROOT
+    pack = os.path.join(ROOT, "bench_data", cid + ".mcrtpack.xz")
+    if not os.path.exists(pack):
+        pytest.skip(f"{pack} not present (git-ignored, regenerable: tools/validate_big.py make)")
+    scene = mcrt.Scene.from_pack(pack)
+    g = np.load(os.path.join(GOLDEN, "big", cid + ".npz"))
+    ps = port.PortScene(scene)
+    try:
+        nodes = mcrt.bvh4_host(scene)
+        scale = float(np.float32(np.abs(scene.a["node_bounds"][:6]).max()))
+        rng = np.random.default_rng(8)
+        base = g["tr_rays"]
+        ref0 = ps.trace(base)
+        assert np.array_equal(ref0["prim"], g["tr_prim"])            # the reference-order restatement against the reference itself
+        ok = ref0["prim"] != mcrt.NO_PRIM
+        pts = base[ok, :3] + base[ok, 3:] * ref0["t"][ok, None]
+        n = 60000
+        a = pts[rng.integers(0, len(pts), n)]
+        d2 = rng.normal(size=(n, 3)); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+        rays = np.concatenate([base, np.concatenate([a + 1e-9 * d2, d2], axis=1)], axis=0)
+        ref = ps.trace(rays)
+        fast, flagged, _, _ = ps.trace_fast(nodes, scale, rays)
+        final = ~flagged
+        for f in ("prim", "t", "u", "v"):
+            assert np.array_equal(fast[f][final], ref[f][final]), f
+        assert flagged.mean() < 0.03
+    finally:
+        ps.close()
