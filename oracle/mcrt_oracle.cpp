@@ -795,6 +795,71 @@ namespace
     }
 }
 
+// FastSearch<PRIMS, true> (csrc/bvh4.cuh): occlusion query of next-event estimation. verdict 0: the target is the closest hit (t in *t),
+// 1: something lies in front of it (or the ray misses the target itself), 2: a tie within delta -> the product replays the ray.
+namespace
+{
+    int searchVisible(const Scene& s, const Node4* nodes, const Ray& r, double scene_scale, uint32_t target, double& t_target)
+    {
+        Isect tgt;
+        if (!hitPrim(s, target, r, tgt)) return 1;
+        t_target = tgt.t;
+        auto inv = [](double v) { float f = (float)v; if (!(std::fabs(f) >= 1e-18f)) f = std::copysign(1e-18f, f); return 1.0f / f; };
+        const float id[3] = { inv(r.direction.x), inv(r.direction.y), inv(r.direction.z) };
+        const float od[3] = { (float)r.start.x * id[0], (float)r.start.y * id[1], (float)r.start.z * id[2] };
+        float on[3], of[3];
+        for (int k = 0; k < 3; k++) { const float m = std::fabs(od[k]) * 1.9073486e-6f; on[k] = od[k] + m; of[k] = od[k] - m; }
+        const double delta = ambiguityDelta(tgt.t, scene_scale);
+        const float limit = roundUpToFloat(tgt.t + 2.0 * delta);
+        std::vector<uint32_t> stack(1, 0u);
+        while (!stack.empty())
+        {
+            const uint32_t cur = stack.back(); stack.pop_back();
+            if (cur & 0x80000000u)
+            {
+                const uint32_t first = (cur >> 8) & 0x7FFFFFu, count = cur & 0xFFu;
+                for (uint32_t i = first; i < first + count; i++)
+                {
+                    if (i == target) continue;
+                    Isect c;
+                    if (hitPrim(s, i, r, c))
+                    {
+                        if (c.t < tgt.t - delta) return 1;
+                        if (c.t <= tgt.t + delta) return 2;
+                    }
+                }
+                continue;
+            }
+            const Node4& n = nodes[cur];
+            for (int c = 0; c < 4; c++)
+            {
+                float tn = 0.0f, tf = INFINITY;
+                for (int k = 0; k < 3; k++)
+                {
+                    const float bn = id[k] < 0.0f ? n.hi[k][c] : n.lo[k][c], bf = id[k] < 0.0f ? n.lo[k][c] : n.hi[k][c];
+                    tn = std::fmax(tn, std::fmaf(bn, id[k], -on[k]));
+                    tf = std::fmin(tf, std::fmaf(bf, id[k], -of[k]));
+                }
+                tn *= 0.99999619f; tf *= 1.00000381f;
+                if (n.child[c] != 0u && tn <= tf && tn <= limit) stack.push_back(n.child[c]);   // the verdict does not depend on the visiting order
+            }
+        }
+        return 0;
+    }
+}
+
+void oracle_trace_visible(void* h, const void* nodes128, double scene_scale, const mcrt_ray* rays, const uint32_t* target, size_t n,
+                          uint8_t* verdict, double* t_target)
+{
+    const Scene& s = *static_cast<Scene*>(h);
+    for (size_t i = 0; i < n; i++)
+    {
+        double t = 0.0;
+        verdict[i] = (uint8_t)searchVisible(s, static_cast<const Node4*>(nodes128), makeRay(D3(rays[i].origin), D3(rays[i].direction), s.d.scene_ior), scene_scale, target[i], t);
+        t_target[i] = t;
+    }
+}
+
 void oracle_trace_fast(void* h, const void* nodes128, uint32_t n_nodes, double scene_scale, const mcrt_ray* rays, size_t n, mcrt_hit* hits,
                        uint8_t* flags, uint64_t* box_tests, uint64_t* prim_tests)
 {

@@ -30,6 +30,7 @@ def lib():
         L.oracle_sample_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_trace_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.oracle_trace_visible.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.oracle_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
         L.oracle_bvh_free.argtypes = [C.c_void_p]
         L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -142,6 +143,15 @@ class PortScene:
         bt, pt = C.c_uint64(), C.c_uint64()
         lib().oracle_trace_fast(self.h, _p(nodes), len(nodes), float(scene_scale), _p(rays), len(rays), _p(hits), _p(flags), C.byref(bt), C.byref(pt))
         return hits, flags.astype(bool), bt.value, pt.value
+
+    def trace_visible(self, nodes, scene_scale, rays, target):
+        """The product's occlusion query restated on the CPU. -> (verdict 0 visible / 1 not / 2 tie-to-replay, t of the target)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        target = np.ascontiguousarray(target, dtype=np.uint32)
+        nodes = np.ascontiguousarray(nodes)
+        verdict = np.zeros(len(rays), dtype=np.uint8); t = np.zeros(len(rays))
+        lib().oracle_trace_visible(self.h, _p(nodes), float(scene_scale), _p(rays), _p(target), len(rays), _p(verdict), _p(t))
+        return verdict, t
 
     def sample_pixels(self, camera, pixel, sample, seed):
         """-> (rgb [n,3], camera rays [n,6]) for (pixel, sample) pairs"""

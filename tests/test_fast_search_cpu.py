@@ -118,3 +118,49 @@ def test_big_scene_unflagged_answers_equal_reference_order(cid, mcrt):
         assert flagged.mean() < 0.03
     finally:
         ps.close()
+
+
+@pytest.mark.parametrize("cid", ["c1_hexagon_diffuse_256", "c2_hexagon_room_96", "veach_mis_64", "smooth_mesh_64"])
+def test_occlusion_query_equals_closest_hit_comparison(cid, mcrt):
+    """Shadow rays (integrator.cpp:68-86: visible iff the closest hit is that very light primitive): the product tests the light
+    directly and searches only for something in front of it. Restated on the CPU: verdict 'visible' <=> the reference-order closest
+    hit is the light, with the same t; 'not visible' <=> it is something else; ties are handed to the replay."""
+    scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, cid + ".mcrtpack"))
+    g = np.load(os.path.join(GOLDEN, cid + ".npz"))
+    ps = port.PortScene(scene)
+    try:
+        nodes = mcrt.bvh4_host(scene)
+        scale = float(np.float32(np.abs(scene.a["node_bounds"][:6]).max()))
+        rng = np.random.default_rng(21)
+        base = g["tr_rays"]
+        ref0 = ps.trace(base)
+        ok = ref0["prim"] != mcrt.NO_PRIM
+        pts = base[ok, :3] + base[ok, 3:] * ref0["t"][ok, None]
+        lights = scene.a["light_prim"]
+        assert len(lights) > 0
+        n = 30000
+        tgt = lights[rng.integers(0, len(lights), n)].astype(np.uint32)
+        # a point on each target light: triangle lights by barycentric sampling, sphere lights through their centre
+        a = scene.a
+        lp = np.zeros((n, 3))
+        for j in range(n):
+            t, idx = int(a["prim_type"][tgt[j]]), int(a["prim_index"][tgt[j]])
+            if t == 0:
+                u, v = rng.uniform(0, 1, 2); su = np.sqrt(u)
+                lp[j] = ((1 - su) * a["tri_v0"].reshape(-1, 3)[idx] + (1 - v) * su * a["tri_v1"].reshape(-1, 3)[idx] + v * su * a["tri_v2"].reshape(-1, 3)[idx])
+            else:
+                lp[j] = a["sphere_origin_radius"].reshape(-1, 4)[idx][:3]
+        o = pts[rng.integers(0, len(pts), n)]
+        d = lp - o
+        nrm = np.linalg.norm(d, axis=1, keepdims=True)
+        keep = nrm[:, 0] > 1e-9
+        rays = np.concatenate([o[keep], d[keep] / nrm[keep]], axis=1)
+        tgt = tgt[keep]
+        ref = ps.trace(rays)
+        verdict, t = ps.trace_visible(nodes, scale, rays, tgt)
+        vis, occ = verdict == 0, verdict == 1
+        assert np.array_equal(ref["prim"][vis], tgt[vis]) and np.array_equal(ref["t"][vis], t[vis])
+        assert (ref["prim"][occ] != tgt[occ]).all()
+        assert vis.sum() > 100 and occ.sum() > 100 and (verdict == 2).mean() < 0.02
+    finally:
+        ps.close()
