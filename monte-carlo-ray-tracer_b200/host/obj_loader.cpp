@@ -213,47 +213,59 @@ bool generateVertexNormals(const std::vector<double>& vertices, const std::vecto
 {
     const size_t nv = vertices.size() / 3, nt = tri_v.size() / 3;
     for (uint64_t i : tri_v) if (i >= nv) return false;
-    // incidence lists in triangle order (counting sort by vertex): corner c of triangle t -> slot
-    std::vector<uint64_t> start(nv + 1, 0);
+    if (tri_v.size() > 0xFFFFFFFFull) return false;   // corner indices are kept in 32 bits
+    int n = threadCount(threads);
+    if (nv < 4096) n = 1;
+    auto parallel = [&](size_t count, auto&& body)
+    {
+        std::vector<std::thread> pool;
+        for (int i = 1; i < n; i++) pool.emplace_back([&, i] { body(count * i / n, count * (i + 1) / n); });
+        body(0, count / n);
+        for (auto& t : pool) t.join();
+    };
+    // Phase 1, per triangle (once, not once per corner): the three angle-weighted area normals the reference adds to the
+    // triangle's vertices (scene.cpp:330-347), in its expressions.
+    const D3* V = reinterpret_cast<const D3*>(vertices.data());
+    std::vector<D3> contribution(tri_v.size());
+    parallel(nt, [&](size_t t0, size_t t1)
+    {
+        for (size_t t = t0; t < t1; t++)
+        {
+            const D3 a = V[tri_v[3 * t]], b = V[tri_v[3 * t + 1]], c = V[tri_v[3 * t + 2]];
+            // Surface::Triangle(v0, v1, v2): E1, E2, normal_ = normalize(cross(E1, E2)), area_ = |cross| / 2
+            const D3 e1 = sub(b, a), e2 = sub(c, a), cr = cross(e1, e2);
+            const D3 weighted = mul(normalize(cr), std::sqrt(dot(cr, cr)) / 2.0);
+            contribution[3 * t] = mul(weighted, angleBetween(sub(a, b), sub(a, c)));
+            contribution[3 * t + 1] = mul(weighted, angleBetween(sub(b, a), sub(b, c)));
+            contribution[3 * t + 2] = mul(weighted, angleBetween(sub(c, a), sub(c, b)));
+        }
+    });
+    // incidence lists in triangle order (counting sort by vertex): corner c of triangle t -> slot; the reference accumulates
+    // triangle by triangle, so every vertex sums its corners in ascending triangle order
+    std::vector<uint32_t> start(nv + 1, 0);
     for (uint64_t i : tri_v) start[i + 1]++;
     for (size_t v = 0; v < nv; v++) start[v + 1] += start[v];
-    std::vector<uint64_t> incident(tri_v.size());
+    std::vector<uint32_t> incident(tri_v.size());
     {
-        std::vector<uint64_t> cursor(start.begin(), start.end() - 1);
-        for (size_t k = 0; k < tri_v.size(); k++) incident[cursor[tri_v[k]]++] = k;   // k = 3 * triangle + corner, ascending
+        std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
+        for (size_t k = 0; k < tri_v.size(); k++) incident[cursor[tri_v[k]]++] = (uint32_t)k;   // k = 3 * triangle + corner, ascending
     }
     normals.assign(3 * nv, 0.0);
-    const D3* V = reinterpret_cast<const D3*>(vertices.data());
-    auto work = [&](size_t v0, size_t v1)
+    // Phase 2, per vertex: sum and normalise
+    parallel(nv, [&](size_t v0, size_t v1)
     {
         for (size_t v = v0; v < v1; v++)
         {
             D3 sum{0.0, 0.0, 0.0};
-            for (uint64_t s = start[v]; s < start[v + 1]; s++)
+            for (uint32_t s = start[v]; s < start[v + 1]; s++)
             {
-                const uint64_t k = incident[s], t = k / 3, corner = k % 3;
-                const D3 a = V[tri_v[3 * t]], b = V[tri_v[3 * t + 1]], c = V[tri_v[3 * t + 2]];
-                // Surface::Triangle(v0, v1, v2): E1, E2, normal_ = normalize(cross(E1, E2)), area_ = |cross| / 2
-                const D3 e1 = sub(b, a), e2 = sub(c, a), cr = cross(e1, e2);
-                const D3 weighted = mul(normalize(cr), std::sqrt(dot(cr, cr)) / 2.0);
-                double angle;
-                if (corner == 0) angle = angleBetween(sub(a, b), sub(a, c));
-                else if (corner == 1) angle = angleBetween(sub(b, a), sub(b, c));
-                else angle = angleBetween(sub(c, a), sub(c, b));
-                const D3 add = mul(weighted, angle);
+                const D3& add = contribution[incident[s]];
                 sum.x += add.x; sum.y += add.y; sum.z += add.z;
             }
-            const D3 n = normalize(sum);
-            normals[3 * v] = n.x; normals[3 * v + 1] = n.y; normals[3 * v + 2] = n.z;
+            const D3 nrm = normalize(sum);
+            normals[3 * v] = nrm.x; normals[3 * v + 1] = nrm.y; normals[3 * v + 2] = nrm.z;
         }
-    };
-    int n = threadCount(threads);
-    if (nv < 4096) n = 1;
-    std::vector<std::thread> pool;
-    for (int i = 1; i < n; i++) pool.emplace_back(work, nv * i / n, nv * (i + 1) / n);
-    work(0, nv / n);
-    for (auto& t : pool) t.join();
-    (void)nt;
+    });
     return true;
 }
 }
