@@ -93,11 +93,12 @@ namespace mcrt
 
     // One ordered primitive against the ray with the reference's float64 arithmetic (no acceptance rule)
     template <int PRIMS, class R>
-    MCRT_D bool intersectPrim(const DeviceScene<R>& sc, uint32_t prim, const RayQ<R>& ray, R& t, R& u, R& v)
+    MCRT_D bool intersectPrim(const DeviceScene<R>& sc, uint32_t prim, const RayQ<R>& ray, R& t, R& u, R& v, bool& is_triangle)
     {
         const V4<R> g0 = sc.geom[3 * prim + 0];
         const uint32_t type = PRIMS == PRIMS_TRI ? (uint32_t)PRIM_TRIANGLE : (uint32_t)g0.w;
         u = R(0); v = R(0);
+        is_triangle = type == PRIM_TRIANGLE;
         if (type == PRIM_TRIANGLE)
         {
             const V4<R> g1 = sc.geom[3 * prim + 1];
@@ -117,6 +118,23 @@ namespace mcrt
 
     // distance below which two hits count as competing (see the header)
     MCRT_D double ambiguityDelta(double t, double scene_scale) { return 1e-6 * t + 1e-12 * scene_scale; }
+
+    // Degenerate rays. Where a ray runs exactly along a box plane, through a vertex or along an edge, the reference's float64 slab test
+    // decides by rounding - or by NaN: 0 * inf for a zero direction component - whether a box, and with it a primitive the ray does
+    // touch, is reached at all; the conservative float boxes of the search never miss such a primitive, so there the two can differ
+    // although no second candidate is near. Such rays are handed to the replay as well: a direction component of (nearly) zero, or a
+    // triangle hit within 1e-9 (scaled with distance) of the triangle's boundary. Measure-zero for rays a renderer generates, but
+    // mcrt_trace_closest takes the caller's rays. tests/test_fast_search_cpu.py::test_degenerate_rays_* (CPU restatement, 1.25 M
+    // adversarial rays: no unflagged answer differs from the reference-order answer).
+    MCRT_D bool degenerateDirection(const V3<double>& d)
+    {
+        return fabs(d.x) < 1e-12 || fabs(d.y) < 1e-12 || fabs(d.z) < 1e-12;
+    }
+    MCRT_D bool onTriangleBoundary(double u, double v, double t, double scene_scale)
+    {
+        const double e = 1e-9 * fmax(1.0, t / scene_scale);
+        return u < e || v < e || u + v > 1.0 - e;
+    }
 
     // The search as a resumable state: begin(), then step() until it returns false. One step = walk down
     // through inner nodes to the next leaf, test its primitives, pop the next pending subtree.
@@ -138,6 +156,7 @@ namespace mcrt
         uint2* sstack;         // this thread's column of the shared-memory part of the stack
         uint32_t target;       // OCC: the primitive whose visibility is asked
         uint32_t verdict;      // OCC: 0 target visible so far, 1 occluded, 2 tie -> replay
+        bool degenerate;       // the ray or its winning hit is degenerate (see degenerateDirection / onTriangleBoundary): replay
 
         // -> false: the ray does not hit the target at all (nothing to search)
         MCRT_D bool beginOcclusion(const DeviceScene<double>& sc, const RayQ<double>& ray, uint32_t target_prim, TraceCounters& cnt)
@@ -148,9 +167,12 @@ namespace mcrt
             sp = 0; cur = 0;
             attach();
             double t, u, v;
+            bool is_tri;
             cnt.prim_tests++;
-            if (!intersectPrim<PRIMS>(sc, target_prim, ray, t, u, v)) return false;
+            if (!intersectPrim<PRIMS>(sc, target_prim, ray, t, u, v, is_tri)) return false;
             best.t = t; best.u = u; best.v = v; best.prim = target_prim;
+            degenerate = degenerateDirection(ray.d) || (is_tri && onTriangleBoundary(u, v, t, (double)sc.scene_scale));
+            if (degenerate) { verdict = 2u; return true; }     // step() is not entered: see traceManyFast / traceVisible
             limit = __double2float_ru(t + 2.0 * ambiguityDelta(t, (double)sc.scene_scale));
             fr = makeFastRay(ray.o, ray.d);
             return true;
@@ -163,6 +185,7 @@ namespace mcrt
             limit = __int_as_float(0x7f800000);   // +inf until something is hit
             sp = 0;
             cur = 0;                              // node 0 = root
+            degenerate = degenerateDirection(ray.d);
             attach();
             fr = makeFastRay(ray.o, ray.d);
         }
@@ -241,23 +264,27 @@ namespace mcrt
             for (uint32_t i = first; i < first + count; i++)
             {
                 double t, u, v;
+                bool is_tri;
                 if constexpr (OCC)
                 {
                     if (i == target) continue;
-                    if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
+                    if (intersectPrim<PRIMS>(sc, i, ray, t, u, v, is_tri))
                     {
                         const double delta = ambiguityDelta(best.t, (double)sc.scene_scale);
+                        // an occluder hit on its own boundary may be one the reference never reaches: replay
+                        if (t <= best.t + delta && is_tri && onTriangleBoundary(u, v, t, (double)sc.scene_scale)) { verdict = 2u; cnt.prim_tests += i - first + 1; return false; }
                         if (t < best.t - delta) { verdict = 1u; cnt.prim_tests += i - first + 1; return false; }   // occluder: done
                         if (t <= best.t + delta) { verdict = 2u; cnt.prim_tests += i - first + 1; return false; }  // tie: replay
                     }
                     continue;
                 }
-                if (intersectPrim<PRIMS>(sc, i, ray, t, u, v))
+                if (intersectPrim<PRIMS>(sc, i, ray, t, u, v, is_tri))
                 {
                     if (t < best.t)
                     {
                         second_t = best.t;
                         best.t = t; best.u = u; best.v = v; best.prim = i;
+                        best.interpolate = (is_tri && onTriangleBoundary(u, v, t, (double)sc.scene_scale)) ? 1u : 0u;   // scratch use: winner on its boundary
                         limit = __double2float_ru(t + 2.0 * ambiguityDelta(t, (double)sc.scene_scale));
                     }
                     else if (t < second_t)
@@ -309,7 +336,8 @@ namespace mcrt
         // another hit within delta of the closest: the answer may depend on the visiting order
         MCRT_D bool ambiguous(const DeviceScene<double>& sc) const
         {
-            return best.prim != NO_PRIM && second_t <= best.t + ambiguityDelta(best.t, (double)sc.scene_scale);
+            if (degenerate) return true;
+            return best.prim != NO_PRIM && (best.interpolate != 0u || second_t <= best.t + ambiguityDelta(best.t, (double)sc.scene_scale));
         }
     };
 
@@ -377,7 +405,7 @@ namespace mcrt
                         {
                             uint32_t target;
                             item = load(ii, ray, target);
-                            if (fs.beginOcclusion(sc, ray, target, cnt)) active = true;
+                            if (fs.beginOcclusion(sc, ray, target, cnt)) { active = true; if (fs.verdict == 2u) fs.sp = 0, fs.cur = BVH4_LEAF; }   // degenerate: an empty leaf ends the search at once
                             else { Hit<double> miss = fs.best; miss.prim = NO_PRIM; done(item, ray, miss); }   // the ray misses the light itself
                         }
                         else

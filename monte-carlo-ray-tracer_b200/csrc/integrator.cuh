@@ -299,7 +299,7 @@ namespace mcrt
         if constexpr (PRIMS == PRIMS_ALL) rq.inv_d = 1.0 / d;
         FastSearch<PRIMS, true> fs;
         if (!fs.beginOcclusion(sc, rq, target, cnt)) { Hit<double> miss = fs.best; miss.prim = NO_PRIM; return miss; }
-        while (fs.step(sc, rq, cnt, overflow)) { }
+        if (fs.verdict != 2u) { while (fs.step(sc, rq, cnt, overflow)) { } }     // 2 already: a degenerate ray goes straight to the replay
         Hit<double> h = fs.best;
         if (fs.verdict == 1u) h.prim = NO_PRIM;
         else if (fs.verdict == 2u)

@@ -734,6 +734,29 @@ namespace
 
     float roundUpToFloat(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }   // __double2float_ru
 
+    // barycentrics of a triangle hit whatever the triangle's shading mode (hitPrim reports them for smooth triangles only)
+    bool hitPrimUV(const Scene& s, uint32_t prim, const Ray& r, Isect& out, double& u, double& v)
+    {
+        if (!hitPrim(s, prim, r, out)) return false;
+        if (s.prim_type[prim] == MCRT_PRIM_TRIANGLE)
+        {
+            const uint32_t idx = s.prim_index[prim];
+            D3 v0(&s.tri_v0[3 * idx]), E1(&s.tri_e1[3 * idx]), E2(&s.tri_e2[3 * idx]);
+            D3 P = cross(r.direction, E2);
+            double inv = 1.0 / dot(P, E1);
+            D3 T = r.start - v0;
+            u = dot(P, T) * inv;
+            v = dot(cross(T, E1), r.direction) * inv;
+        }
+        return true;
+    }
+    bool onBoundary(double u, double v, double t, double scale) { const double e = 1e-9 * std::fmax(1.0, t / scale); return u < e || v < e || u + v > 1.0 - e; }
+    bool degenerateDirection(const Ray& r)
+    {
+        const double e = 1e-12;
+        return std::fabs(r.direction.x) < e || std::fabs(r.direction.y) < e || std::fabs(r.direction.z) < e;
+    }
+
     Isect searchFast(const Scene& s, const Node4* nodes, const Ray& r, double scene_scale, bool& ambiguous, uint64_t& box_tests, uint64_t& prim_tests)
     {
         auto inv = [](double v) { float f = (float)v; if (!(std::fabs(f) >= 1e-18f)) f = std::copysign(1e-18f, f); return 1.0f / f; };
@@ -742,6 +765,7 @@ namespace
         float on[3], of[3];
         for (int k = 0; k < 3; k++) { const float m = std::fabs(od[k]) * 1.9073486e-6f; on[k] = od[k] + m; of[k] = od[k] - m; }
         Isect best;
+        bool best_edge = false;
         double second_t = std::numeric_limits<double>::max();
         float limit = INFINITY;
         struct Entry { uint32_t ref; float tn; };
@@ -782,15 +806,18 @@ namespace
             {
                 Isect c;
                 prim_tests++;
-                if (hitPrim(s, i, r, c))
+                double eu = 0.5, ev = 0.25;
+                if (hitPrimUV(s, i, r, c, eu, ev))
                 {
-                    if (c.t < best.t) { second_t = best.t; best = c; best.prim = i; limit = roundUpToFloat(c.t + 2.0 * ambiguityDelta(c.t, scene_scale)); }
+                    if (c.t < best.t) { second_t = best.t; best = c; best.prim = i; best_edge = onBoundary(eu, ev, c.t, scene_scale); limit = roundUpToFloat(c.t + 2.0 * ambiguityDelta(c.t, scene_scale)); }
                     else if (c.t < second_t) second_t = c.t;
                 }
             }
             if (!pop()) break;
         }
         ambiguous = best.prim != 0xFFFFFFFFu && second_t <= best.t + ambiguityDelta(best.t, scene_scale);
+        if (best.prim != 0xFFFFFFFFu && best_edge) ambiguous = true;      // R2: the winner is hit on its boundary
+        if (degenerateDirection(r)) ambiguous = true;                     // R1: a direction component is (nearly) zero
         return best;
     }
 }
@@ -802,8 +829,10 @@ namespace
     int searchVisible(const Scene& s, const Node4* nodes, const Ray& r, double scene_scale, uint32_t target, double& t_target)
     {
         Isect tgt;
-        if (!hitPrim(s, target, r, tgt)) return 1;
+        double tu = 0.5, tv = 0.25;
+        if (!hitPrimUV(s, target, r, tgt, tu, tv)) return 1;
         t_target = tgt.t;
+        if (degenerateDirection(r) || onBoundary(tu, tv, tgt.t, scene_scale)) return 2;
         auto inv = [](double v) { float f = (float)v; if (!(std::fabs(f) >= 1e-18f)) f = std::copysign(1e-18f, f); return 1.0f / f; };
         const float id[3] = { inv(r.direction.x), inv(r.direction.y), inv(r.direction.z) };
         const float od[3] = { (float)r.start.x * id[0], (float)r.start.y * id[1], (float)r.start.z * id[2] };
@@ -822,8 +851,10 @@ namespace
                 {
                     if (i == target) continue;
                     Isect c;
-                    if (hitPrim(s, i, r, c))
+                    double cu = 0.5, cv = 0.25;
+                    if (hitPrimUV(s, i, r, c, cu, cv))
                     {
+                        if (c.t <= tgt.t + delta && onBoundary(cu, cv, c.t, scene_scale)) return 2;   // an occluder hit on its edge: the reference may have missed it
                         if (c.t < tgt.t - delta) return 1;
                         if (c.t <= tgt.t + delta) return 2;
                     }
