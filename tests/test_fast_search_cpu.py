@@ -228,3 +228,46 @@ def test_degenerate_rays_are_flagged_not_answered_differently(cid, mcrt):
             assert final.sum() > 10000          # the generic members of the families are still answered by the search
     finally:
         ps.close()
+
+
+@pytest.mark.parametrize("cid", ["c2_hexagon_room_96", "quadric_64", "metals_64"])
+def test_curved_primitives_and_near_degenerate_directions(cid, mcrt):
+    """Sphere tangents (impact parameter r (1 +- 0, 1e-12, 1e-7)), rays through / from sphere centres and surfaces, rays from exact hit
+    points with zero offset, direction components of 2e-12 .. 1e-9 (just above the replay rule), near-tangent leaving rays: every answer the
+    search does not flag equals the reference-order answer."""
+    scene = mcrt.Scene.from_pack(os.path.join(GOLDEN, cid + ".mcrtpack"))
+    g = np.load(os.path.join(GOLDEN, cid + ".npz"))
+    a = scene.a
+    ps = port.PortScene(scene)
+    try:
+        rng = np.random.default_rng(9)
+        n = 6000
+        base = g["tr_rays"]
+        ref0 = ps.trace(base)
+        ok = ref0["prim"] != mcrt.NO_PRIM
+        pts = base[ok, :3] + base[ok, 3:] * ref0["t"][ok, None]
+        fam = []
+        sph = a["sphere_origin_radius"].reshape(-1, 4)
+        if len(sph):
+            i = rng.integers(0, len(sph), n); c, r = sph[i, :3], sph[i, 3:4]
+            dirn = _unit(rng.normal(size=(n, 3)))
+            perp = _unit(np.cross(dirn, rng.normal(size=(n, 3))))
+            for eps in (0.0, 1e-12, -1e-12, 1e-7, -1e-7):
+                fam.append(np.concatenate([c + perp * r * (1 + eps) - dirn * 5.0, dirn], 1))
+            fam.append(np.concatenate([c - dirn * 3.0, dirn], 1))
+            fam.append(np.concatenate([c + dirn * r, _unit(rng.normal(size=(n, 3)))], 1))
+            fam.append(np.concatenate([c, dirn], 1))
+        d = _unit(rng.normal(size=(n, 3))); k = rng.integers(0, 3, n)
+        d[np.arange(n), k] = rng.choice([1e-9, 2e-12, 1e-11, -3e-12, 1e-10], n)
+        fam.append(np.concatenate([pts[rng.integers(0, len(pts), n)] + rng.normal(0, 1e-3, (n, 3)), _unit(d)], 1))
+        fam.append(np.concatenate([pts[rng.integers(0, len(pts), n)], _unit(rng.normal(size=(n, 3)))], 1))
+        rays = np.concatenate(fam, 0)
+        ref = ps.trace(rays)
+        scale = float(np.float32(np.abs(a["node_bounds"][:6]).max()))
+        fast, flagged, _, _ = ps.trace_fast(mcrt.bvh4_host(scene), scale, rays)
+        final = ~flagged
+        for f_ in ("prim", "t", "u", "v"):
+            assert np.array_equal(fast[f_][final], ref[f_][final]), (cid, f_)
+        assert final.mean() > 0.9
+    finally:
+        ps.close()
