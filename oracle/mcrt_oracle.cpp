@@ -254,7 +254,20 @@ namespace
         void pop() { if (H.size() > 1) { NodeHit v = H.back(); H.pop_back(); shiftDown(v, 0); } else H.pop_back(); }
     };
 
+    // optional cross-check of every Scene::intersect call of a render against the order-free search (oracle_render_rows_checked)
+    struct SearchCheck { const void* nodes; double scale; uint64_t calls, flagged, mismatches; };
+    SearchCheck* g_search_check = nullptr;
+    Isect intersectReferenceOrder(const Scene& s, const Ray& r, uint64_t* counter);
+    void (*g_cross_fn)(const Scene& s, const Ray& r, const Isect& ref) = nullptr;
+
     Isect intersect(const Scene& s, const Ray& r, uint64_t* counter)
+    {
+        Isect is = intersectReferenceOrder(s, r, counter);
+        if (g_search_check && g_cross_fn) g_cross_fn(s, r, is);
+        return is;
+    }
+
+    Isect intersectReferenceOrder(const Scene& s, const Ray& r, uint64_t* counter)
     {
         if (counter) (*counter)++;
         Isect best;
@@ -889,6 +902,35 @@ void oracle_trace_visible(void* h, const void* nodes128, double scene_scale, con
         verdict[i] = (uint8_t)searchVisible(s, static_cast<const Node4*>(nodes128), makeRay(D3(rays[i].origin), D3(rays[i].direction), s.d.scene_ior), scene_scale, target[i], t);
         t_target[i] = t;
     }
+}
+
+namespace
+{
+    void crossCheckImpl(const Scene& s, const Ray& r, const Isect& ref)
+    {
+        SearchCheck& c = *g_search_check;
+        bool amb = false; uint64_t bt = 0, pt = 0;
+        Isect f = searchFast(s, static_cast<const Node4*>(c.nodes), r, c.scale, amb, bt, pt);
+        c.calls++;
+        if (amb) { c.flagged++; return; }
+        if (f.prim != ref.prim || (ref.prim != 0xFFFFFFFFu && (f.t != ref.t || f.u != ref.u || f.v != ref.v))) c.mismatches++;
+    }
+}
+
+// A whole render (rows [y0, y1)) by the restated path tracer, with EVERY Scene::intersect call - camera, bounce and shadow rays - also
+// answered by the order-free search over `nodes128`: counts[0] calls, counts[1] flagged (would be replayed), counts[2] unflagged answers
+// that differ from the reference-order answer (must be 0).
+void oracle_render_rows(void* h, const mcrt_camera* cam, uint32_t y0, uint32_t y1, uint32_t sqrtspp, uint32_t seed, double* out, uint64_t* rays);
+void oracle_render_rows_checked(void* h, const void* nodes128, double scene_scale, const mcrt_camera* cam, uint32_t y0, uint32_t y1,
+                                uint32_t sqrtspp, uint32_t seed, double* out, uint64_t* counts)
+{
+    SearchCheck c{ nodes128, scene_scale, 0, 0, 0 };
+    g_search_check = &c;
+    g_cross_fn = crossCheckImpl;
+    uint64_t rays = 0;
+    oracle_render_rows(h, cam, y0, y1, sqrtspp, seed, out, &rays);
+    g_search_check = nullptr;
+    counts[0] = c.calls; counts[1] = c.flagged; counts[2] = c.mismatches;
 }
 
 void oracle_trace_fast(void* h, const void* nodes128, uint32_t n_nodes, double scene_scale, const mcrt_ray* rays, size_t n, mcrt_hit* hits,

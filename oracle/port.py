@@ -31,6 +31,8 @@ def lib():
         L.oracle_trace_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_trace_visible.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_render_rows_checked.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                 C.c_void_p, C.c_void_p]
         L.oracle_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
         L.oracle_bvh_free.argtypes = [C.c_void_p]
         L.oracle_octree_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -159,6 +161,14 @@ class PortScene:
         rgb = np.zeros((len(pixel), 3)); rays = np.zeros((len(pixel), 6))
         lib().oracle_sample_pixels(self.h, C.addressof(camera.rec), _p(pixel), _p(sample), len(pixel), seed, _p(rgb), _p(rays))
         return rgb, rays
+
+    def render_rows_checked(self, nodes, scene_scale, camera, y0, y1, sqrtspp, seed):
+        """render_rows with every Scene::intersect call cross-checked against the order-free search -> (image, calls, flagged, mismatches)"""
+        nodes = np.ascontiguousarray(nodes)
+        out = np.zeros((y1 - y0, camera.width, 3))
+        counts = np.zeros(3, dtype=np.uint64)
+        lib().oracle_render_rows_checked(self.h, _p(nodes), float(scene_scale), C.addressof(camera.rec), y0, y1, sqrtspp, seed, _p(out), _p(counts))
+        return out, int(counts[0]), int(counts[1]), int(counts[2])
 
     def render_rows(self, camera, y0, y1, sqrtspp, seed):
         out = np.zeros((y1 - y0, camera.width, 3))
